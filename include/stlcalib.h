@@ -1,0 +1,260 @@
+/*
+ * stlcalib.h — C-ABI of the B200-native calibration cost-evaluation path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: the
+ * three optimisers call plain C++ functions/functors.  Every entry point below
+ * names the reference interface it replaces (paths relative to the reference
+ * tree).  Plain pointers and sizes only; no C++/torch types cross this line;
+ * nothing throws across it (every call returns an stl_status_t).
+ *
+ *   reference call                                     → C-ABI entry
+ *   -------------------------------------------------------------------------
+ *   BALoss ctor: builds one KDTree3D per scan          → stl_create + stl_upload_pack
+ *     (src/examples/iba_global.cpp:349-367)
+ *   BAError(xvec, PointClouds, KdTrees, vTwl, ...)      → stl_eval_batch (B = 1)
+ *     (src/examples/iba_global.cpp:169-344,
+ *      src/examples/iba_func.cpp:179-354)
+ *   iba_func main loop over a Sim3 list                → stl_eval_batch (B = list size)
+ *     (src/examples/iba_func.cpp:458-470)
+ *   BALoss::eval_x / Nomad eval_block                  → stl_eval_batch + stl_bbo
+ *     (src/examples/iba_global.cpp:377-396)
+ *   BuildProblem (association at the current estimate) → stl_associate
+ *     (src/examples/iba_local.cpp:145-323)
+ *   ceres::Problem::Evaluate over IBA_PlaneFactor /    → stl_linearize_batch
+ *     Point2Point_Factor / Point2Plane_Factor + Huber
+ *     (include/IBACalib2.hpp:152-184,570-584,611-625;
+ *      src/examples/iba_local.cpp:263-309)
+ *   g2o IBAPlaneEdge computeError/linearizeOplus       → stl_linearize_batch
+ *     (include/IBACalib.hpp:74-155)
+ */
+#ifndef STLCALIB_H_
+#define STLCALIB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STL_ABI_VERSION 1
+#define STL_MAX_COVIS 10 /* IBAPlaneEdge is fixed at <=10 covisible KFs (IBACalib.hpp:74) */
+
+typedef enum stl_status {
+    STL_OK = 0,
+    STL_ERR_INVALID = 1,   /* bad argument / inconsistent pack            */
+    STL_ERR_CUDA = 2,      /* CUDA runtime error (see stl_last_error)     */
+    STL_ERR_NO_DEVICE = 3, /* no usable sm_100 device: there is NO CPU fallback */
+    STL_ERR_STATE = 4,     /* call order violated (e.g. eval before upload) */
+    STL_ERR_CAPACITY = 5   /* input exceeds a documented limit            */
+} stl_status_t;
+
+/*
+ * Hot-path parameters: IBAGlobalParams (iba_global.cpp:26-52) and the
+ * IBALocalParams members that BuildProblem reads (IBACalib2.hpp:104-137).
+ * Defaults set by stl_default_params() are the KITTI-00 YAML values
+ * (config/calib/00/iba_calib_global.yml:21-48).
+ */
+typedef struct stl_params {
+    double max_pixel_dist;        /* 1.5   2-D association gate (px)                 */
+    double corr_3d_2d_threshold;  /* 40    re-projection gate (px)                   */
+    double corr_3d_3d_threshold;  /* 10    3-D/3-D gate (m)                          */
+    double norm_radius;           /* 0.6   k-NN radius (m) (= neigh_radius)          */
+    double norm_reg_threshold;    /* 0.02  plane regression gate                     */
+    double min_diff_dist;         /* 0.2   min extent of the neighbourhood (m)       */
+    double err_weight[2];         /* {1,1}                                           */
+    double he_threshold;          /* 0.094 (host shim: BBO constraint)               */
+    double valid_rate;            /* 0.95  (host shim: BBO constraint)               */
+    double max_3d_dist;           /* 1.0   LM path: map-point NN gate (m)            */
+    double robust_kernel_delta;   /* 2.98  Huber delta of 3-D/2-D blocks             */
+    double robust_kernel_3ddelta; /* 1.0   Huber delta of 3-D/3-D blocks             */
+    int32_t num_min_corr;         /* 30    frame skipped below this (iba_global.cpp:203) */
+    int32_t norm_max_pts;         /* 30    k of the k-NN (<= 32)                     */
+    int32_t norm_min_pts;         /* 5                                               */
+    int32_t use_plane;            /* 1                                               */
+} stl_params_t;
+
+/*
+ * KeyFramePack — everything the hot path reads, flattened.
+ * All buffers are HOST memory owned by the caller; stl_upload_pack copies.
+ * Matrices are row-major 3x4 [R|t].  float32 members are the float32 values
+ * ORB-SLAM2 holds (KeyFrame.h:221,228; MapPoint.cc:84-87); scans are the
+ * float32 values of the KITTI .bin files (io_tools.h:170-187).
+ */
+typedef struct stl_pack {
+    int32_t n_kf;              /* keyframes in this pack (this rank's shard)        */
+    int32_t n_covis;           /* covisible slots per keyframe, <= STL_MAX_COVIS    */
+    const int64_t *scan_offset; /* [n_kf+1] first point of each scan in scan_xyz    */
+    const float *scan_xyz;     /* [scan_offset[n_kf]][3] LiDAR-frame points         */
+    const float *intrinsics;   /* [n_kf][4] fx, fy, cx, cy                          */
+    const int32_t *image_wh;   /* [n_kf][2] mnMaxX, mnMaxY                          */
+    const int64_t *kp_offset;  /* [n_kf+1] first keypoint of each keyframe          */
+    const float *kp_xy;        /* [kp_offset[n_kf]][2] mvKeysUn[i].pt               */
+    const float *kp_mappoint;  /* [kp_offset[n_kf]][3] MapPoint::GetWorldPos of the
+                                  map point seen at this keypoint; x = NaN if none  */
+    const float *Tcw;          /* [n_kf][12] KeyFrame::GetPose                      */
+    const float *covis_relpose;/* [n_kf][n_covis][12] Tcw_j * Twc_ref, float32
+                                  product, UNSCALED (iba_global.cpp:280)            */
+    const uint8_t *covis_valid;/* [n_kf][n_covis] 1 if the slot holds a keyframe    */
+    const float *covis_uv;     /* [kp_offset[n_kf]][n_covis][2] (u1,v1) of the keypoint
+                                  matched in covisible slot c (GetMatchedKptIds,
+                                  KeyFrame.cc:528); u1 = NaN if unmatched           */
+    const float *he_Tc;        /* [n_kf][12] Tcw_{i+1} * Twc_i, float32 product
+                                  (iba_global.cpp:267)                              */
+    const double *he_Tl;       /* [n_kf][12] Twl_{i+1}^-1 * Twl_i (iba_global.cpp:269) */
+    const uint8_t *he_valid;   /* [n_kf] 1 iff a next keyframe exists (Fi < F-1,
+                                  iba_global.cpp:264); 0 for the globally last one  */
+} stl_pack_t;
+
+/*
+ * Per-candidate sums returned by stl_eval_batch — exactly the accumulators of
+ * BAError (iba_global.cpp:175-186).  Integer counters are carried as doubles
+ * (exact below 2^53) so that one fp64 all-reduce covers the whole record.
+ */
+typedef struct stl_eval_sums {
+    double sum_3d2d;    /* corr_3d_2d_err before the division  */
+    double sum_3d3d;    /* corr_3d_3d_err before the division  */
+    double sum_he;      /* Cval before the division            */
+    double cnt_he;      /* Ccnt                                */
+    double cnt_3d2d;    /* cnt_3d_2d                           */
+    double valid_3d2d;  /* valid_cnt_3d_2d                     */
+    double cnt_3d3d;    /* cnt_3d_3d                           */
+    double valid_3d3d;  /* valid_cnt_3d_3d                     */
+    double valid_pl;    /* valid_pl_3d_3d                      */
+    double valid_pt;    /* valid_pt_3d_3d                      */
+    double n_frames;    /* frames that passed the num_min_corr gate */
+    double n_corr;      /* total 2-D correspondences over kept frames */
+} stl_eval_sums_t;
+#define STL_EVAL_NSUMS 12
+
+/* What BAError returns (iba_global.cpp:330-343): f1, f2, C, valid, cnt. */
+typedef struct stl_ba_error {
+    double f1;              /* mean 3-D/2-D error  (DBL_MAX if no valid edge) */
+    double f2;              /* mean 3-D/3-D error  (DBL_MAX if no valid edge) */
+    double C;               /* mean hand-eye term                            */
+    int32_t valid_cnt_3d_2d;
+    int32_t cnt_3d_2d;
+} stl_ba_error_t;
+
+/*
+ * Linearisation of the LM path: sum over all residual blocks of the Huber-
+ * corrected cost, gradient J^T r and Gauss-Newton matrix J^T J w.r.t. the raw
+ * 7 parameters [omega, upsilon, s] (VertexSim3 oplus is plain addition,
+ * g2o_tools.h:21-24).  H is the full symmetric 7x7, row-major.
+ */
+typedef struct stl_lin_sums {
+    double cost;     /* sum 0.5 * rho(||e||^2)                 */
+    double g[7];     /* J^T r  (corrected)                     */
+    double H[49];    /* J^T J  (corrected)                     */
+    double n_blocks_2d; /* IBA_PlaneFactor blocks              */
+    double n_blocks_pt; /* Point2Point_Factor blocks           */
+    double n_blocks_pl; /* Point2Plane_Factor blocks           */
+    double n_residuals; /* total scalar residuals              */
+} stl_lin_sums_t;
+#define STL_LIN_NSUMS 61
+
+typedef struct stl_ctx stl_ctx_t;
+
+/* ---- life cycle ------------------------------------------------------- */
+
+/* Defaults = config/calib/00/iba_calib_global.yml:21-48. */
+void stl_default_params(stl_params_t *p);
+
+/* Creates a context on CUDA device `device` (one context per GPU / process).
+ * Fails with STL_ERR_NO_DEVICE if the device is missing or not sm_100:
+ * there is no CPU fallback.  Replaces BALoss's constructor state
+ * (iba_global.cpp:349-361). */
+stl_status_t stl_create(const stl_params_t *params, int32_t device, stl_ctx_t **out);
+void stl_destroy(stl_ctx_t *ctx);
+const char *stl_last_error(const stl_ctx_t *ctx);
+int32_t stl_abi_version(void);
+
+/* Copies the pack to HBM and builds the per-scan 3-D index (replaces the
+ * KDTree3D-per-scan build, iba_global.cpp:362-367).  May be called again to
+ * replace the pack. */
+stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *pack);
+
+/* ---- Nomad / iba_func path ------------------------------------------- */
+
+/* Evaluates B candidates x[b][7] = [omega, upsilon, s] (Sim3 log as BAError's
+ * xvec, iba_global.cpp:188) over this context's keyframes.  HOST in, HOST out;
+ * blocking; thread-safe (internally serialised — Nomad calls eval_x from
+ * several threads).  sums[b] are this pack's partial sums: with one GPU they
+ * are the totals, with keyframe sharding they are all-reduced by the caller
+ * (see stl_eval_batch_device). */
+stl_status_t stl_eval_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl_eval_sums_t *sums);
+
+/* Same, but leaves the [B][STL_EVAL_NSUMS] fp64 record in DEVICE memory
+ * `d_sums` on CUDA stream `stream` (a cudaStream_t; NULL = the context's own
+ * stream) without synchronising: the caller all-reduces it (NCCL, sum) and
+ * then finalises.  x is HOST memory. */
+stl_status_t stl_eval_batch_device(stl_ctx_t *ctx, const double *x, int32_t B, double *d_sums,
+                                   void *stream);
+
+/* BAError's epilogue (iba_global.cpp:330-343): sums -> (f1, f2, C, valid, cnt). */
+void stl_finalize(const stl_params_t *params, const stl_eval_sums_t *sums, stl_ba_error_t *out);
+
+/* BALoss::eval_x's epilogue (iba_global.cpp:386-388): bbo = {f, C1, C2, C3}. */
+void stl_bbo(const stl_params_t *params, const stl_ba_error_t *e, double bbo[4]);
+
+/* ---- Ceres / g2o (LM) path -------------------------------------------- */
+
+/* BuildProblem (iba_local.cpp:145-323): associates at x0[7] and freezes the
+ * residual blocks (plane / point-to-point / point-to-plane) on the device.
+ * n_blocks[3] (optional) receives the block counts {2d, pt, pl} of this pack. */
+stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[3]);
+
+/* Evaluates the frozen blocks at B parameter vectors: cost, J^T r, J^T J
+ * (Ceres semantics: Huber via residual/Jacobian rescaling). */
+stl_status_t stl_linearize_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl_lin_sums_t *out);
+stl_status_t stl_linearize_batch_device(stl_ctx_t *ctx, const double *x, int32_t B, double *d_out,
+                                        void *stream);
+
+/* ---- debug getters (parity tests only) --------------------------------- */
+
+/* 2-D correspondences of keyframe `kf` for the candidate at index `b` of the
+ * LAST stl_eval_batch call (FindProjectCorrespondences' corrset,
+ * iba_global.cpp:55-96).  Writes up to `cap` pairs ordered by keypoint index;
+ * returns the pair count in *n (even if > cap). */
+stl_status_t stl_debug_corrset(stl_ctx_t *ctx, int32_t b, int32_t kf, uint32_t *kp_idx,
+                               uint32_t *pt_idx, int32_t cap, int32_t *n);
+
+/* Per-query 3-D results of the LAST stl_eval_batch for (b, kf)
+ * (ComputeAlignmentDist, iba_global.cpp:111-156): for each correspondence that
+ * has a map point, in corrset order: nn index, neighbour count after radius
+ * truncation, is_plane, dist.  knn_idx (optional) is [cap][32] neighbour
+ * indices in distance order. */
+stl_status_t stl_debug_align(stl_ctx_t *ctx, int32_t b, int32_t kf, uint32_t *kp_idx,
+                             uint32_t *nn_idx, int32_t *n_neigh, int32_t *is_plane, double *dist,
+                             uint32_t *knn_idx, int32_t cap, int32_t *n);
+
+/* Stand-alone exact k-NN over scan `kf` (nanoflann findNeighbors,
+ * nanoflann.hpp:1588): nq queries q[nq][3] (fp64), k <= 32, radius2 <= 0 means
+ * unbounded.  out_idx/out_d2 are [nq][k] sorted ascending by (d2, index);
+ * unused slots hold 0xFFFFFFFF / +inf.  HOST in, HOST out. */
+stl_status_t stl_knn3d(stl_ctx_t *ctx, int32_t kf, const double *q, int32_t nq, int32_t k,
+                       double radius2, uint32_t *out_idx, double *out_d2, int32_t *out_count);
+
+/* ---- measurement -------------------------------------------------------- */
+
+#define STL_STAGE_ASSOC2D 0  /* K1 transform + project + 2-D association      */
+#define STL_STAGE_KNN3D 1    /* K2 3-D 1-NN + k-NN + PCA + gates              */
+#define STL_STAGE_REDUCE 2   /* K3 per-candidate reduction                    */
+#define STL_STAGE_LINEARIZE 3
+#define STL_STAGE_BUILD 4    /* one-off index build of stl_upload_pack        */
+#define STL_NSTAGES 8
+
+/* When enabled, every stage launch is bracketed by CUDA events on its stream;
+ * stl_stage_stats returns accumulated milliseconds / launch counts since the
+ * last reset and resets them. */
+stl_status_t stl_set_profiling(stl_ctx_t *ctx, int32_t enabled);
+stl_status_t stl_stage_stats(stl_ctx_t *ctx, double ms[STL_NSTAGES], int64_t launches[STL_NSTAGES]);
+
+/* Work counters of the last stl_eval_batch (host-side, summed over b):
+ * [0] points streamed by K1, [1] 2-D 1-NN queries (= keypoints),
+ * [2] 3-D 1-NN queries, [3] 3-D k-NN queries, [4] algorithmic bytes of K1. */
+stl_status_t stl_work_counters(stl_ctx_t *ctx, double out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STLCALIB_H_ */
