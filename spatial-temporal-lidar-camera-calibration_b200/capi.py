@@ -1,0 +1,159 @@
+"""Thin ctypes binding of the C-ABI (include/stlcalib.h).  No compute, no fallback."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from .pack import KeyFramePack, default_params
+
+_dp = _abi._dp
+
+
+def _check(lib, h, code):
+    if code != 0:
+        msg = lib.stl_last_error(h).decode() if h else ""
+        raise _abi.StlError(code, msg)
+
+
+class Context:
+    """One GPU's evaluator: owns the device-resident pack, index and workspaces.
+
+    Plays the role of BALoss's constructor state (iba_global.cpp:349-367)."""
+
+    def __init__(self, params: _abi.Params | None = None, device: int = 0):
+        self.lib = _abi.load_calib()
+        self.params = params if params is not None else default_params()
+        h = C.c_void_p()
+        code = self.lib.stl_create(C.byref(self.params), device, C.byref(h))
+        if code != 0:
+            raise _abi.StlError(code, "stl_create failed (an sm_100 GPU is required; there is no CPU fallback)")
+        self.h = h
+        self.device = device
+        self.pack = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.stl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- state -------------------------------------------------------------
+    def upload(self, pack: KeyFramePack):
+        cp = pack.as_c()
+        _check(self.lib, self.h, self.lib.stl_upload_pack(self.h, C.byref(cp)))
+        self.pack = pack
+
+    # -- Nomad / iba_func path ---------------------------------------------
+    def eval_sums(self, x) -> np.ndarray:
+        """x [B,7] (host) -> partial sums [B,12] (host) of this context's keyframes."""
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        B = x.shape[0]
+        out = np.empty((B, _abi.STL_EVAL_NSUMS), dtype=np.float64)
+        _check(self.lib, self.h, self.lib.stl_eval_batch(self.h, x.ctypes.data_as(_dp), B,
+                                                         out.ctypes.data_as(C.POINTER(_abi.EvalSums))))
+        return out
+
+    def eval_sums_device(self, x, d_out_ptr: int, stream_ptr: int = 0):
+        """Enqueue on `stream_ptr`; result rows land in device memory at d_out_ptr ([B,12] fp64)."""
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        _check(self.lib, self.h, self.lib.stl_eval_batch_device(self.h, x.ctypes.data_as(_dp), x.shape[0],
+                                                                C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr)))
+
+    def finalize(self, sums_row):
+        """BAError's return tuple (f1, f2, C, valid_cnt_3d_2d, cnt_3d_2d), iba_global.cpp:330-343."""
+        s = _abi.EvalSums(*[float(v) for v in sums_row])
+        o = _abi.BAErrorOut()
+        self.lib.stl_finalize(C.byref(self.params), C.byref(s), C.byref(o))
+        return o.f1, o.f2, o.C, o.valid_cnt_3d_2d, o.cnt_3d_2d
+
+    def bbo(self, ba):
+        """BALoss::eval_x's BBO values (f, C1, C2, C3), iba_global.cpp:386-388."""
+        o = _abi.BAErrorOut(ba[0], ba[1], ba[2], int(ba[3]), int(ba[4]))
+        out = (C.c_double * 4)()
+        self.lib.stl_bbo(C.byref(self.params), C.byref(o), out)
+        return tuple(out)
+
+    # -- LM path -------------------------------------------------------------
+    def associate(self, x0):
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        nb = np.zeros(3, np.int64)
+        _check(self.lib, self.h, self.lib.stl_associate(self.h, x0.ctypes.data_as(_dp), nb.ctypes.data_as(_abi._i64p)))
+        return nb
+
+    def linearize(self, x) -> np.ndarray:
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        B = x.shape[0]
+        out = np.empty((B, _abi.STL_LIN_NSUMS), dtype=np.float64)
+        _check(self.lib, self.h, self.lib.stl_linearize_batch(self.h, x.ctypes.data_as(_dp), B,
+                                                              out.ctypes.data_as(C.POINTER(_abi.LinSums))))
+        return out
+
+    def linearize_device(self, x, d_out_ptr: int, stream_ptr: int = 0):
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        _check(self.lib, self.h, self.lib.stl_linearize_batch_device(self.h, x.ctypes.data_as(_dp), x.shape[0],
+                                                                     C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr)))
+
+    # -- debug getters (parity tests) ------------------------------------------
+    def debug_corrset(self, b: int, kf: int):
+        cap = int(self.pack.kp_offset[kf + 1] - self.pack.kp_offset[kf]) if self.pack is not None else 65536
+        kp = np.zeros(max(cap, 1), np.uint32)
+        pt = np.zeros(max(cap, 1), np.uint32)
+        n = C.c_int32(0)
+        _check(self.lib, self.h, self.lib.stl_debug_corrset(self.h, b, kf, kp.ctypes.data_as(_abi._u32p),
+                                                            pt.ctypes.data_as(_abi._u32p), cap, C.byref(n)))
+        return kp[:n.value], pt[:n.value]
+
+    def debug_align(self, b: int, kf: int):
+        cap = int(self.pack.kp_offset[kf + 1] - self.pack.kp_offset[kf]) if self.pack is not None else 65536
+        cap = max(cap, 1)
+        kp = np.zeros(cap, np.uint32)
+        nn = np.zeros(cap, np.uint32)
+        m = np.zeros(cap, np.int32)
+        pl = np.zeros(cap, np.int32)
+        d = np.zeros(cap, np.float64)
+        knn = np.zeros((cap, 32), np.uint32)
+        n = C.c_int32(0)
+        _check(self.lib, self.h, self.lib.stl_debug_align(
+            self.h, b, kf, kp.ctypes.data_as(_abi._u32p), nn.ctypes.data_as(_abi._u32p), m.ctypes.data_as(_abi._i32p),
+            pl.ctypes.data_as(_abi._i32p), d.ctypes.data_as(_dp), knn.ctypes.data_as(_abi._u32p), cap, C.byref(n)))
+        k = n.value
+        return dict(kp=kp[:k], nn=nn[:k], m=m[:k], is_plane=pl[:k], dist=d[:k], knn=knn[:k])
+
+    def knn3d(self, kf: int, q, k: int, radius2: float = 0.0):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, 3)
+        nq = q.shape[0]
+        idx = np.zeros((nq, k), np.uint32)
+        d2 = np.zeros((nq, k), np.float64)
+        cnt = np.zeros(nq, np.int32)
+        _check(self.lib, self.h, self.lib.stl_knn3d(self.h, kf, q.ctypes.data_as(_dp), nq, k, radius2,
+                                                    idx.ctypes.data_as(_abi._u32p), d2.ctypes.data_as(_dp),
+                                                    cnt.ctypes.data_as(_abi._i32p)))
+        return idx, d2, cnt
+
+    # -- measurement -------------------------------------------------------------
+    def set_profiling(self, on: bool):
+        _check(self.lib, self.h, self.lib.stl_set_profiling(self.h, int(on)))
+
+    def stage_stats(self):
+        ms = np.zeros(_abi.STL_NSTAGES)
+        n = np.zeros(_abi.STL_NSTAGES, np.int64)
+        _check(self.lib, self.h, self.lib.stl_stage_stats(self.h, ms.ctypes.data_as(_dp), n.ctypes.data_as(_abi._i64p)))
+        return {name: (float(ms[i]), int(n[i])) for i, name in enumerate(_abi.STAGE_NAMES)}
+
+    def work_counters(self):
+        out = np.zeros(8)
+        _check(self.lib, self.h, self.lib.stl_work_counters(self.h, out.ctypes.data_as(_dp)))
+        return dict(points=out[0], q2d=out[1], q3d_nn=out[2], q3d_knn=out[3], k1_bytes=out[4])

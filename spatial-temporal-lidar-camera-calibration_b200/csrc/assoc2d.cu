@@ -1,0 +1,313 @@
+// assoc2d.cu — K1: transform + project + 2-D association + 3-D/2-D and hand-eye terms.
+//
+// Replaces, per (candidate, keyframe):
+//   TransformPointCloud            include/pointcloud.h:82-86   (iba_global.cpp:199)
+//   FindProjectCorrespondences     src/examples/iba_global.cpp:55-96
+//     (projection + cull :68-81, KDTree2D build :84, 1-NN per keypoint :85-95)
+//   frame gate                     src/examples/iba_global.cpp:203
+//   hand-eye term                  src/examples/iba_global.cpp:264-276
+//   covisible re-projection term   src/examples/iba_global.cpp:291-328
+//
+// One CTA per (candidate, keyframe).  No index is ever built over the projected
+// points (the reference rebuilds a KD-tree per candidate and keyframe): only points
+// within max_pixel_dist of a keypoint can become a correspondence, so the scan is
+// STREAMED once (SoA float4, 12 B/point) through a float32 pre-cull against a
+// shared-memory occupancy bitmap of the dilated keypoints; the ~1-2 % survivors are
+// re-evaluated in the reference's exact fp64 arithmetic and min-reduced per keypoint
+// with (distance, original index) order — the result equals the KD-tree 1-NN +
+// threshold whenever no exact distance tie exists (index-order tie-break otherwise).
+// Bound: HBM: 12 B x points + 16 B x keypoints per launch unit.
+#include "kernels.h"
+#include "se3.cuh"
+
+namespace stl {
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kSurvCap = 6144;
+constexpr unsigned long long kInf64 = 0x7ff0000000000000ull;  // +inf bits
+constexpr unsigned long long kNoKey = 0xffffffffffffffffull;
+
+struct Smem {  // fixed part; dynamic arrays follow
+    float mu[4], mv[4], mz[4];  // fast projection rows: u*z, v*z, z
+    float zmin, ub_u, ub_v, ez;
+    float u_hi, v_hi;
+    int n_surv, overflow;
+    int warp_cnt[16], warp_q[16];
+    int base_corr, base_q;
+    double red[3][16];
+};
+
+__device__ __forceinline__ bool exact_project(const DevCand &c, double fx, double cx, double cy, double W, double H, float xf,
+                                              float yf, float zf, double &u, double &v) {
+    double xc, yc, zc;
+    xform(c.R, c.t, (double)xf, (double)yf, (double)zf, xc, yc, zc);
+    if (!(zc > 0.0)) return false;
+    u = ddiv(dadd(dmul(fx, xc), dmul(cx, zc)), zc);
+    v = ddiv(dadd(dmul(fx, yc), dmul(cy, zc)), zc);  // fx, not fy (iba_global.cpp:73)
+    return (0.0 <= u && u < W && 0.0 <= v && v < H);
+}
+
+
+// hand-eye term ||log(Tcl*Tl) - log(Tc*Tcl)|| of one keyframe (iba_global.cpp:264-276); kept out of
+// line so that its 4x4 temporaries do not inflate the streaming kernel's register budget
+__device__ __noinline__ double hand_eye_term(const DevPack &pk, const DevCand &c, int f) {
+    double TcR[9], Tct[3], TlR[9], Tlt[3], C1R[9], C1t[3], C2R[9], C2t[3], l1[6], l2[6];
+    const float *tc = pk.he_Tc + (long long)f * 12;
+    const double *tl = pk.he_Tl + (long long)f * 12;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) { TcR[i * 3 + j] = (double)tc[i * 4 + j]; TlR[i * 3 + j] = tl[i * 4 + j]; }
+        Tct[i] = dmul((double)tc[i * 4 + 3], c.s);  // Tc.topRightCorner *= scale
+        Tlt[i] = tl[i * 4 + 3];
+    }
+    rt_compose(c.R, c.t, TlR, Tlt, C1R, C1t);
+    rt_compose(TcR, Tct, c.R, c.t, C2R, C2t);
+    se3_log(C1R, C1t, l1);
+    se3_log(C2R, C2t, l2);
+    double ss = 0;
+    for (int i = 0; i < 6; ++i) { const double d = l1[i] - l2[i]; ss += d * d; }
+    return sqrt(ss);
+}
+
+// phase 1: atomicMin of d2 per keypoint; phase 2: atomicMin of (orig, sorted) among the d2 ties
+template <int PHASE>
+__device__ __forceinline__ void exact_point(const DevPack &pk, const DevKf &K, const DevCand &c, const DevParams &pr, uint32_t si,
+                                            unsigned long long *best_d2, unsigned long long *best_key) {
+    const long long g = K.pt_off + si;
+    const float xf = pk.px[g], yf = pk.py[g], zf = pk.pz[g];
+    double u, v;
+    if (!exact_project(c, (double)K.fx, (double)K.cx, (double)K.cy, (double)K.W, (double)K.H, xf, yf, zf, u, v)) return;
+    const double rp = sqrt(pr.max_pixel_dist2) + 1e-6;
+    int gx0 = (int)floor((u - rp) * (1.0 / kGridCell)), gx1 = (int)floor((u + rp) * (1.0 / kGridCell));
+    int gy0 = (int)floor((v - rp) * (1.0 / kGridCell)), gy1 = (int)floor((v + rp) * (1.0 / kGridCell));
+    gx0 = max(gx0, 0); gy0 = max(gy0, 0); gx1 = min(gx1, K.gw - 1); gy1 = min(gy1, K.gh - 1);
+    const uint32_t *gs = pk.grid_start + K.grid_off;
+    const uint32_t *gk = pk.grid_kp + K.kp_off;
+    const float2 *kp = pk.kp_xy + K.kp_off;
+    for (int gy = gy0; gy <= gy1; ++gy) {
+        const uint32_t a = gs[gy * K.gw + gx0], b = gs[gy * K.gw + gx1 + 1];  // cells of one row are contiguous
+        for (uint32_t j = a; j < b; ++j) {
+            const uint32_t k = gk[j];
+            const float2 q = kp[k];
+            const double dx = dsub((double)q.x, u), dy = dsub((double)q.y, v);
+            const double d2 = dadd(dmul(dx, dx), dmul(dy, dy));  // nanoflann.hpp:524-535, query - data
+            if (d2 <= pr.max_pixel_dist2) {
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(d2);
+                if (PHASE == 1) {
+                    atomicMin(&best_d2[k], bits);
+                } else if (bits == best_d2[k]) {
+                    atomicMin(&best_key[k], ((unsigned long long)pk.orig[g] << 32) | si);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int f = blockIdx.x / B, b = blockIdx.x - f * B;
+    const DevKf K = pk.kf[f];
+    const DevCand &c = wk.cand[b];
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    unsigned long long *best_d2 = reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(Smem) + 15) & ~size_t(15)));
+    unsigned long long *best_key = best_d2 + K.n_kp;
+    uint32_t *surv = reinterpret_cast<uint32_t *>(best_key + K.n_kp);
+    uint32_t *bm = surv + kSurvCap;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- prologue: fast rows, error bounds, bitmap, per-keypoint minima
+    if (tid == 0) {
+        const double fx = K.fx, cx = K.cx, cy = K.cy;
+        double ru[4], rv[4], rz[4];
+        for (int j = 0; j < 3; ++j) {
+            ru[j] = fx * c.R[j] + cx * c.R[6 + j];
+            rv[j] = fx * c.R[3 + j] + cy * c.R[6 + j];
+            rz[j] = c.R[6 + j];
+        }
+        ru[3] = fx * c.t[0] + cx * c.t[2];
+        rv[3] = fx * c.t[1] + cy * c.t[2];
+        rz[3] = c.t[2];
+        for (int j = 0; j < 4; ++j) { S.mu[j] = (float)ru[j]; S.mv[j] = (float)rv[j]; S.mz[j] = (float)rz[j]; }
+        // float32 error model of the fast path: 3 FMAs + rounded matrix entries
+        const double eps = 1.1920928955078125e-07, pm = K.pmax;
+        const double Az = (fabs(rz[0]) + fabs(rz[1]) + fabs(rz[2])) * pm + fabs(rz[3]);
+        const double Au = (fabs(ru[0]) + fabs(ru[1]) + fabs(ru[2])) * pm + fabs(ru[3]);
+        const double Av = (fabs(rv[0]) + fabs(rv[1]) + fabs(rv[2])) * pm + fabs(rv[3]);
+        const double ez = 4 * eps * Az, eu = 4 * eps * fmax(Au, Av);
+        const double Umax = (double)max(K.W, K.H) + 8.0;
+        const double zmin = (eu + Umax * ez) / ((double)kFastErrPx - Umax * 3 * eps);
+        S.zmin = (float)(zmin * 1.0001) + 1e-30f;
+        S.ez = (float)(ez * 1.0001);
+        S.ub_u = (float)(((double)K.W + 2.0) * (zmin + ez) + eu);
+        S.ub_v = (float)(((double)K.H + 2.0) * (zmin + ez) + eu);
+        S.u_hi = (float)(kBmCell * (K.bm_wpr * 32 - 1));  // never index past the row
+        S.u_hi = fminf(S.u_hi, (float)(K.W + kBmCell));
+        S.v_hi = (float)(K.H + kBmCell);
+        S.n_surv = 0;
+        S.overflow = 0;
+        S.base_corr = 0;
+        S.base_q = 0;
+    }
+    for (int k = tid; k < K.n_kp; k += kThreads) { best_d2[k] = kInf64; best_key[k] = kNoKey; }
+    {
+        const int nw = K.bm_wpr * K.bm_rows;
+        const uint32_t *src = pk.bitmap + K.bm_off;
+        for (int i = tid; i < nw; i += kThreads) bm[i] = src[i];
+    }
+    __syncthreads();
+
+    // ---- phase A: stream the scan (SoA float4 loads, 12 B/point), float32 pre-cull
+    {
+        const float mu0 = S.mu[0], mu1 = S.mu[1], mu2 = S.mu[2], mu3 = S.mu[3];
+        const float mv0 = S.mv[0], mv1 = S.mv[1], mv2 = S.mv[2], mv3 = S.mv[3];
+        const float mz0 = S.mz[0], mz1 = S.mz[1], mz2 = S.mz[2], mz3 = S.mz[3];
+        const float zmin = S.zmin, u_hi = S.u_hi, v_hi = S.v_hi, lo = -(float)kBmCell;
+        const int wpr = K.bm_wpr, cu_max = K.bm_wpr * 32 - 1, cv_max = K.bm_rows - 1;
+        const float4 *X = reinterpret_cast<const float4 *>(pk.px + K.pt_off);
+        const float4 *Y = reinterpret_cast<const float4 *>(pk.py + K.pt_off);
+        const float4 *Z = reinterpret_cast<const float4 *>(pk.pz + K.pt_off);
+        const int n4 = K.n_pad >> 2;
+#pragma unroll 2
+        for (int i = tid; i < n4; i += kThreads) {
+            const float4 x4 = ld_stream_f4(X + i), y4 = ld_stream_f4(Y + i), z4 = ld_stream_f4(Z + i);
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float zc = fmaf(mz0, xs[e], fmaf(mz1, ys[e], fmaf(mz2, zs[e], mz3)));
+                const float uz = fmaf(mu0, xs[e], fmaf(mu1, ys[e], fmaf(mu2, zs[e], mu3)));
+                const float vz = fmaf(mv0, xs[e], fmaf(mv1, ys[e], fmaf(mv2, zs[e], mv3)));
+                bool pass = false;
+                if (zc > zmin) {
+                    // inside the apron-extended image?  (no division for the ~87 % that are not)
+                    if (uz >= lo * zc && uz < u_hi * zc && vz >= lo * zc && vz < v_hi * zc) {
+                        const float inv = __frcp_rn(zc);
+                        const int cu = min(max((int)floorf(uz * inv * (1.0f / kBmCell)) + 1, 0), cu_max);
+                        const int cv = min(max((int)floorf(vz * inv * (1.0f / kBmCell)) + 1, 0), cv_max);
+                        pass = (bm[cv * wpr + (cu >> 5)] >> (cu & 31)) & 1u;
+                    }
+                } else if (zc > -S.ez) {
+                    // thin slab in front of the camera plane where the float32 bound does not hold: exact path decides
+                    pass = fabsf(uz) <= S.ub_u && fabsf(vz) <= S.ub_v;
+                }
+                if (pass) {
+                    const int pos = atomicAdd(&S.n_surv, 1);
+                    if (pos < kSurvCap) surv[pos] = (uint32_t)(i * 4 + e);
+                    else S.overflow = 1;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phases B/C: exact fp64 re-evaluation of the survivors, (d2, original index) minimum per keypoint
+    const bool ovf = S.overflow != 0;
+    const int ns = ovf ? K.n_pts : min(S.n_surv, kSurvCap);
+    for (int s = tid; s < ns; s += kThreads) exact_point<1>(pk, K, c, pr, ovf ? (uint32_t)s : surv[s], best_d2, best_key);
+    __syncthreads();
+    for (int s = tid; s < ns; s += kThreads) exact_point<2>(pk, K, c, pr, ovf ? (uint32_t)s : surv[s], best_d2, best_key);
+    __syncthreads();
+    if (ovf && tid == 0 && wk.overflow) atomicAdd(wk.overflow, 1);
+
+    // ---- phase D: corrset in keypoint order (block scan), query list = correspondences with a map point
+    const long long out_base = (long long)b * pk.n_kp_total + K.kp_off;
+    const float *mp = pk.kp_mp + K.kp_off * 3;
+    for (int k0 = 0; k0 < K.n_kp; k0 += kThreads) {
+        const int k = k0 + tid;
+        const bool has = k < K.n_kp && best_key[k] != kNoKey;
+        const bool hasq = has && !isnan(mp[k * 3]);
+        const unsigned m1 = __ballot_sync(0xffffffffu, has), m2 = __ballot_sync(0xffffffffu, hasq);
+        if (lane == 0) { S.warp_cnt[warp] = __popc(m1); S.warp_q[warp] = __popc(m2); }
+        __syncthreads();
+        int pc = S.base_corr, pq = S.base_q;
+        for (int w = 0; w < warp; ++w) { pc += S.warp_cnt[w]; pq += S.warp_q[w]; }
+        pc += __popc(m1 & ((1u << lane) - 1));
+        pq += __popc(m2 & ((1u << lane) - 1));
+        if (has) {
+            const unsigned long long key = best_key[k];
+            wk.corr_kp[out_base + pc] = (uint32_t)k;
+            wk.corr_pt[out_base + pc] = (uint32_t)(key >> 32);
+            wk.corr_sp[out_base + pc] = (uint32_t)(key & 0xffffffffu);
+            if (hasq) wk.q_corr[out_base + pq] = (uint32_t)pc;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tc = 0, tq = 0;
+            for (int w = 0; w < kThreads / 32; ++w) { tc += S.warp_cnt[w]; tq += S.warp_q[w]; }
+            S.base_corr += tc;
+            S.base_q += tq;
+        }
+        __syncthreads();
+    }
+    const int ncorr = S.base_corr, nq = S.base_q;
+    const bool kept = ncorr >= pr.num_min_corr;  // iba_global.cpp:203
+
+    // ---- 3-D/2-D term over (correspondence x covisible keyframe), iba_global.cpp:291-328
+    double s2d = 0, v2d = 0, c2d = 0;
+    if (kept) {
+        const int C = pk.n_covis;
+        const double fx = K.fx, fy = K.fy, cx = K.cx, cy = K.cy, W = K.W, H = K.H;
+        for (int k = tid; k < K.n_kp; k += kThreads) {
+            const unsigned long long key = best_key[k];
+            if (key == kNoKey) continue;
+            const long long g = K.pt_off + (uint32_t)(key & 0xffffffffu);
+            double p0x, p0y, p0z;
+            xform(c.R, c.t, (double)pk.px[g], (double)pk.py[g], (double)pk.pz[g], p0x, p0y, p0z);
+            for (int j = 0; j < C; ++j) {
+                if (!pk.covis_valid[f * C + j]) continue;
+                const float2 uv = pk.covis_uv[(K.kp_off + k) * C + j];
+                if (isnan(uv.x)) continue;
+                const float *rp = pk.relpose + ((long long)f * C + j) * 12;
+                const double p1x = dadd(dot3e((double)rp[0], (double)rp[1], (double)rp[2], p0x, p0y, p0z), dmul((double)rp[3], c.s));
+                const double p1y = dadd(dot3e((double)rp[4], (double)rp[5], (double)rp[6], p0x, p0y, p0z), dmul((double)rp[7], c.s));
+                const double p1z = dadd(dot3e((double)rp[8], (double)rp[9], (double)rp[10], p0x, p0y, p0z), dmul((double)rp[11], c.s));
+                const double ou = dadd(ddiv(dmul(fx, p1x), p1z), cx);
+                const double ov = dadd(ddiv(dmul(fy, p1y), p1z), cy);
+                if (!(ou >= 0 && ou < W && ov >= 0 && ov < H)) continue;
+                const double du = dsub(ou, (double)uv.x), dv = dsub(ov, (double)uv.y);
+                const double dist = sqrt(dadd(dmul(du, du), dmul(dv, dv)));
+                if (dist < pr.thr2d) { s2d += dist; v2d += 1.0; }
+                c2d += 1.0;
+            }
+        }
+    }
+    // fixed-order block reduction (deterministic)
+    for (int o = 16; o; o >>= 1) {
+        s2d += __shfl_down_sync(0xffffffffu, s2d, o);
+        v2d += __shfl_down_sync(0xffffffffu, v2d, o);
+        c2d += __shfl_down_sync(0xffffffffu, c2d, o);
+    }
+    if (lane == 0) { S.red[0][warp] = s2d; S.red[1][warp] = v2d; S.red[2][warp] = c2d; }
+    __syncthreads();
+    if (tid == 0) {
+        FrameRec r;
+        r.s2d = r.v2d = r.c2d = 0;
+        for (int w = 0; w < kThreads / 32; ++w) { r.s2d += S.red[0][w]; r.v2d += S.red[1][w]; r.c2d += S.red[2][w]; }
+        r.she = 0; r.che = 0;
+        if (kept && K.he_valid) { r.she = hand_eye_term(pk, c, f); r.che = 1; }
+        r.kept = kept ? 1.0 : 0.0;
+        r.ncorr = kept ? (double)ncorr : 0.0;
+        r.nq = kept ? (double)nq : 0.0;
+        wk.frame[(long long)b * pk.n_kf + f] = r;
+        wk.n_corr[(long long)b * pk.n_kf + f] = ncorr;
+        wk.n_q[(long long)b * pk.n_kf + f] = kept ? nq : 0;
+    }
+}
+
+}  // namespace
+
+size_t assoc2d_smem_bytes(int max_kp, int max_bm_words) {
+    return ((sizeof(Smem) + 15) & ~size_t(15)) + (size_t)max_kp * 16 + (size_t)kSurvCap * 4 + (size_t)max_bm_words * 4;
+}
+
+cudaError_t assoc2d_configure(size_t smem) {
+    return cudaFuncSetAttribute(k_assoc2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, cudaStream_t st) {
+    if (B <= 0 || pk.n_kf <= 0) return cudaSuccess;
+    k_assoc2d<<<(unsigned)(pk.n_kf * B), kThreads, smem, st>>>(pk, wk, pr, B);
+    return cudaGetLastError();
+}
+
+}  // namespace stl

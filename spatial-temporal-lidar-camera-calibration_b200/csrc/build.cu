@@ -1,0 +1,211 @@
+// build.cu — K0: one-off per-scan 3-D index build (replaces the KDTree3D-per-scan
+// construction of BALoss's constructor, src/examples/iba_global.cpp:362-367).
+//
+// Candidate-independent.  For a chunk of keyframes whose raw float32 points are on
+// the device:  bbox -> 48-bit Morton key (16 bit/axis, isotropic cell) tagged with
+// the keyframe -> one stable radix sort (cub) -> scatter into the padded SoA layout
+// -> AABBs of every block of 32 points, then two 32-ary levels above them.
+// HBM-bound streaming; algorithmic bytes ~ 12 B read + 16 B written per point.
+#include <cub/cub.cuh>
+
+#include "kernels.h"
+
+namespace stl {
+namespace {
+
+__device__ __forceinline__ unsigned long long spread16(unsigned v) {  // abcd -> a00b00c00d
+    unsigned long long x = v & 0xffffull;
+    x = (x | (x << 16)) & 0x0000ff0000ffull;
+    x = (x | (x << 8)) & 0x00f00f00f00full;
+    x = (x | (x << 4)) & 0x0c30c30c30c3ull;
+    x = (x | (x << 2)) & 0x249249249249ull;
+    return x;
+}
+
+// one block per keyframe: bbox + pmax
+__global__ void k_bbox(const float *__restrict__ raw, const long long *__restrict__ raw_off, float *__restrict__ bbox, DevKf *kf,
+                       int kf_begin) {
+    const int f = blockIdx.x;
+    const long long b = raw_off[f], e = raw_off[f + 1];
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = raw[i * 3 + a];
+            lo[a] = fminf(lo[a], v);
+            hi[a] = fmaxf(hi[a], v);
+        }
+    }
+    __shared__ float slo[3][32], shi[3][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        for (int o = 16; o; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { slo[a][w] = lo[a]; shi[a][w] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        float pm = 0.f;
+        for (int a = 0; a < 3; ++a) {
+            float l = slo[a][0], h = shi[a][0];
+            for (int i = 1; i < nw; ++i) { l = fminf(l, slo[a][i]); h = fmaxf(h, shi[a][i]); }
+            bbox[f * 6 + a] = l;
+            bbox[f * 6 + 3 + a] = h;
+            pm = fmaxf(pm, fmaxf(fabsf(l), fabsf(h)));
+        }
+        if (!(pm >= 1.f)) pm = 1.f;
+        kf[kf_begin + f].pmax = pm;
+    }
+}
+
+// grid (tiles, nkf)
+__global__ void k_morton(const float *__restrict__ raw, const long long *__restrict__ raw_off, const float *__restrict__ bbox,
+                         unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const int f = blockIdx.y;
+    const long long b = raw_off[f], e = raw_off[f + 1];
+    const float lx = bbox[f * 6], ly = bbox[f * 6 + 1], lz = bbox[f * 6 + 2];
+    float ext = fmaxf(fmaxf(bbox[f * 6 + 3] - lx, bbox[f * 6 + 4] - ly), bbox[f * 6 + 5] - lz);
+    if (!(ext > 0.f)) ext = 1.f;
+    const float scale = 65535.0f / ext;
+    for (long long i = b + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (long long)gridDim.x * blockDim.x) {
+        const float x = raw[i * 3], y = raw[i * 3 + 1], z = raw[i * 3 + 2];
+        const unsigned qx = (unsigned)fminf(fmaxf((x - lx) * scale, 0.f), 65535.f);
+        const unsigned qy = (unsigned)fminf(fmaxf((y - ly) * scale, 0.f), 65535.f);
+        const unsigned qz = (unsigned)fminf(fmaxf((z - lz) * scale, 0.f), 65535.f);
+        const unsigned long long m = spread16(qx) | (spread16(qy) << 1) | (spread16(qz) << 2);
+        keys[i] = ((unsigned long long)f << 48) | m;
+        vals[i] = (uint32_t)(i - b);
+    }
+}
+
+// grid (tiles, nkf): sorted rank j of keyframe f -> padded SoA slot
+__global__ void k_scatter(const float *__restrict__ raw, const long long *__restrict__ raw_off, const uint32_t *__restrict__ vals,
+                          const DevKf *__restrict__ kf, int kf_begin, float *__restrict__ px, float *__restrict__ py,
+                          float *__restrict__ pz, uint32_t *__restrict__ orig) {
+    const int f = blockIdx.y;
+    const DevKf K = kf[kf_begin + f];
+    const long long b = raw_off[f];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < K.n_pad; j += gridDim.x * blockDim.x) {
+        const long long dst = K.pt_off + j;
+        if (j < K.n_pts) {
+            const uint32_t v = vals[b + j];
+            const float *p = raw + (b + v) * 3;
+            px[dst] = p[0]; py[dst] = p[1]; pz[dst] = p[2];
+            orig[dst] = v;
+        } else {
+            const float qn = __int_as_float(0x7fc00000);
+            px[dst] = qn; py[dst] = qn; pz[dst] = qn;
+            orig[dst] = 0xffffffffu;
+        }
+    }
+}
+
+__device__ __forceinline__ void warp_box(float4 &lo, float4 &hi) {
+    for (int o = 16; o; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o));
+        lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o));
+        hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o));
+        hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+    }
+}
+
+// one warp per leaf slot (n0 per keyframe); grid (ceil(max_n0/warps), nkf)
+__global__ void k_leaf_aabb(const DevKf *__restrict__ kf, int kf_begin, const float *__restrict__ px, const float *__restrict__ py,
+                            const float *__restrict__ pz, float4 *__restrict__ node_lo, float4 *__restrict__ node_hi) {
+    const DevKf K = kf[kf_begin + blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int leaf = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (leaf >= K.n0) return;
+    float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+    const int j = leaf * kLeaf + lane;
+    if (j < K.n_pts) {  // fminf/fmaxf ignore the NaN pads anyway; this also skips slots past n_pad
+        const long long s = K.pt_off + j;
+        lo.x = hi.x = px[s]; lo.y = hi.y = py[s]; lo.z = hi.z = pz[s];
+    }
+    warp_box(lo, hi);
+    if (lane == 0) { node_lo[K.node_off + leaf] = lo; node_hi[K.node_off + leaf] = hi; }
+}
+
+// one warp per inner node; level 1: children = leaves, level 2: children = level-1 nodes
+__global__ void k_inner_aabb(const DevKf *__restrict__ kf, int kf_begin, int level, float4 *__restrict__ node_lo,
+                             float4 *__restrict__ node_hi) {
+    const DevKf K = kf[kf_begin + blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int node = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int n_here = level == 1 ? K.n1 : 32;  // level-2 slots are always padded to 32
+    if (node >= n_here) return;
+    const long long child_base = K.node_off + (level == 1 ? 0 : K.n0);
+    const int n_child = level == 1 ? K.n0 : K.n1;
+    const long long out_base = K.node_off + (level == 1 ? K.n0 : K.n0 + K.n1);
+    float4 lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+    const int c = node * 32 + lane;
+    if (c < n_child) { lo = node_lo[child_base + c]; hi = node_hi[child_base + c]; }
+    warp_box(lo, hi);
+    if (lane == 0) { node_lo[out_base + node] = lo; node_hi[out_base + node] = hi; }
+}
+
+}  // namespace
+
+cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int nkf, int kf_begin, const DevKf *h_kf, DevPack &pack,
+                             cudaStream_t st) {
+    const long long n = h_raw_off[nkf] - h_raw_off[0];
+    cudaError_t err = cudaSuccess;
+    long long *d_off = nullptr;
+    float *d_bbox = nullptr;
+    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
+    uint32_t *d_vals = nullptr, *d_vals2 = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int max_pad = 0, max_n0 = 0, max_n1 = 0;
+    for (int f = 0; f < nkf; ++f) {
+        max_pad = max_pad > h_kf[kf_begin + f].n_pad ? max_pad : h_kf[kf_begin + f].n_pad;
+        max_n0 = max_n0 > h_kf[kf_begin + f].n0 ? max_n0 : h_kf[kf_begin + f].n0;
+        max_n1 = max_n1 > h_kf[kf_begin + f].n1 ? max_n1 : h_kf[kf_begin + f].n1;
+    }
+    // chunk-relative offsets
+    long long *h_rel = (long long *)malloc(sizeof(long long) * (nkf + 1));
+    for (int f = 0; f <= nkf; ++f) h_rel[f] = h_raw_off[f] - h_raw_off[0];
+#define STL_TRY(x) do { err = (x); if (err != cudaSuccess) goto done; } while (0)
+    STL_TRY(cudaMalloc(&d_off, sizeof(long long) * (nkf + 1)));
+    STL_TRY(cudaMemcpyAsync(d_off, h_rel, sizeof(long long) * (nkf + 1), cudaMemcpyHostToDevice, st));
+    STL_TRY(cudaMalloc(&d_bbox, sizeof(float) * 6 * nkf));
+    if (n > 0) {
+        STL_TRY(cudaMalloc(&d_keys, sizeof(unsigned long long) * n));
+        STL_TRY(cudaMalloc(&d_keys2, sizeof(unsigned long long) * n));
+        STL_TRY(cudaMalloc(&d_vals, sizeof(uint32_t) * n));
+        STL_TRY(cudaMalloc(&d_vals2, sizeof(uint32_t) * n));
+    }
+    k_bbox<<<nkf, 512, 0, st>>>(d_raw, d_off, d_bbox, pack.kf, kf_begin);
+    if (n > 0) {
+        const int tiles = (max_pad + 256 * 8 - 1) / (256 * 8);
+        k_morton<<<dim3(tiles, nkf), 256, 0, st>>>(d_raw, d_off, d_bbox, d_keys, d_vals);
+        int kf_bits = 1;
+        while ((1 << kf_bits) < nkf) ++kf_bits;
+        STL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, 48 + kf_bits, st));
+        STL_TRY(cudaMalloc(&d_tmp, tmp_bytes));
+        STL_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, 48 + kf_bits, st));
+    }
+    {
+        const int tiles = (max_pad + 256 * 8 - 1) / (256 * 8);
+        k_scatter<<<dim3(tiles > 0 ? tiles : 1, nkf), 256, 0, st>>>(d_raw, d_off, d_vals2, pack.kf, kf_begin, pack.px, pack.py, pack.pz,
+                                                                    pack.orig);
+        k_leaf_aabb<<<dim3((max_n0 + 7) / 8, nkf), 256, 0, st>>>(pack.kf, kf_begin, pack.px, pack.py, pack.pz, pack.node_lo, pack.node_hi);
+        k_inner_aabb<<<dim3((max_n1 + 7) / 8, nkf), 256, 0, st>>>(pack.kf, kf_begin, 1, pack.node_lo, pack.node_hi);
+        k_inner_aabb<<<dim3(4, nkf), 256, 0, st>>>(pack.kf, kf_begin, 2, pack.node_lo, pack.node_hi);
+    }
+    STL_TRY(cudaGetLastError());
+    STL_TRY(cudaStreamSynchronize(st));
+#undef STL_TRY
+done:
+    free(h_rel);
+    cudaFree(d_off); cudaFree(d_bbox); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_tmp);
+    return err;
+}
+
+}  // namespace stl

@@ -1,0 +1,637 @@
+// capi.cu — the C-ABI of include/stlcalib.h: context, pack upload, batched evaluation.
+// Host orchestration only; every number comes from the CUDA kernels.  No CPU fallback:
+// stl_create fails without an sm_100 device.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/stlcalib.h"
+#include "hostmath.hpp"
+#include "kernels.h"
+#include "lm.h"
+
+using namespace stl;
+
+struct stl_ctx {
+    int device = 0;
+    stl_params_t params;
+    DevParams dpr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    bool has_pack = false;
+    DevPack pk;
+    std::vector<DevKf> h_kf;
+    int max_kp = 0, max_bm_words = 0;
+    size_t k1_smem = 0;
+    long long n_pts_total = 0;
+    // workspace
+    DevWork wk;
+    int wk_cap = 0;
+    bool dbg_alloc = false;
+    double *d_sums = nullptr;
+    int d_sums_cap = 0;
+    DevCand *h_cand = nullptr;  // pinned
+    double *h_sums = nullptr;   // pinned
+    int h_cap = 0;
+    std::vector<double> last_x;
+    int dbg_b = -1;
+    // LM path
+    LmState lm;
+    double *d_lin = nullptr;
+    double *h_lin = nullptr;
+    int lin_cap = 0;
+    // profiling
+    bool profiling = false;
+    struct Ev { cudaEvent_t a, b; int stage; };
+    std::vector<Ev> evs;
+    std::vector<cudaEvent_t> ev_pool;
+    double stage_ms[STL_NSTAGES] = {0};
+    long long stage_n[STL_NSTAGES] = {0};
+    double counters[8] = {0};
+};
+
+namespace {
+
+stl_status_t fail(stl_ctx *c, stl_status_t code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T> void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
+
+void free_pack(stl_ctx *c) {
+    DevPack &p = c->pk;
+    dfree(p.kf); dfree(p.px); dfree(p.py); dfree(p.pz); dfree(p.orig); dfree(p.node_lo); dfree(p.node_hi);
+    dfree(p.bitmap); dfree(p.grid_start); dfree(p.grid_kp); dfree(p.kp_xy); dfree(p.kp_mp); dfree(p.Tcw);
+    dfree(p.relpose); dfree(p.covis_valid); dfree(p.covis_uv); dfree(p.he_Tc); dfree(p.he_Tl);
+    p = DevPack();
+    c->has_pack = false;
+}
+void free_work(stl_ctx *c) {
+    DevWork &w = c->wk;
+    dfree(w.cand); dfree(w.corr_kp); dfree(w.corr_pt); dfree(w.corr_sp); dfree(w.q_corr); dfree(w.n_corr); dfree(w.n_q);
+    dfree(w.frame); dfree(w.align); dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn);
+    dfree(w.overflow);
+    w = DevWork();
+    c->wk_cap = 0;
+    c->dbg_alloc = false;
+}
+
+void set_dev_params(stl_ctx *c) {
+    const stl_params_t &p = c->params;
+    DevParams &d = c->dpr;
+    d.max_pixel_dist2 = p.max_pixel_dist * p.max_pixel_dist;
+    d.thr2d = p.corr_3d_2d_threshold;
+    d.thr3d = p.corr_3d_3d_threshold;
+    d.radius2 = p.norm_radius * p.norm_radius;
+    d.reg_thr = p.norm_reg_threshold;
+    d.min_diff2 = p.min_diff_dist * p.min_diff_dist;
+    d.max_3d_dist2 = p.max_3d_dist * p.max_3d_dist;
+    d.delta2d = p.robust_kernel_delta;
+    d.delta3d = p.robust_kernel_3ddelta;
+    d.w0 = p.err_weight[0];
+    d.w1 = p.err_weight[1];
+    d.num_min_corr = p.num_min_corr;
+    d.k = p.norm_max_pts;
+    d.min_pts = p.norm_min_pts;
+    d.use_plane = p.use_plane;
+}
+
+struct StageTimer {
+    stl_ctx *c; int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(stl_ctx *c_, int s, cudaStream_t st_) : c(c_), stage(s), st(st_) {
+        if (!c->profiling) return;
+        auto get = [&]() { cudaEvent_t e; if (c->ev_pool.empty()) cudaEventCreate(&e); else { e = c->ev_pool.back(); c->ev_pool.pop_back(); } return e; };
+        a = get(); b = get();
+        cudaEventRecord(a, st);
+    }
+    ~StageTimer() {
+        if (!a) return;
+        cudaEventRecord(b, st);
+        c->evs.push_back({a, b, stage});
+    }
+};
+
+void drain_events(stl_ctx *c) {
+    for (auto &e : c->evs) {
+        cudaEventSynchronize(e.b);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { c->stage_ms[e.stage] += ms; c->stage_n[e.stage] += 1; }
+        c->ev_pool.push_back(e.a);
+        c->ev_pool.push_back(e.b);
+    }
+    c->evs.clear();
+}
+
+stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
+    const DevPack &pk = ctx->pk;
+    if (ctx->wk_cap == 0) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_cand = (size_t)pk.n_kp_total * 16 + (size_t)pk.n_kf * (sizeof(FrameRec) + 4 * sizeof(AlignRec) + 8) + sizeof(DevCand);
+        size_t budget = std::min<size_t>((size_t)4 << 30, free_b / 4);
+        int cap = (int)std::max<size_t>(1, std::min<size_t>(budget / std::max<size_t>(per_cand, 1), 256));
+        DevWork &w = ctx->wk;
+        w.Bc = cap;
+        w.sub = 4;
+        const size_t nk = (size_t)std::max<long long>(pk.n_kp_total, 1) * cap, nf = (size_t)pk.n_kf * cap;
+        CK(cudaMalloc(&w.cand, sizeof(DevCand) * cap));
+        CK(cudaMalloc(&w.corr_kp, 4 * nk)); CK(cudaMalloc(&w.corr_pt, 4 * nk)); CK(cudaMalloc(&w.corr_sp, 4 * nk)); CK(cudaMalloc(&w.q_corr, 4 * nk));
+        CK(cudaMalloc(&w.n_corr, 4 * nf)); CK(cudaMalloc(&w.n_q, 4 * nf));
+        CK(cudaMalloc(&w.frame, sizeof(FrameRec) * nf)); CK(cudaMalloc(&w.align, sizeof(AlignRec) * nf * w.sub));
+        CK(cudaMalloc(&w.overflow, 4));
+        CK(cudaMemset(w.overflow, 0, 4));
+        ctx->wk_cap = cap;
+    }
+    if (debug && !ctx->dbg_alloc) {
+        DevWork &w = ctx->wk;
+        const size_t nk = (size_t)std::max<long long>(pk.n_kp_total, 1);
+        CK(cudaMalloc(&w.dbg_nn, 4 * nk)); CK(cudaMalloc(&w.dbg_m, 4 * nk)); CK(cudaMalloc(&w.dbg_plane, 4 * nk));
+        CK(cudaMalloc(&w.dbg_dist, 8 * nk)); CK(cudaMalloc(&w.dbg_knn, 4 * nk * kMaxK));
+        ctx->dbg_alloc = true;
+    }
+    if (B > ctx->h_cap) {
+        if (ctx->h_cand) cudaFreeHost(ctx->h_cand);
+        if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
+        ctx->h_cand = nullptr; ctx->h_sums = nullptr;
+        CK(cudaMallocHost(&ctx->h_cand, sizeof(DevCand) * B));
+        CK(cudaMallocHost(&ctx->h_sums, sizeof(double) * STL_EVAL_NSUMS * B));
+        ctx->h_cap = B;
+    }
+    if (B > ctx->d_sums_cap) {
+        dfree(ctx->d_sums);
+        CK(cudaMalloc(&ctx->d_sums, sizeof(double) * STL_EVAL_NSUMS * B));
+        ctx->d_sums_cap = B;
+    }
+    return STL_OK;
+}
+
+// Enqueues the evaluation of B candidates; d_out [B][STL_EVAL_NSUMS] device.
+stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, cudaStream_t st, bool debug) {
+    stl_status_t s = ensure_work(ctx, B, debug);
+    if (s != STL_OK) return s;
+    for (int b = 0; b < B; ++b) make_candidate(x + (size_t)b * 7, ctx->h_cand + b);
+    const int Bc = ctx->wk.Bc;
+    for (int c0 = 0; c0 < B; c0 += Bc) {
+        const int nb = std::min(Bc, B - c0);
+        CK(cudaMemcpyAsync(ctx->wk.cand, ctx->h_cand + c0, sizeof(DevCand) * nb, cudaMemcpyHostToDevice, st));
+        { StageTimer t(ctx, STL_STAGE_ASSOC2D, st); CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_smem, st)); }
+        { StageTimer t(ctx, STL_STAGE_KNN3D, st); CK(launch_align3d(ctx->pk, ctx->wk, ctx->dpr, nb, debug ? 1 : 0, st)); }
+        { StageTimer t(ctx, STL_STAGE_REDUCE, st); CK(launch_reduce(ctx->pk, ctx->wk, ctx->dpr, nb, d_out + (size_t)c0 * STL_EVAL_NSUMS, st)); }
+    }
+    ctx->counters[0] = (double)ctx->n_pts_total * B;
+    ctx->counters[1] = (double)ctx->pk.n_kp_total * B;
+    ctx->counters[4] = ((double)ctx->n_pts_total * 12.0 + (double)ctx->pk.n_kp_total * 16.0) * B;
+    ctx->last_x.assign(x, x + (size_t)B * 7);
+    ctx->dbg_b = -1;
+    return STL_OK;
+}
+
+stl_status_t run_debug(stl_ctx *ctx, int b) {
+    if (!ctx->has_pack) return fail(ctx, STL_ERR_STATE, "no pack uploaded");
+    if (b < 0 || (size_t)b * 7 + 7 > ctx->last_x.size()) return fail(ctx, STL_ERR_INVALID, "candidate %d was not part of the last batch", b);
+    if (ctx->dbg_b == b) return STL_OK;
+    std::vector<double> keep = ctx->last_x;
+    double xb[7];
+    memcpy(xb, &keep[(size_t)b * 7], sizeof(xb));
+    stl_status_t s = ensure_work(ctx, 1, true);
+    if (s != STL_OK) return s;
+    s = enqueue_eval(ctx, xb, 1, ctx->d_sums, ctx->stream, true);
+    ctx->last_x = keep;
+    if (s != STL_OK) return s;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->dbg_b = b;
+    return STL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t stl_abi_version(void) { return STL_ABI_VERSION; }
+
+void stl_default_params(stl_params_t *p) {
+    memset(p, 0, sizeof(*p));
+    p->max_pixel_dist = 1.5; p->corr_3d_2d_threshold = 40.0; p->corr_3d_3d_threshold = 10.0;
+    p->norm_radius = 0.6; p->norm_reg_threshold = 0.02; p->min_diff_dist = 0.2;
+    p->err_weight[0] = 1.0; p->err_weight[1] = 1.0;
+    p->he_threshold = 0.094; p->valid_rate = 0.95;
+    p->max_3d_dist = 1.0; p->robust_kernel_delta = 2.98; p->robust_kernel_3ddelta = 1.0;
+    p->num_min_corr = 30; p->norm_max_pts = 30; p->norm_min_pts = 5; p->use_plane = 1;
+}
+
+stl_status_t stl_create(const stl_params_t *params, int32_t device, stl_ctx_t **out) {
+    if (!out || !params) return STL_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) { cudaGetLastError(); return STL_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return STL_ERR_NO_DEVICE;
+    if (prop.major != 10) return STL_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    if (params->norm_max_pts < 1 || params->norm_max_pts > kMaxK) return STL_ERR_CAPACITY;
+    if (cudaSetDevice(device) != cudaSuccess) return STL_ERR_CUDA;
+    stl_ctx *c = new stl_ctx();
+    c->device = device;
+    c->params = *params;
+    set_dev_params(c);
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return STL_ERR_CUDA; }
+    *out = c;
+    return STL_OK;
+}
+
+void stl_destroy(stl_ctx_t *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    drain_events(c);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    free_work(c);
+    free_pack(c);
+    lm_free(c->lm);
+    dfree(c->d_sums); dfree(c->d_lin);
+    if (c->h_cand) cudaFreeHost(c->h_cand);
+    if (c->h_sums) cudaFreeHost(c->h_sums);
+    if (c->h_lin) cudaFreeHost(c->h_lin);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *stl_last_error(const stl_ctx_t *c) { return c ? c->err.c_str() : "null context"; }
+
+stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
+    if (!ctx || !p) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (p->n_kf <= 0 || p->n_covis < 0 || p->n_covis > STL_MAX_COVIS) return fail(ctx, STL_ERR_INVALID, "bad n_kf/n_covis");
+    if (!p->scan_offset || !p->kp_offset || !p->intrinsics || !p->image_wh || !p->Tcw || !p->he_Tc || !p->he_Tl || !p->he_valid)
+        return fail(ctx, STL_ERR_INVALID, "null pack member");
+    const int F = p->n_kf, C = p->n_covis;
+    if (p->scan_offset[0] != 0 || p->kp_offset[0] != 0) return fail(ctx, STL_ERR_INVALID, "offsets must start at 0");
+    for (int f = 0; f < F; ++f)
+        if (p->scan_offset[f + 1] < p->scan_offset[f] || p->kp_offset[f + 1] < p->kp_offset[f])
+            return fail(ctx, STL_ERR_INVALID, "offsets must be non-decreasing (keyframe %d)", f);
+    free_work(ctx);
+    free_pack(ctx);
+    lm_free(ctx->lm);
+    cudaStream_t st = ctx->stream;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
+
+    // ---- per-keyframe metadata
+    std::vector<DevKf> &hk = ctx->h_kf;
+    hk.assign(F, DevKf());
+    long long pt = 0, nodes = 0, bmw = 0, gcells = 0;
+    int max_kp = 0, max_bm = 0;
+    for (int f = 0; f < F; ++f) {
+        DevKf &K = hk[f];
+        const long long n = p->scan_offset[f + 1] - p->scan_offset[f];
+        const long long nk = p->kp_offset[f + 1] - p->kp_offset[f];
+        if (n > (1 << 20)) return fail(ctx, STL_ERR_CAPACITY, "scan %d has %lld points (limit 1048576)", f, n);
+        K.n_pts = (int)n;
+        K.n_pad = (int)((n + kPadPts - 1) / kPadPts * kPadPts);
+        const int nleaf = K.n_pad / kLeaf;
+        K.n0 = std::max(32, (nleaf + 31) / 32 * 32);
+        K.n1 = std::max(32, (K.n0 / 32 + 31) / 32 * 32);
+        K.n2 = K.n1 / 32;
+        K.pt_off = pt; pt += K.n_pad;
+        K.node_off = nodes; nodes += K.n0 + K.n1 + 32;
+        K.kp_off = p->kp_offset[f];
+        K.n_kp = (int)nk;
+        K.fx = p->intrinsics[f * 4]; K.fy = p->intrinsics[f * 4 + 1]; K.cx = p->intrinsics[f * 4 + 2]; K.cy = p->intrinsics[f * 4 + 3];
+        K.W = p->image_wh[f * 2]; K.H = p->image_wh[f * 2 + 1];
+        if (K.W <= 0 || K.H <= 0 || K.W > 16384 || K.H > 16384) return fail(ctx, STL_ERR_INVALID, "bad image size of keyframe %d", f);
+        const int bw_total = (K.W + kBmCell - 1) / kBmCell + 2;
+        K.bm_wpr = (bw_total + 1 + 31) / 32;
+        K.bm_rows = (K.H + kBmCell - 1) / kBmCell + 3;
+        K.bm_off = bmw; bmw += (long long)K.bm_wpr * K.bm_rows;
+        K.gw = std::max(1, (K.W + kGridCell - 1) / kGridCell);
+        K.gh = std::max(1, (K.H + kGridCell - 1) / kGridCell);
+        K.grid_off = gcells; gcells += (long long)K.gw * K.gh + 1;
+        K.he_valid = p->he_valid[f] ? 1 : 0;
+        K.pmax = 1.f;
+        max_kp = std::max(max_kp, K.n_kp);
+        max_bm = std::max(max_bm, K.bm_wpr * K.bm_rows);
+    }
+    const long long NK = p->kp_offset[F];
+    ctx->max_kp = max_kp; ctx->max_bm_words = max_bm;
+    ctx->k1_smem = assoc2d_smem_bytes(max_kp, max_bm);
+    int smem_optin = 0;
+    CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    if (ctx->k1_smem > (size_t)smem_optin)
+        return fail(ctx, STL_ERR_CAPACITY, "K1 needs %zu B of shared memory (%d keypoints); device limit %d", ctx->k1_smem, max_kp, smem_optin);
+    CK(assoc2d_configure(ctx->k1_smem));
+
+    // ---- keypoint bitmap + cell grid (host, candidate-independent)
+    std::vector<uint32_t> bitmap((size_t)bmw, 0u), gstart((size_t)gcells, 0u), gkp((size_t)std::max<long long>(NK, 1), 0u);
+    const double Rdil = ctx->params.max_pixel_dist + (double)kFastErrPx;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int f = 0; f < F; ++f) {
+        const DevKf &K = hk[f];
+        uint32_t *bm = bitmap.data() + K.bm_off;
+        uint32_t *gs = gstart.data() + K.grid_off;
+        uint32_t *gk = gkp.data() + K.kp_off;
+        const float *kp = p->kp_xy + K.kp_off * 2;
+        const int bw_total = (K.W + kBmCell - 1) / kBmCell + 2, bh_total = (K.H + kBmCell - 1) / kBmCell + 2;
+        const int ncell = K.gw * K.gh;
+        std::vector<uint32_t> cell(K.n_kp);
+        for (int k = 0; k < K.n_kp; ++k) {
+            const double kx = kp[k * 2], ky = kp[k * 2 + 1];
+            int gx = (int)std::floor(kx / kGridCell), gy = (int)std::floor(ky / kGridCell);
+            gx = std::min(std::max(gx, 0), K.gw - 1); gy = std::min(std::max(gy, 0), K.gh - 1);
+            if (!(kx == kx) || !(ky == ky)) { gx = 0; gy = 0; }
+            cell[k] = (uint32_t)(gy * K.gw + gx);
+            gs[cell[k] + 1]++;
+            if (!(kx == kx) || !(ky == ky)) continue;
+            int c0 = (int)std::floor((kx - Rdil) / kBmCell) + 1, c1 = (int)std::floor((kx + Rdil) / kBmCell) + 1;
+            int r0 = (int)std::floor((ky - Rdil) / kBmCell) + 1, r1 = (int)std::floor((ky + Rdil) / kBmCell) + 1;
+            c0 = std::max(c0, 0); r0 = std::max(r0, 0); c1 = std::min(c1, bw_total - 1); r1 = std::min(r1, bh_total - 1);
+            for (int r = r0; r <= r1; ++r)
+                for (int cc = c0; cc <= c1; ++cc) bm[r * K.bm_wpr + (cc >> 5)] |= 1u << (cc & 31);
+        }
+        for (int i = 0; i < ncell; ++i) gs[i + 1] += gs[i];
+        std::vector<uint32_t> cur(gs, gs + ncell);
+        for (int k = 0; k < K.n_kp; ++k) gk[cur[cell[k]]++] = (uint32_t)k;
+    }
+
+    // ---- device allocation + small uploads
+    DevPack &pk = ctx->pk;
+    pk.n_kf = F; pk.n_covis = C; pk.n_pad_total = pt; pk.n_nodes_total = nodes; pk.n_kp_total = NK;
+    ctx->n_pts_total = p->scan_offset[F];
+    const size_t npt = (size_t)std::max<long long>(pt, 4), nkk = (size_t)std::max<long long>(NK, 1);
+    CK(cudaMalloc(&pk.kf, sizeof(DevKf) * F));
+    CK(cudaMalloc(&pk.px, 4 * npt)); CK(cudaMalloc(&pk.py, 4 * npt)); CK(cudaMalloc(&pk.pz, 4 * npt)); CK(cudaMalloc(&pk.orig, 4 * npt));
+    CK(cudaMalloc(&pk.node_lo, sizeof(float4) * nodes)); CK(cudaMalloc(&pk.node_hi, sizeof(float4) * nodes));
+    CK(cudaMalloc(&pk.bitmap, 4 * (size_t)bmw)); CK(cudaMalloc(&pk.grid_start, 4 * (size_t)gcells)); CK(cudaMalloc(&pk.grid_kp, 4 * nkk));
+    CK(cudaMalloc(&pk.kp_xy, sizeof(float2) * nkk)); CK(cudaMalloc(&pk.kp_mp, 12 * nkk));
+    CK(cudaMalloc(&pk.Tcw, 48 * (size_t)F)); CK(cudaMalloc(&pk.relpose, 48 * (size_t)std::max(F * C, 1)));
+    CK(cudaMalloc(&pk.covis_valid, (size_t)std::max(F * C, 1))); CK(cudaMalloc(&pk.covis_uv, sizeof(float2) * std::max<size_t>(nkk * C, 1)));
+    CK(cudaMalloc(&pk.he_Tc, 48 * (size_t)F)); CK(cudaMalloc(&pk.he_Tl, 96 * (size_t)F));
+    CK(cudaMemcpyAsync(pk.kf, hk.data(), sizeof(DevKf) * F, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(pk.bitmap, bitmap.data(), 4 * (size_t)bmw, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(pk.grid_start, gstart.data(), 4 * (size_t)gcells, cudaMemcpyHostToDevice, st));
+    if (NK > 0) {
+        CK(cudaMemcpyAsync(pk.grid_kp, gkp.data(), 4 * (size_t)NK, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(pk.kp_xy, p->kp_xy, 8 * (size_t)NK, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(pk.kp_mp, p->kp_mappoint, 12 * (size_t)NK, cudaMemcpyHostToDevice, st));
+        if (C > 0) CK(cudaMemcpyAsync(pk.covis_uv, p->covis_uv, 8 * (size_t)NK * C, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(pk.Tcw, p->Tcw, 48 * (size_t)F, cudaMemcpyHostToDevice, st));
+    if (C > 0) {
+        CK(cudaMemcpyAsync(pk.relpose, p->covis_relpose, 48 * (size_t)F * C, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(pk.covis_valid, p->covis_valid, (size_t)F * C, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(pk.he_Tc, p->he_Tc, 48 * (size_t)F, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(pk.he_Tl, p->he_Tl, 96 * (size_t)F, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+
+    // ---- scans: chunked upload + index build
+    {
+        const long long chunk_pts = 32ll << 20;
+        float *d_raw = nullptr;
+        long long raw_cap = 0;
+        int f0 = 0;
+        while (f0 < F) {
+            int f1 = f0 + 1;
+            while (f1 < F && p->scan_offset[f1 + 1] - p->scan_offset[f0] <= chunk_pts && f1 - f0 < 32768) ++f1;
+            const long long n = p->scan_offset[f1] - p->scan_offset[f0];
+            if (n > raw_cap) { dfree(d_raw); raw_cap = std::max(n, std::min(chunk_pts, (long long)ctx->n_pts_total)); CK(cudaMalloc(&d_raw, 12 * (size_t)std::max<long long>(raw_cap, 1))); }
+            if (n > 0) CK(cudaMemcpyAsync(d_raw, p->scan_xyz + p->scan_offset[f0] * 3, 12 * (size_t)n, cudaMemcpyHostToDevice, st));
+            std::vector<long long> off(f1 - f0 + 1);
+            for (int f = f0; f <= f1; ++f) off[f - f0] = p->scan_offset[f];
+            cudaError_t e = build_scan_index(d_raw, off.data(), f1 - f0, f0, hk.data(), pk, st);
+            if (e != cudaSuccess) { dfree(d_raw); return fail(ctx, STL_ERR_CUDA, "index build: %s", cudaGetErrorString(e)); }
+            f0 = f1;
+        }
+        dfree(d_raw);
+    }
+    CK(cudaMemcpy(hk.data(), pk.kf, sizeof(DevKf) * F, cudaMemcpyDeviceToHost));  // pmax filled by the build
+    cudaEventRecord(ev1, st);
+    cudaEventSynchronize(ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    ctx->stage_ms[STL_STAGE_BUILD] += ms;
+    ctx->stage_n[STL_STAGE_BUILD] += 1;
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    ctx->has_pack = true;
+    return STL_OK;
+}
+
+stl_status_t stl_eval_batch_device(stl_ctx_t *ctx, const double *x, int32_t B, double *d_sums, void *stream) {
+    if (!ctx || !x || !d_sums || B <= 0) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->has_pack) return fail(ctx, STL_ERR_STATE, "stl_upload_pack has not been called");
+    CK(cudaSetDevice(ctx->device));
+    return enqueue_eval(ctx, x, B, d_sums, stream ? (cudaStream_t)stream : ctx->stream, false);
+}
+
+stl_status_t stl_eval_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl_eval_sums_t *sums) {
+    if (!ctx || !x || !sums || B <= 0) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->has_pack) return fail(ctx, STL_ERR_STATE, "stl_upload_pack has not been called");
+    CK(cudaSetDevice(ctx->device));
+    stl_status_t s = ensure_work(ctx, B, false);
+    if (s != STL_OK) return s;
+    s = enqueue_eval(ctx, x, B, ctx->d_sums, ctx->stream, false);
+    if (s != STL_OK) return s;
+    CK(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums, sizeof(double) * STL_EVAL_NSUMS * B, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(sums, ctx->h_sums, sizeof(double) * STL_EVAL_NSUMS * B);
+    double q3 = 0;
+    for (int b = 0; b < B; ++b) q3 += sums[b].cnt_3d3d;
+    ctx->counters[2] = ctx->params.err_weight[1] > 1e-10 ? q3 : 0.0;
+    ctx->counters[3] = (ctx->params.use_plane && ctx->params.err_weight[1] > 1e-10) ? q3 : 0.0;
+    return STL_OK;
+}
+
+void stl_finalize(const stl_params_t *pr, const stl_eval_sums_t *s, stl_ba_error_t *o) {
+    // iba_global.cpp:330-343
+    if (s->valid_3d2d == 0 && pr->err_weight[0] > 1e-10) o->f1 = DBL_MAX; else o->f1 = s->sum_3d2d / s->valid_3d2d;
+    if (s->valid_3d3d == 0 && pr->err_weight[1] > 1e-10) o->f2 = DBL_MAX; else o->f2 = s->sum_3d3d / s->valid_3d3d;
+    o->C = s->sum_he / s->cnt_he;
+    o->valid_cnt_3d_2d = (int32_t)s->valid_3d2d;
+    o->cnt_3d_2d = (int32_t)s->cnt_3d2d;
+}
+
+void stl_bbo(const stl_params_t *pr, const stl_ba_error_t *e, double bbo[4]) {
+    // iba_global.cpp:386-388
+    bbo[0] = e->f1 * pr->err_weight[0] + e->f2 * pr->err_weight[1];
+    bbo[1] = e->C - pr->he_threshold;
+    bbo[2] = -e->C - pr->he_threshold;
+    bbo[3] = pr->valid_rate - (double)e->valid_cnt_3d_2d / (e->cnt_3d_2d + 1);
+}
+
+stl_status_t stl_debug_corrset(stl_ctx_t *ctx, int32_t b, int32_t kf, uint32_t *kp_idx, uint32_t *pt_idx, int32_t cap, int32_t *n) {
+    if (!ctx || !n) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    stl_status_t s = run_debug(ctx, b);
+    if (s != STL_OK) return s;
+    if (kf < 0 || kf >= ctx->pk.n_kf) return fail(ctx, STL_ERR_INVALID, "keyframe out of range");
+    int nc = 0;
+    CK(cudaMemcpy(&nc, ctx->wk.n_corr + kf, 4, cudaMemcpyDeviceToHost));
+    *n = nc;
+    const int m = std::min(nc, cap);
+    if (m > 0 && kp_idx) CK(cudaMemcpy(kp_idx, ctx->wk.corr_kp + ctx->h_kf[kf].kp_off, 4 * (size_t)m, cudaMemcpyDeviceToHost));
+    if (m > 0 && pt_idx) CK(cudaMemcpy(pt_idx, ctx->wk.corr_pt + ctx->h_kf[kf].kp_off, 4 * (size_t)m, cudaMemcpyDeviceToHost));
+    return STL_OK;
+}
+
+stl_status_t stl_debug_align(stl_ctx_t *ctx, int32_t b, int32_t kf, uint32_t *kp_idx, uint32_t *nn_idx, int32_t *n_neigh, int32_t *is_plane,
+                             double *dist, uint32_t *knn_idx, int32_t cap, int32_t *n) {
+    if (!ctx || !n) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    stl_status_t s = run_debug(ctx, b);
+    if (s != STL_OK) return s;
+    if (kf < 0 || kf >= ctx->pk.n_kf) return fail(ctx, STL_ERR_INVALID, "keyframe out of range");
+    int nq = 0;
+    CK(cudaMemcpy(&nq, ctx->wk.n_q + kf, 4, cudaMemcpyDeviceToHost));
+    *n = nq;
+    const int m = std::min(nq, cap);
+    if (m <= 0) return STL_OK;
+    const long long off = ctx->h_kf[kf].kp_off;
+    if (kp_idx) {
+        int nc = 0;
+        CK(cudaMemcpy(&nc, ctx->wk.n_corr + kf, 4, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> qc(m), ck(std::max(nc, 1));
+        CK(cudaMemcpy(qc.data(), ctx->wk.q_corr + off, 4 * (size_t)m, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(ck.data(), ctx->wk.corr_kp + off, 4 * (size_t)nc, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; ++i) kp_idx[i] = ck[qc[i]];
+    }
+    if (nn_idx) CK(cudaMemcpy(nn_idx, ctx->wk.dbg_nn + off, 4 * (size_t)m, cudaMemcpyDeviceToHost));
+    if (n_neigh) CK(cudaMemcpy(n_neigh, ctx->wk.dbg_m + off, 4 * (size_t)m, cudaMemcpyDeviceToHost));
+    if (is_plane) CK(cudaMemcpy(is_plane, ctx->wk.dbg_plane + off, 4 * (size_t)m, cudaMemcpyDeviceToHost));
+    if (dist) CK(cudaMemcpy(dist, ctx->wk.dbg_dist + off, 8 * (size_t)m, cudaMemcpyDeviceToHost));
+    if (knn_idx) CK(cudaMemcpy(knn_idx, ctx->wk.dbg_knn + off * kMaxK, 4 * (size_t)m * kMaxK, cudaMemcpyDeviceToHost));
+    return STL_OK;
+}
+
+stl_status_t stl_knn3d(stl_ctx_t *ctx, int32_t kf, const double *q, int32_t nq, int32_t k, double radius2, uint32_t *out_idx, double *out_d2,
+                       int32_t *out_count) {
+    if (!ctx || !q || nq < 0 || k < 1 || k > kMaxK) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->has_pack) return fail(ctx, STL_ERR_STATE, "no pack uploaded");
+    if (kf < 0 || kf >= ctx->pk.n_kf) return fail(ctx, STL_ERR_INVALID, "keyframe out of range");
+    if (nq == 0) return STL_OK;
+    CK(cudaSetDevice(ctx->device));
+    double *dq = nullptr, *dd = nullptr; uint32_t *di = nullptr; int *dc = nullptr;
+    CK(cudaMalloc(&dq, 24 * (size_t)nq)); CK(cudaMalloc(&dd, 8 * (size_t)nq * k)); CK(cudaMalloc(&di, 4 * (size_t)nq * k)); CK(cudaMalloc(&dc, 4 * (size_t)nq));
+    CK(cudaMemcpyAsync(dq, q, 24 * (size_t)nq, cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = launch_knn3d(ctx->pk, kf, dq, nq, k, radius2, di, dd, dc, ctx->stream);
+    if (e == cudaSuccess && out_idx) e = cudaMemcpyAsync(out_idx, di, 4 * (size_t)nq * k, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && out_d2) e = cudaMemcpyAsync(out_d2, dd, 8 * (size_t)nq * k, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && out_count) e = cudaMemcpyAsync(out_count, dc, 4 * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dq); cudaFree(dd); cudaFree(di); cudaFree(dc);
+    if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "knn3d: %s", cudaGetErrorString(e));
+    return STL_OK;
+}
+
+// ---- LM path -------------------------------------------------------------------
+
+stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[3]) {
+    if (!ctx || !x0) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->has_pack) return fail(ctx, STL_ERR_STATE, "stl_upload_pack has not been called");
+    CK(cudaSetDevice(ctx->device));
+    stl_status_t s = ensure_work(ctx, 1, false);
+    if (s != STL_OK) return s;
+    DevCand *hc = ctx->h_cand;
+    make_candidate(x0, hc);
+    CK(cudaMemcpyAsync(ctx->wk.cand, hc, sizeof(DevCand), cudaMemcpyHostToDevice, ctx->stream));
+    // 2-D association at x0 (FindProjectCorrespondences, iba_local.cpp:191) reuses K1
+    { StageTimer t(ctx, STL_STAGE_ASSOC2D, ctx->stream); CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, ctx->stream)); }
+    cudaError_t e;
+    { StageTimer t(ctx, 5, ctx->stream); e = lm_associate(ctx->pk, ctx->wk, ctx->dpr, ctx->lm, ctx->stream); }
+    if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "associate: %s", cudaGetErrorString(e));
+    if (n_blocks) { n_blocks[0] = ctx->lm.n_blocks[0]; n_blocks[1] = ctx->lm.n_blocks[1]; n_blocks[2] = ctx->lm.n_blocks[2]; }
+    ctx->dbg_b = -1;
+    ctx->last_x.clear();
+    return STL_OK;
+}
+
+static stl_status_t lin_enqueue(stl_ctx *ctx, const double *x, int B, double *d_out, cudaStream_t st) {
+    if (!ctx->lm.ready) return fail(ctx, STL_ERR_STATE, "stl_associate has not been called");
+    cudaError_t e;
+    { StageTimer t(ctx, STL_STAGE_LINEARIZE, st); e = lm_linearize(ctx->pk, ctx->dpr, ctx->lm, x, B, d_out, st); }
+    if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "linearize: %s", cudaGetErrorString(e));
+    return STL_OK;
+}
+
+stl_status_t stl_linearize_batch_device(stl_ctx_t *ctx, const double *x, int32_t B, double *d_out, void *stream) {
+    if (!ctx || !x || !d_out || B <= 0) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    return lin_enqueue(ctx, x, B, d_out, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+stl_status_t stl_linearize_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl_lin_sums_t *out) {
+    if (!ctx || !x || !out || B <= 0) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (B > ctx->lin_cap) {
+        dfree(ctx->d_lin);
+        if (ctx->h_lin) cudaFreeHost(ctx->h_lin);
+        ctx->h_lin = nullptr;
+        CK(cudaMalloc(&ctx->d_lin, sizeof(double) * STL_LIN_NSUMS * B));
+        CK(cudaMallocHost(&ctx->h_lin, sizeof(double) * STL_LIN_NSUMS * B));
+        ctx->lin_cap = B;
+    }
+    stl_status_t s = lin_enqueue(ctx, x, B, ctx->d_lin, ctx->stream);
+    if (s != STL_OK) return s;
+    CK(cudaMemcpyAsync(ctx->h_lin, ctx->d_lin, sizeof(double) * STL_LIN_NSUMS * B, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->h_lin, sizeof(double) * STL_LIN_NSUMS * B);
+    return STL_OK;
+}
+
+// ---- measurement -----------------------------------------------------------------
+
+stl_status_t stl_set_profiling(stl_ctx_t *ctx, int32_t enabled) {
+    if (!ctx) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->profiling = enabled != 0;
+    return STL_OK;
+}
+
+stl_status_t stl_stage_stats(stl_ctx_t *ctx, double ms[STL_NSTAGES], int64_t launches[STL_NSTAGES]) {
+    if (!ctx) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
+    drain_events(ctx);
+    for (int i = 0; i < STL_NSTAGES; ++i) {
+        if (ms) ms[i] = ctx->stage_ms[i];
+        if (launches) launches[i] = ctx->stage_n[i];
+        ctx->stage_ms[i] = 0;
+        ctx->stage_n[i] = 0;
+    }
+    return STL_OK;
+}
+
+stl_status_t stl_work_counters(stl_ctx_t *ctx, double out[8]) {
+    if (!ctx || !out) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    memcpy(out, ctx->counters, sizeof(ctx->counters));
+    return STL_OK;
+}
+
+}  // extern "C"

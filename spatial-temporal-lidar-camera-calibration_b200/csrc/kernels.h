@@ -1,0 +1,73 @@
+// kernels.h — host-callable launchers of the CUDA kernels (one .cu per stage).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace stl {
+
+// Device-resident pack (all pointers are device memory owned by the context).
+struct DevPack {
+    int n_kf = 0, n_covis = 0;
+    long long n_pad_total = 0, n_nodes_total = 0, n_kp_total = 0;
+    DevKf *kf = nullptr;
+    float *px = nullptr, *py = nullptr, *pz = nullptr;
+    uint32_t *orig = nullptr;
+    float4 *node_lo = nullptr, *node_hi = nullptr;
+    uint32_t *bitmap = nullptr;
+    uint32_t *grid_start = nullptr;  // per keyframe gw*gh+1 entries
+    uint32_t *grid_kp = nullptr;     // [n_kp_total] keypoint ids sorted by cell (local ids)
+    float2 *kp_xy = nullptr;         // [n_kp_total]
+    float *kp_mp = nullptr;          // [n_kp_total][3]
+    float *Tcw = nullptr;            // [n_kf][12]
+    float *relpose = nullptr;        // [n_kf][C][12]
+    uint8_t *covis_valid = nullptr;  // [n_kf][C]
+    float2 *covis_uv = nullptr;      // [n_kp_total][C]
+    float *he_Tc = nullptr;          // [n_kf][12]
+    double *he_Tl = nullptr;         // [n_kf][12]
+};
+
+// Workspace of one candidate chunk (Bc candidates x all keyframes).
+struct DevWork {
+    int Bc = 0;            // candidates per chunk
+    int sub = 4;           // K2 sub-blocks per (candidate, keyframe)
+    DevCand *cand = nullptr;      // [Bc]
+    uint32_t *corr_kp = nullptr;  // [Bc][n_kp_total]  keypoint index of correspondence i of keyframe f at kp_off[f]+i
+    uint32_t *corr_pt = nullptr;  // [Bc][n_kp_total]  original scan index
+    uint32_t *corr_sp = nullptr;  // [Bc][n_kp_total]  sorted scan position
+    uint32_t *q_corr = nullptr;   // [Bc][n_kp_total]  correspondence indices that carry a map point
+    int *n_corr = nullptr;        // [Bc][n_kf]
+    int *n_q = nullptr;           // [Bc][n_kf]
+    FrameRec *frame = nullptr;    // [Bc][n_kf]
+    AlignRec *align = nullptr;    // [Bc][n_kf][sub]
+    // optional per-query debug (allocated on demand, Bc_dbg = 1)
+    uint32_t *dbg_nn = nullptr;   // [n_kp_total]
+    int *dbg_m = nullptr;
+    int *dbg_plane = nullptr;
+    double *dbg_dist = nullptr;
+    uint32_t *dbg_knn = nullptr;  // [n_kp_total][32]
+    int *overflow = nullptr;      // K1 survivor-list overflow counter (diagnostic)
+};
+
+// ---- index build (build.cu) ---------------------------------------------------
+// raw: [n][3] float32 device points of a chunk of keyframes; raw_off[nkf+1] host offsets.
+cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int nkf, int kf_begin, const DevKf *h_kf,
+                             DevPack &pack, cudaStream_t st);
+
+// ---- K1 (assoc2d.cu) ------------------------------------------------------------
+size_t assoc2d_smem_bytes(int max_kp, int max_bm_words);
+cudaError_t assoc2d_configure(size_t smem);
+cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, cudaStream_t st);
+
+// ---- K2 (knn3d.cu) ---------------------------------------------------------------
+cudaError_t launch_align3d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, int debug, cudaStream_t st);
+cudaError_t launch_knn3d(const DevPack &pk, int kf, const double *d_q, int nq, int k, double radius2, uint32_t *d_idx, double *d_d2,
+                         int *d_cnt, cudaStream_t st);
+
+// ---- K3 (reduce.cu) ----------------------------------------------------------------
+// out: [B][STL_EVAL_NSUMS] fp64, written (not accumulated)
+cudaError_t launch_reduce(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, double *d_out, cudaStream_t st);
+
+}  // namespace stl
