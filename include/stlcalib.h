@@ -227,6 +227,11 @@ stl_status_t stl_debug_align(stl_ctx_t *ctx, int32_t b, int32_t kf, uint32_t *kp
                              uint32_t *nn_idx, int32_t *n_neigh, int32_t *is_plane, double *dist,
                              uint32_t *knn_idx, int32_t cap, int32_t *n);
 
+/* Per-keyframe partial record of the LAST stl_eval_batch for (b, kf):
+ * out = {sum_3d2d, valid_3d2d, cnt_3d2d, sum_he, cnt_he, kept, n_corr, n_queries,
+ *        sum_3d3d, valid_3d3d, cnt_3d3d, valid_pl, valid_pt}. */
+stl_status_t stl_debug_frame(stl_ctx_t *ctx, int32_t b, int32_t kf, double out[13]);
+
 /* Stand-alone exact k-NN over scan `kf` (nanoflann findNeighbors,
  * nanoflann.hpp:1588): nq queries q[nq][3] (fp64), k <= 32, radius2 <= 0 means
  * unbounded.  out_idx/out_d2 are [nq][k] sorted ascending by (d2, index);

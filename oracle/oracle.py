@@ -37,6 +37,7 @@ _SYMS = {
     "orc_ba_error": (None, [_vp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_abi.EvalSums), _i64p, _dp]),
     "orc_finalize": (None, [C.POINTER(_abi.Params), C.POINTER(_abi.EvalSums), C.POINTER(_abi.BAErrorOut)]),
     "orc_frame_debug": (C.c_int, [_vp, _dp, C.c_int, _i64p]),
+    "orc_frame_sums": (None, [_vp, _dp, C.c_int, _dp]),
     "orc_frame_corr": (C.c_int, [_vp, _u32p, _u32p, C.c_int]),
     "orc_frame_align": (C.c_int, [_vp, _u32p, _u32p, _i32p, _i32p, _dp, _u32p, _dp, C.c_int]),
     "orc_knn3d": (None, [_vp, C.c_int, _dp, C.c_int, C.c_int, C.c_double, C.c_int, _u32p, _dp, _i32p, _i64p]),
@@ -153,6 +154,14 @@ class Oracle:
                                       apl.ctypes.data_as(_i32p), _d(ad), aknn.ctypes.data_as(_u32p), _d(anrm), cap)
         return dict(corr_kp=kp[:n], corr_pt=pt[:n], align_kp=akp[:na], align_nn=ann[:na], align_m=am[:na],
                     align_is_plane=apl[:na], align_dist=ad[:na], align_knn=aknn[:na], align_normal=anrm[:na], ties=ties)
+
+    def frame_sums(self, x, kf: int):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros(13)
+        self.lib.orc_frame_sums(self.h, _d(x), kf, _d(out))
+        names = ("sum_3d2d", "valid_3d2d", "cnt_3d2d", "sum_he", "cnt_he", "kept", "n_corr", "n_queries",
+                 "sum_3d3d", "valid_3d3d", "cnt_3d3d", "valid_pl", "valid_pt")
+        return dict(zip(names, out))
 
     def knn3d(self, kf: int, q, k: int, radius2: float = 0.0, strict: bool = False):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, 3)

@@ -339,6 +339,20 @@ class Oracle {
         eval_frame(f, Tcl, Tlc, s, acc, false, ties, &dbg);
     }
 
+    void frame_sums(const double x[7], int f, double out[13]) const {
+        double R[9], t[3], s;
+        Sim3Exp<double>(x, R, t, s);
+        Rt Tcl;
+        std::memcpy(Tcl.R, R, sizeof(R));
+        std::memcpy(Tcl.t, t, sizeof(t));
+        const Rt Tlc = inverse(Tcl);
+        FrameSums a;
+        eval_frame(f, Tcl, Tlc, s, a, false, nullptr, nullptr);
+        const double v[13] = {a.s2d, (double)a.v2d, (double)a.c2d, a.she, (double)a.che, (double)a.kept, (double)a.ncorr, (double)a.q3d_nn,
+                              a.s3d, (double)a.v3d, (double)a.c3d, (double)a.vpl, (double)a.vpt};
+        for (int i = 0; i < 13; ++i) out[i] = v[i];
+    }
+
     // Stand-alone 3-D k-NN on scan f (for the KNN parity tests); (d2, idx) order.
     size_t knn3d(int f, const double q[3], size_t k, uint32_t *idx, double *d2, bool strict, bool *tie) const {
         return knn(*trees_[f], q, k, idx, d2, strict, tie);

@@ -20,9 +20,10 @@ struct RefTree {
     RefTree(const double *pts, size_t n, int leaf) : data(n) {
         for (size_t i = 0; i < n; ++i)
             for (int d = 0; d < DIM; ++d) data[i][d] = pts[i * DIM + d];
-        kd.reset(new KD(DIM, data, leaf));
+        if (n > 0) kd.reset(new KD(DIM, data, leaf));  // the adaptor asserts on an empty set (KDTreeVectorOfVectorsAdaptor.h:86)
     }
     size_t knn(const double *q, size_t k, uint32_t *idx, double *d2) const {
+        if (!kd) return 0;
         nanoflann::KNNResultSet<double, std::uint32_t> rs(k);
         rs.init(idx, d2);
         kd->index->findNeighbors(rs, q, nanoflann::SearchParameters());

@@ -35,3 +35,5 @@ for b in range(min(B, 2)):
         print(f"b{b} kf{kf}: corr n={len(kp)}/{len(d['corr_kp'])} ok={ok}  align n={len(al['nn'])}/{len(d['align_nn'])} idx={ok2} knn={ok3} max|ddist|={derr:.3e}")
         bad += (not ok) + (not ok2) + (not ok3)
 print("BAD", bad)
+for kf in range(min(nkf, 3)):
+    print("frame", kf, "gpu", ctx.debug_frame(0, kf)); print("   oracle", orc.frame_sums(X[0], kf))

@@ -125,6 +125,7 @@ CALIB_SYMBOLS = {
     "stl_debug_corrset": (C.c_int, [_vp, C.c_int32, C.c_int32, _u32p, _u32p, C.c_int32, _i32p]),
     "stl_debug_align": (C.c_int, [_vp, C.c_int32, C.c_int32, _u32p, _u32p, _i32p, _i32p, _dp, _u32p,
                                   C.c_int32, _i32p]),
+    "stl_debug_frame": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp]),
     "stl_knn3d": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32, C.c_int32, C.c_double, _u32p, _dp, _i32p]),
     "stl_set_profiling": (C.c_int, [_vp, C.c_int32]),
     "stl_stage_stats": (C.c_int, [_vp, _dp, _i64p]),

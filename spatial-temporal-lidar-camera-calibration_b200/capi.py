@@ -132,6 +132,13 @@ class Context:
         k = n.value
         return dict(kp=kp[:k], nn=nn[:k], m=m[:k], is_plane=pl[:k], dist=d[:k], knn=knn[:k])
 
+    def debug_frame(self, b: int, kf: int):
+        out = np.zeros(13)
+        _check(self.lib, self.h, self.lib.stl_debug_frame(self.h, b, kf, out.ctypes.data_as(_dp)))
+        names = ("sum_3d2d", "valid_3d2d", "cnt_3d2d", "sum_he", "cnt_he", "kept", "n_corr", "n_queries",
+                 "sum_3d3d", "valid_3d3d", "cnt_3d3d", "valid_pl", "valid_pt")
+        return dict(zip(names, out))
+
     def knn3d(self, kf: int, q, k: int, radius2: float = 0.0):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, 3)
         nq = q.shape[0]

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -40,6 +41,7 @@ struct stl_ctx {
     DevCand *h_cand = nullptr;  // pinned
     double *h_sums = nullptr;   // pinned
     int h_cap = 0;
+    cudaEvent_t h2d_done = nullptr;  // pinned candidate staging is reused only after its copies completed
     std::vector<double> last_x;
     int dbg_b = -1;
     // LM path
@@ -88,7 +90,7 @@ void free_pack(stl_ctx *c) {
 void free_work(stl_ctx *c) {
     DevWork &w = c->wk;
     dfree(w.cand); dfree(w.corr_kp); dfree(w.corr_pt); dfree(w.corr_sp); dfree(w.q_corr); dfree(w.n_corr); dfree(w.n_q);
-    dfree(w.frame); dfree(w.align); dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn);
+    dfree(w.frame); dfree(w.align); dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn); dfree(w.dbg_stats);
     dfree(w.overflow);
     w = DevWork();
     c->wk_cap = 0;
@@ -166,6 +168,7 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
         const size_t nk = (size_t)std::max<long long>(pk.n_kp_total, 1);
         CK(cudaMalloc(&w.dbg_nn, 4 * nk)); CK(cudaMalloc(&w.dbg_m, 4 * nk)); CK(cudaMalloc(&w.dbg_plane, 4 * nk));
         CK(cudaMalloc(&w.dbg_dist, 8 * nk)); CK(cudaMalloc(&w.dbg_knn, 4 * nk * kMaxK));
+        CK(cudaMalloc(&w.dbg_stats, 64)); CK(cudaMemset(w.dbg_stats, 0, 64));
         ctx->dbg_alloc = true;
     }
     if (B > ctx->h_cap) {
@@ -188,6 +191,8 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
 stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, cudaStream_t st, bool debug) {
     stl_status_t s = ensure_work(ctx, B, debug);
     if (s != STL_OK) return s;
+    if (!ctx->h2d_done) CK(cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming));
+    CK(cudaEventSynchronize(ctx->h2d_done));
     for (int b = 0; b < B; ++b) make_candidate(x + (size_t)b * 7, ctx->h_cand + b);
     const int Bc = ctx->wk.Bc;
     for (int c0 = 0; c0 < B; c0 += Bc) {
@@ -197,6 +202,7 @@ stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, c
         { StageTimer t(ctx, STL_STAGE_KNN3D, st); CK(launch_align3d(ctx->pk, ctx->wk, ctx->dpr, nb, debug ? 1 : 0, st)); }
         { StageTimer t(ctx, STL_STAGE_REDUCE, st); CK(launch_reduce(ctx->pk, ctx->wk, ctx->dpr, nb, d_out + (size_t)c0 * STL_EVAL_NSUMS, st)); }
     }
+    CK(cudaEventRecord(ctx->h2d_done, st));
     ctx->counters[0] = (double)ctx->n_pts_total * B;
     ctx->counters[1] = (double)ctx->pk.n_kp_total * B;
     ctx->counters[4] = ((double)ctx->n_pts_total * 12.0 + (double)ctx->pk.n_kp_total * 16.0) * B;
@@ -270,6 +276,7 @@ void stl_destroy(stl_ctx_t *c) {
     if (c->h_cand) cudaFreeHost(c->h_cand);
     if (c->h_sums) cudaFreeHost(c->h_sums);
     if (c->h_lin) cudaFreeHost(c->h_lin);
+    if (c->h2d_done) cudaEventDestroy(c->h2d_done);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -525,6 +532,29 @@ stl_status_t stl_debug_align(stl_ctx_t *ctx, int32_t b, int32_t kf, uint32_t *kp
     return STL_OK;
 }
 
+stl_status_t stl_debug_frame(stl_ctx_t *ctx, int32_t b, int32_t kf, double out[13]) {
+    if (!ctx || !out) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    stl_status_t s = run_debug(ctx, b);
+    if (s != STL_OK) return s;
+    if (kf < 0 || kf >= ctx->pk.n_kf) return fail(ctx, STL_ERR_INVALID, "keyframe out of range");
+    FrameRec r;
+    CK(cudaMemcpy(&r, ctx->wk.frame + kf, sizeof(r), cudaMemcpyDeviceToHost));
+    std::vector<AlignRec> a(ctx->wk.sub);
+    CK(cudaMemcpy(a.data(), ctx->wk.align + (size_t)kf * ctx->wk.sub, sizeof(AlignRec) * ctx->wk.sub, cudaMemcpyDeviceToHost));
+    out[0] = r.s2d; out[1] = r.v2d; out[2] = r.c2d; out[3] = r.she; out[4] = r.che; out[5] = r.kept; out[6] = r.ncorr; out[7] = r.nq;
+    for (int i = 8; i < 13; ++i) out[i] = 0;
+    if (getenv("STL_DEBUG_STATS")) {
+        unsigned long long st[8];
+        cudaMemcpy(st, ctx->wk.dbg_stats, 64, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[stl] traversal stats (cumulative): queries %llu | 1-NN iters %.1f visits %.1f | k-NN iters %.1f visits %.1f inserts %.1f m %.1f\n",
+                st[0], (double)st[1] / st[0], (double)st[2] / st[0], (double)st[3] / st[0], (double)st[4] / st[0], (double)st[5] / st[0], (double)st[6] / st[0]);
+    }
+    for (auto &x : a) { out[8] += x.s3d; out[9] += x.v3d; out[10] += x.c3d; out[11] += x.vpl; out[12] += x.vpt; }
+    return STL_OK;
+}
+
 stl_status_t stl_knn3d(stl_ctx_t *ctx, int32_t kf, const double *q, int32_t nq, int32_t k, double radius2, uint32_t *out_idx, double *out_d2,
                        int32_t *out_count) {
     if (!ctx || !q || nq < 0 || k < 1 || k > kMaxK) return STL_ERR_INVALID;
@@ -556,8 +586,11 @@ stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[3]
     stl_status_t s = ensure_work(ctx, 1, false);
     if (s != STL_OK) return s;
     DevCand *hc = ctx->h_cand;
+    if (!ctx->h2d_done) CK(cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming));
+    CK(cudaEventSynchronize(ctx->h2d_done));
     make_candidate(x0, hc);
     CK(cudaMemcpyAsync(ctx->wk.cand, hc, sizeof(DevCand), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->h2d_done, ctx->stream));
     // 2-D association at x0 (FindProjectCorrespondences, iba_local.cpp:191) reuses K1
     { StageTimer t(ctx, STL_STAGE_ASSOC2D, ctx->stream); CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, ctx->stream)); }
     cudaError_t e;

@@ -48,6 +48,7 @@ struct DevWork {
     int *dbg_plane = nullptr;
     double *dbg_dist = nullptr;
     uint32_t *dbg_knn = nullptr;  // [n_kp_total][32]
+    unsigned long long *dbg_stats = nullptr;  // [8] traversal statistics (debug runs)
     int *overflow = nullptr;      // K1 survivor-list overflow counter (diagnostic)
 };
 

@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "geom.cuh"
+#include "kernels.h"
 
 namespace stl {
 
@@ -42,10 +43,12 @@ __device__ __forceinline__ unsigned order_key(double lb) { return __float_as_uin
 // ---- result sinks ---------------------------------------------------------------
 // 1-NN: (d2, orig) lexicographic minimum.  All members are warp-uniform.
 struct Sink1 {
+    int n_iter = 0, n_visit = 0, n_ins = 0;
     double d = DBL_MAX;
     uint32_t oi = 0xffffffffu, pos = 0xffffffffu;
     __device__ __forceinline__ bool may_contain(double lb) const { return lb <= d; }
     __device__ __forceinline__ void visit(const ScanView &S, int leaf, double qx, double qy, double qz, int lane) {
+        ++n_visit;
         const int g = leaf * kLeaf + lane;
         const double dd = dist3e(qx, qy, qz, (double)S.px[g], (double)S.py[g], (double)S.pz[g]);  // NaN for pads
         const bool q = dd <= d;
@@ -67,6 +70,7 @@ struct Sink1 {
 
 // k-NN (k <= 32) restricted to d2 < r2: lane j holds the j-th best (d2, orig, pos).
 struct SinkK {
+    int n_iter = 0, n_visit = 0, n_ins = 0;
     double kd = DBL_MAX;       // per lane
     uint32_t ki = 0xffffffffu, kpos = 0xffffffffu;
     int count = 0, k;          // uniform
@@ -81,6 +85,7 @@ struct SinkK {
         const int g = leaf * kLeaf + lane;
         const double dd = dist3e(qx, qy, qz, (double)S.px[g], (double)S.py[g], (double)S.pz[g]);
         const bool pre = dd < r2 && (count < k || dd <= wd);
+        ++n_visit;
         unsigned mask = __ballot_sync(kFull, pre);
         if (!mask) return;
         const uint32_t o = pre ? S.orig[g] : 0xffffffffu;
@@ -90,6 +95,7 @@ struct SinkK {
             const double cd = __shfl_sync(kFull, dd, src);
             const uint32_t ci = __shfl_sync(kFull, o, src);
             if (!accept(cd, ci)) continue;
+            ++n_ins;
             const bool less = lane < count && (kd < cd || (kd == cd && ki < ci));
             const int at = __popc(__ballot_sync(kFull, less));
             const double sd = __shfl_up_sync(kFull, kd, 1);
@@ -111,6 +117,7 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
     const unsigned key2 = order_key(lb2);
     unsigned done2 = 0;
     for (;;) {
+        ++sink.n_iter;
         const bool c2 = !((done2 >> lane) & 1u) && sink.may_contain(lb2);
         const unsigned m2 = __reduce_min_sync(kFull, c2 ? key2 : 0xffffffffu);
         if (m2 == 0xffffffffu) break;
@@ -121,6 +128,7 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
         const unsigned key1 = order_key(lb1);
         unsigned done1 = 0;
         for (;;) {
+            ++sink.n_iter;
             const bool c1 = !((done1 >> lane) & 1u) && sink.may_contain(lb1);
             const unsigned m1 = __reduce_min_sync(kFull, c1 ? key1 : 0xffffffffu);
             if (m1 == 0xffffffffu) break;
@@ -131,6 +139,7 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
             const unsigned key0 = order_key(lb0);
             unsigned done0 = 0;
             for (;;) {
+                ++sink.n_iter;
                 const bool c0 = !((done0 >> lane) & 1u) && sink.may_contain(lb0);
                 const unsigned m0 = __reduce_min_sync(kFull, c0 ? key0 : 0xffffffffu);
                 if (m0 == 0xffffffffu) break;

@@ -58,9 +58,11 @@ k_align3d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
             const double dx = dsub(nx, qx), dy = dsub(ny, qy), dz = dsub(nz, qz);
             double dist = sqrt(dot3e(dx, dy, dz, dx, dy, dz));  // pt2pt
             int is_plane = 0, m = 0;
+            int stat_k[3] = {0, 0, 0};
             if (pr.use_plane) {
                 SinkK kn(pr.k, pr.radius2);
                 traverse(S, nx, ny, nz, kn, lane);
+                stat_k[0] = kn.n_iter; stat_k[1] = kn.n_visit; stat_k[2] = kn.n_ins;
                 const PlaneOut po = plane_from_knn(S, kn, nx, ny, nz, pr, lane);
                 m = po.m;
                 if (po.gates_ok && !(po.reg > pr.reg_thr)) {
@@ -77,6 +79,13 @@ k_align3d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
             }
             c3d += 1.0;
             if (debug && lane == 0) {
+                atomicAdd(&wk.dbg_stats[0], 1ull);
+                atomicAdd(&wk.dbg_stats[1], (unsigned long long)nn.n_iter);
+                atomicAdd(&wk.dbg_stats[2], (unsigned long long)nn.n_visit);
+                atomicAdd(&wk.dbg_stats[3], (unsigned long long)stat_k[0]);
+                atomicAdd(&wk.dbg_stats[4], (unsigned long long)stat_k[1]);
+                atomicAdd(&wk.dbg_stats[5], (unsigned long long)stat_k[2]);
+                atomicAdd(&wk.dbg_stats[6], (unsigned long long)m);
                 wk.dbg_nn[K.kp_off + qi] = nn.oi;
                 wk.dbg_m[K.kp_off + qi] = m;
                 wk.dbg_plane[K.kp_off + qi] = is_plane;

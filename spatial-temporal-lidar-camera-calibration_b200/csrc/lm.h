@@ -4,25 +4,38 @@
 
 namespace stl {
 
-// Residual block frozen by stl_associate (BuildProblem, iba_local.cpp:263-309). SoA on the device.
+// Residual blocks frozen by stl_associate (BuildProblem, src/examples/iba_local.cpp:145-323).
+// One slot per 2-D correspondence of the association pass (slot = kp_off[kf] + i); dense index
+// lists select the slots that carry a 3-D/2-D block (IBA_PlaneFactor) and a 3-D/3-D block
+// (Point2Point_Factor / Point2Plane_Factor).
 struct LmState {
     bool ready = false;
     long long n_blocks[3] = {0, 0, 0};  // plane (3-D/2-D), point-to-point, point-to-plane
-    long long cap = 0;
-    int *count = nullptr;       // device counters [3] + total
-    int *b_type = nullptr;      // [cap] 0/1/2
-    int *b_kf = nullptr;        // [cap]
-    uint32_t *b_kp = nullptr;   // [cap]
-    double *b_geo = nullptr;    // [cap][9]: plane: p0[3], n0[3], -  |  3-D: map_pt[3], query_pt[3], normal[3]
-    double *partial = nullptr;  // linearisation partials
+    long long n_slots = 0;
+    int *slot_kf = nullptr;       // [n_slots]
+    uint32_t *slot_kp = nullptr;  // [n_slots]
+    uint8_t *flag2d = nullptr;    // [n_slots] 1 = plane block
+    uint8_t *type3d = nullptr;    // [n_slots] 0 none, 1 point-to-point, 2 point-to-plane
+    uint8_t *flag3d = nullptr;    // [n_slots] type3d != 0
+    double *geo2d = nullptr;      // [n_slots][6]  p0 (scan point, LiDAR frame), n0 (normal)
+    double *geo3d = nullptr;      // [n_slots][9]  map point (camera frame, unscaled), query point, normal
+    int *idx2d = nullptr, *idx3d = nullptr;  // [n_slots] dense slot lists
+    int *d_counts = nullptr;      // [2]
+    int n2d = 0, n3d = 0;
+    void *d_tmp = nullptr;        // cub scratch
+    size_t tmp_bytes = 0;
+    double *partial = nullptr;    // [B][grid][kLinVals]
     long long partial_cap = 0;
-    double *d_x = nullptr;      // [B][LmCand] device candidates
-    long long x_cap = 0;
-    void *h_x = nullptr;        // pinned staging
+    void *d_cand = nullptr;       // [B] LmCand
+    void *h_cand = nullptr;       // pinned
+    int cand_cap = 0;
+    cudaEvent_t h2d_done = nullptr;  // guards the pinned staging buffer against reuse while a copy is in flight
 };
 
 void lm_free(LmState &lm);
+// wk must hold the K1 result (correspondences) of the association extrinsic at candidate slot 0.
 cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st);
+// x: HOST [B][7]; d_out: DEVICE [B][STL_LIN_NSUMS]
 cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st);
 
 }  // namespace stl

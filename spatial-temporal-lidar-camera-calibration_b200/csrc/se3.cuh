@@ -37,16 +37,33 @@ __device__ inline void se3_log(const double *Rin, const double *t, double *out) 
         q[1] = (Rin[2] - Rin[6]) * s;
         q[2] = (Rin[3] - Rin[1]) * s;
     } else {
+        // i = index of the largest diagonal entry, (i, j, k) cyclic; written out per case so that
+        // nothing is indexed dynamically (keeps q[] in registers)
         int i = 0;
         if (Rin[4] > Rin[0]) i = 1;
-        if (Rin[8] > Rin[i * 4]) i = 2;
-        const int j = (i + 1) % 3, k = (j + 1) % 3;
-        double s = sqrt(Rin[i * 4] - Rin[j * 4] - Rin[k * 4] + 1.0);
-        q[i] = 0.5 * s;
-        s = 0.5 / s;
-        q[3] = (Rin[k * 3 + j] - Rin[j * 3 + k]) * s;
-        q[j] = (Rin[j * 3 + i] + Rin[i * 3 + j]) * s;
-        q[k] = (Rin[k * 3 + i] + Rin[i * 3 + k]) * s;
+        if (Rin[8] > (i == 0 ? Rin[0] : Rin[4])) i = 2;
+        if (i == 0) {  // j = 1, k = 2
+            double s = sqrt(Rin[0] - Rin[4] - Rin[8] + 1.0);
+            q[0] = 0.5 * s;
+            s = 0.5 / s;
+            q[3] = (Rin[7] - Rin[5]) * s;
+            q[1] = (Rin[3] + Rin[1]) * s;
+            q[2] = (Rin[6] + Rin[2]) * s;
+        } else if (i == 1) {  // j = 2, k = 0
+            double s = sqrt(Rin[4] - Rin[8] - Rin[0] + 1.0);
+            q[1] = 0.5 * s;
+            s = 0.5 / s;
+            q[3] = (Rin[2] - Rin[6]) * s;
+            q[2] = (Rin[7] + Rin[5]) * s;
+            q[0] = (Rin[1] + Rin[3]) * s;
+        } else {  // j = 0, k = 1
+            double s = sqrt(Rin[8] - Rin[0] - Rin[4] + 1.0);
+            q[2] = 0.5 * s;
+            s = 0.5 / s;
+            q[3] = (Rin[3] - Rin[1]) * s;
+            q[0] = (Rin[2] + Rin[6]) * s;
+            q[1] = (Rin[5] + Rin[7]) * s;
+        }
     }
     if (q[3] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
     const double n = sqrt(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]);
