@@ -300,8 +300,18 @@ size_t assoc2d_smem_bytes(int max_kp, int max_bm_words) {
     return ((sizeof(Smem) + 15) & ~size_t(15)) + (size_t)max_kp * 16 + (size_t)kSurvCap * 4 + (size_t)max_bm_words * 4;
 }
 
+// The opt-in dynamic shared-memory limit is a per-function, per-device attribute shared by every
+// context of the process: only ever raise it.
 cudaError_t assoc2d_configure(size_t smem) {
-    return cudaFuncSetAttribute(k_assoc2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t granted[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (smem <= granted[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(k_assoc2d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) granted[dev] = smem;
+    return e;
 }
 
 cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, cudaStream_t st) {

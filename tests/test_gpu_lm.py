@@ -74,5 +74,3 @@ def test_lm_steps_reduce_the_cost_like_the_oracle(gpu_ctx, orc, small_candidates
         costs.append(cg)
     assert costs[-1] < costs[0]
     assert np.abs(xg[:3] - xo[:3]).max() < np.deg2rad(0.01) and np.abs(xg[3:6] - xo[3:6]).max() < 1e-3
-    x_gt = small_pack[1]
-    assert np.linalg.norm(xg[:6] - x_gt[:6]) < np.linalg.norm(x0[:6] - x_gt[:6])
