@@ -248,6 +248,12 @@ stl_status_t stl_knn3d(stl_ctx_t *ctx, int32_t kf, const double *q, int32_t nq, 
 #define STL_STAGE_BUILD 4    /* one-off index build of stl_upload_pack        */
 #define STL_NSTAGES 8
 
+/* Sets the CUDA stream (a cudaStream_t) on which the calls WITHOUT an explicit stream argument
+ * enqueue their work (NULL = the context's own stream).  A context's calls share one workspace:
+ * whenever the stream changes from one call to the next, the library makes the new stream wait
+ * for the work already queued on the previous one. */
+stl_status_t stl_set_stream(stl_ctx_t *ctx, void *stream);
+
 /* When enabled, every stage launch is bracketed by CUDA events on its stream;
  * stl_stage_stats returns accumulated milliseconds / launch counts since the
  * last reset and resets them. */
@@ -256,7 +262,8 @@ stl_status_t stl_stage_stats(stl_ctx_t *ctx, double ms[STL_NSTAGES], int64_t lau
 
 /* Work counters of the last stl_eval_batch (host-side, summed over b):
  * [0] points streamed by K1, [1] 2-D 1-NN queries (= keypoints),
- * [2] 3-D 1-NN queries, [3] 3-D k-NN queries, [4] algorithmic bytes of K1. */
+ * [2] 3-D 1-NN queries, [3] 3-D k-NN queries, [4] algorithmic bytes of K1,
+ * [5] kernels of this library launched by the context since its creation. */
 stl_status_t stl_work_counters(stl_ctx_t *ctx, double out[8]);
 
 #ifdef __cplusplus

@@ -127,6 +127,7 @@ CALIB_SYMBOLS = {
                                   C.c_int32, _i32p]),
     "stl_debug_frame": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp]),
     "stl_knn3d": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32, C.c_int32, C.c_double, _u32p, _dp, _i32p]),
+    "stl_set_stream": (C.c_int, [_vp, _vp]),
     "stl_set_profiling": (C.c_int, [_vp, C.c_int32]),
     "stl_stage_stats": (C.c_int, [_vp, _dp, _i64p]),
     "stl_work_counters": (C.c_int, [_vp, _dp]),

@@ -151,6 +151,10 @@ class Context:
         return idx, d2, cnt
 
     # -- measurement -------------------------------------------------------------
+    def set_stream(self, stream_ptr: int = 0):
+        """All later calls without an explicit stream enqueue on this cudaStream_t (0 = the context's own)."""
+        _check(self.lib, self.h, self.lib.stl_set_stream(self.h, C.c_void_p(stream_ptr)))
+
     def set_profiling(self, on: bool):
         _check(self.lib, self.h, self.lib.stl_set_profiling(self.h, int(on)))
 
@@ -163,4 +167,4 @@ class Context:
     def work_counters(self):
         out = np.zeros(8)
         _check(self.lib, self.h, self.lib.stl_work_counters(self.h, out.ctypes.data_as(_dp)))
-        return dict(points=out[0], q2d=out[1], q3d_nn=out[2], q3d_knn=out[3], k1_bytes=out[4])
+        return dict(points=out[0], q2d=out[1], q3d_nn=out[2], q3d_knn=out[3], k1_bytes=out[4], launches=out[5])

@@ -23,7 +23,11 @@ struct stl_ctx {
     int device = 0;
     stl_params_t params;
     DevParams dpr;
-    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;   // created by the context
+    cudaStream_t stream = nullptr;       // default stream of calls without an explicit one (stl_set_stream)
+    cudaStream_t last_stream = nullptr;  // stream of the previous call: a change inserts an event dependency
+    cudaEvent_t handoff = nullptr;
+    long long launches = 0;
     std::mutex mu;
     std::string err;
     bool has_pack = false;
@@ -69,6 +73,20 @@ stl_status_t fail(stl_ctx *c, stl_status_t code, const char *fmt, ...) {
     va_end(ap);
     if (c) c->err = buf;
     return code;
+}
+
+// Every call of a context runs on ONE stream at a time (they share the workspace): when the
+// stream changes, the new one waits for the work already queued on the previous one.
+cudaStream_t acquire_stream(stl_ctx *c, void *requested) {
+    cudaStream_t st = requested ? (cudaStream_t)requested : c->stream;
+    if (st != c->last_stream) {
+        if (c->last_stream) {
+            cudaEventRecord(c->handoff, c->last_stream);
+            cudaStreamWaitEvent(st, c->handoff, 0);
+        }
+        c->last_stream = st;
+    }
+    return st;
 }
 
 #define CK(call)                                                                                          \
@@ -201,6 +219,7 @@ stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, c
         { StageTimer t(ctx, STL_STAGE_ASSOC2D, st); CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_smem, st)); }
         { StageTimer t(ctx, STL_STAGE_KNN3D, st); CK(launch_align3d(ctx->pk, ctx->wk, ctx->dpr, nb, debug ? 1 : 0, st)); }
         { StageTimer t(ctx, STL_STAGE_REDUCE, st); CK(launch_reduce(ctx->pk, ctx->wk, ctx->dpr, nb, d_out + (size_t)c0 * STL_EVAL_NSUMS, st)); }
+        ctx->launches += 3;
     }
     CK(cudaEventRecord(ctx->h2d_done, st));
     ctx->counters[0] = (double)ctx->n_pts_total * B;
@@ -220,10 +239,11 @@ stl_status_t run_debug(stl_ctx *ctx, int b) {
     memcpy(xb, &keep[(size_t)b * 7], sizeof(xb));
     stl_status_t s = ensure_work(ctx, 1, true);
     if (s != STL_OK) return s;
-    s = enqueue_eval(ctx, xb, 1, ctx->d_sums, ctx->stream, true);
+    cudaStream_t st = acquire_stream(ctx, nullptr);
+    s = enqueue_eval(ctx, xb, 1, ctx->d_sums, st, true);
     ctx->last_x = keep;
     if (s != STL_OK) return s;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(st));
     ctx->dbg_b = b;
     return STL_OK;
 }
@@ -258,7 +278,10 @@ stl_status_t stl_create(const stl_params_t *params, int32_t device, stl_ctx_t **
     c->device = device;
     c->params = *params;
     set_dev_params(c);
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return STL_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return STL_ERR_CUDA; }
+    c->stream = c->own_stream;
+    c->last_stream = c->own_stream;
+    cudaEventCreateWithFlags(&c->handoff, cudaEventDisableTiming);
     *out = c;
     return STL_OK;
 }
@@ -277,7 +300,8 @@ void stl_destroy(stl_ctx_t *c) {
     if (c->h_sums) cudaFreeHost(c->h_sums);
     if (c->h_lin) cudaFreeHost(c->h_lin);
     if (c->h2d_done) cudaEventDestroy(c->h2d_done);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->handoff) cudaEventDestroy(c->handoff);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -298,7 +322,7 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     free_work(ctx);
     free_pack(ctx);
     lm_free(ctx->lm);
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = acquire_stream(ctx, nullptr);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEventCreate(&ev0); cudaEventCreate(&ev1);
     cudaEventRecord(ev0, st);
@@ -447,7 +471,7 @@ stl_status_t stl_eval_batch_device(stl_ctx_t *ctx, const double *x, int32_t B, d
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!ctx->has_pack) return fail(ctx, STL_ERR_STATE, "stl_upload_pack has not been called");
     CK(cudaSetDevice(ctx->device));
-    return enqueue_eval(ctx, x, B, d_sums, stream ? (cudaStream_t)stream : ctx->stream, false);
+    return enqueue_eval(ctx, x, B, d_sums, acquire_stream(ctx, stream), false);
 }
 
 stl_status_t stl_eval_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl_eval_sums_t *sums) {
@@ -457,10 +481,11 @@ stl_status_t stl_eval_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl_eval
     CK(cudaSetDevice(ctx->device));
     stl_status_t s = ensure_work(ctx, B, false);
     if (s != STL_OK) return s;
-    s = enqueue_eval(ctx, x, B, ctx->d_sums, ctx->stream, false);
+    cudaStream_t st = acquire_stream(ctx, nullptr);
+    s = enqueue_eval(ctx, x, B, ctx->d_sums, st, false);
     if (s != STL_OK) return s;
-    CK(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums, sizeof(double) * STL_EVAL_NSUMS * B, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums, sizeof(double) * STL_EVAL_NSUMS * B, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     memcpy(sums, ctx->h_sums, sizeof(double) * STL_EVAL_NSUMS * B);
     double q3 = 0;
     for (int b = 0; b < B; ++b) q3 += sums[b].cnt_3d3d;
@@ -565,12 +590,13 @@ stl_status_t stl_knn3d(stl_ctx_t *ctx, int32_t kf, const double *q, int32_t nq, 
     CK(cudaSetDevice(ctx->device));
     double *dq = nullptr, *dd = nullptr; uint32_t *di = nullptr; int *dc = nullptr;
     CK(cudaMalloc(&dq, 24 * (size_t)nq)); CK(cudaMalloc(&dd, 8 * (size_t)nq * k)); CK(cudaMalloc(&di, 4 * (size_t)nq * k)); CK(cudaMalloc(&dc, 4 * (size_t)nq));
-    CK(cudaMemcpyAsync(dq, q, 24 * (size_t)nq, cudaMemcpyHostToDevice, ctx->stream));
-    cudaError_t e = launch_knn3d(ctx->pk, kf, dq, nq, k, radius2, di, dd, dc, ctx->stream);
-    if (e == cudaSuccess && out_idx) e = cudaMemcpyAsync(out_idx, di, 4 * (size_t)nq * k, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && out_d2) e = cudaMemcpyAsync(out_d2, dd, 8 * (size_t)nq * k, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && out_count) e = cudaMemcpyAsync(out_count, dc, 4 * (size_t)nq, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaStream_t st = acquire_stream(ctx, nullptr);
+    CK(cudaMemcpyAsync(dq, q, 24 * (size_t)nq, cudaMemcpyHostToDevice, st));
+    cudaError_t e = launch_knn3d(ctx->pk, kf, dq, nq, k, radius2, di, dd, dc, st);
+    if (e == cudaSuccess && out_idx) e = cudaMemcpyAsync(out_idx, di, 4 * (size_t)nq * k, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && out_d2) e = cudaMemcpyAsync(out_d2, dd, 8 * (size_t)nq * k, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && out_count) e = cudaMemcpyAsync(out_count, dc, 4 * (size_t)nq, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(dq); cudaFree(dd); cudaFree(di); cudaFree(dc);
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "knn3d: %s", cudaGetErrorString(e));
     return STL_OK;
@@ -585,17 +611,19 @@ stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[3]
     CK(cudaSetDevice(ctx->device));
     stl_status_t s = ensure_work(ctx, 1, false);
     if (s != STL_OK) return s;
+    cudaStream_t st = acquire_stream(ctx, nullptr);
     DevCand *hc = ctx->h_cand;
     if (!ctx->h2d_done) CK(cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming));
     CK(cudaEventSynchronize(ctx->h2d_done));
     make_candidate(x0, hc);
-    CK(cudaMemcpyAsync(ctx->wk.cand, hc, sizeof(DevCand), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaEventRecord(ctx->h2d_done, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->wk.cand, hc, sizeof(DevCand), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->h2d_done, st));
     // 2-D association at x0 (FindProjectCorrespondences, iba_local.cpp:191) reuses K1
-    { StageTimer t(ctx, STL_STAGE_ASSOC2D, ctx->stream); CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, ctx->stream)); }
+    { StageTimer t(ctx, STL_STAGE_ASSOC2D, st); CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, st)); }
     cudaError_t e;
-    { StageTimer t(ctx, 5, ctx->stream); e = lm_associate(ctx->pk, ctx->wk, ctx->dpr, ctx->lm, ctx->stream); }
+    { StageTimer t(ctx, 5, st); e = lm_associate(ctx->pk, ctx->wk, ctx->dpr, ctx->lm, st); }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "associate: %s", cudaGetErrorString(e));
+    ctx->launches += 2 + (ctx->lm.n3d > 0 ? 1 : 0);  // K1, k_lm_associate, k_count_types (cub select kernels not counted)
     if (n_blocks) { n_blocks[0] = ctx->lm.n_blocks[0]; n_blocks[1] = ctx->lm.n_blocks[1]; n_blocks[2] = ctx->lm.n_blocks[2]; }
     ctx->dbg_b = -1;
     ctx->last_x.clear();
@@ -607,6 +635,7 @@ static stl_status_t lin_enqueue(stl_ctx *ctx, const double *x, int B, double *d_
     cudaError_t e;
     { StageTimer t(ctx, STL_STAGE_LINEARIZE, st); e = lm_linearize(ctx->pk, ctx->dpr, ctx->lm, x, B, d_out, st); }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "linearize: %s", cudaGetErrorString(e));
+    ctx->launches += 2;  // k_linearize, k_lin_finish
     return STL_OK;
 }
 
@@ -614,7 +643,7 @@ stl_status_t stl_linearize_batch_device(stl_ctx_t *ctx, const double *x, int32_t
     if (!ctx || !x || !d_out || B <= 0) return STL_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
-    return lin_enqueue(ctx, x, B, d_out, stream ? (cudaStream_t)stream : ctx->stream);
+    return lin_enqueue(ctx, x, B, d_out, acquire_stream(ctx, stream));
 }
 
 stl_status_t stl_linearize_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl_lin_sums_t *out) {
@@ -629,15 +658,23 @@ stl_status_t stl_linearize_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl
         CK(cudaMallocHost(&ctx->h_lin, sizeof(double) * STL_LIN_NSUMS * B));
         ctx->lin_cap = B;
     }
-    stl_status_t s = lin_enqueue(ctx, x, B, ctx->d_lin, ctx->stream);
+    cudaStream_t st = acquire_stream(ctx, nullptr);
+    stl_status_t s = lin_enqueue(ctx, x, B, ctx->d_lin, st);
     if (s != STL_OK) return s;
-    CK(cudaMemcpyAsync(ctx->h_lin, ctx->d_lin, sizeof(double) * STL_LIN_NSUMS * B, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_lin, ctx->d_lin, sizeof(double) * STL_LIN_NSUMS * B, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     memcpy(out, ctx->h_lin, sizeof(double) * STL_LIN_NSUMS * B);
     return STL_OK;
 }
 
 // ---- measurement -----------------------------------------------------------------
+
+stl_status_t stl_set_stream(stl_ctx_t *ctx, void *stream) {
+    if (!ctx) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    return STL_OK;
+}
 
 stl_status_t stl_set_profiling(stl_ctx_t *ctx, int32_t enabled) {
     if (!ctx) return STL_ERR_INVALID;
@@ -663,6 +700,7 @@ stl_status_t stl_stage_stats(stl_ctx_t *ctx, double ms[STL_NSTAGES], int64_t lau
 stl_status_t stl_work_counters(stl_ctx_t *ctx, double out[8]) {
     if (!ctx || !out) return STL_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->counters[5] = (double)ctx->launches;
     memcpy(out, ctx->counters, sizeof(ctx->counters));
     return STL_OK;
 }
