@@ -24,3 +24,13 @@ print("K1 achieved GB/s (algorithmic): %.1f" % (wc["k1_bytes"] / k1 / 1e9))
 k2 = st["knn3d"][0] / max(st["knn3d"][1], 1) * 1e-3
 print("K2 queries/s: %.3e (nn %.0f + knn %.0f per call)" % ((wc["q3d_nn"] + wc["q3d_knn"]) / k2, wc["q3d_nn"], wc["q3d_knn"]))
 print(s[0])
+ctx.associate(X[0]); ctx.linearize(X[:1]); ctx.stage_stats()
+t = time.time()
+for _ in range(reps):
+    nb = ctx.associate(X[0]); L = ctx.linearize(X[:1])
+dt = (time.time() - t) / reps
+st = ctx.stage_stats()
+print("associate+linearize %.3f ms/call, blocks %s" % (dt * 1e3, nb.tolist()))
+for k, (ms, n) in st.items():
+    if n: print("  %-10s %.3f ms/launch x %d" % (k, ms / n, n))
+print(L[0][:3])

@@ -104,6 +104,117 @@ __global__ void k_scatter(const float *__restrict__ raw, const long long *__rest
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// KD refinement of the Morton order.  Blocks of 32 Morton-consecutive points make poor leaves
+// (the curve jumps; LiDAR returns lie on 2-D surfaces), so every aligned group of 8192 sorted
+// points (= 256 leaves = 8 of the 32-ary level-1 nodes) is re-ordered in shared memory by eight
+// rounds of "sort the segment along the longest axis of its bounding box, split in the middle"
+// — a balanced KD-tree whose cells are exactly the implicit 32-point leaves and 1024-point
+// level-1 nodes.  Halves the boxes an exact query has to open (profiles/r01_leaf_quality.txt).
+constexpr int kGroup = 8192;
+constexpr int kRefThreads = 1024;
+constexpr int kGroupLevels = 8;  // 8192 -> 32
+
+__device__ __forceinline__ int f2ord(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }
+
+struct RefineSmem {
+    float x[kGroup], y[kGroup], z[kGroup];
+    uint32_t o[kGroup];
+    float key[kGroup];
+    unsigned short perm[kGroup];
+    int bb[128][6];
+    unsigned char axis[128];
+};
+
+__device__ __forceinline__ void cmp_swap(RefineSmem &S, int i, int l) {
+    const float ki = S.key[i], kl = S.key[l];
+    const unsigned short pi = S.perm[i], pl = S.perm[l];
+    if (ki > kl || (ki == kl && pi > pl)) { S.key[i] = kl; S.key[l] = ki; S.perm[i] = pl; S.perm[l] = pi; }
+}
+
+// grid (groups, nkf)
+__global__ void __launch_bounds__(kRefThreads, 1)
+k_kd_refine(const DevKf *__restrict__ kf, int kf_begin, float *__restrict__ px, float *__restrict__ py, float *__restrict__ pz,
+            uint32_t *__restrict__ orig) {
+    extern __shared__ __align__(16) unsigned char refine_raw[];
+    RefineSmem &S = *reinterpret_cast<RefineSmem *>(refine_raw);
+    const DevKf K = kf[kf_begin + blockIdx.y];
+    const int g0 = blockIdx.x * kGroup;
+    if (g0 >= K.n_pad) return;
+    const int M = min(kGroup, K.n_pad - g0);
+    const long long base = K.pt_off + g0;
+    const int tid = threadIdx.x;
+    const float qn = __int_as_float(0x7fc00000);
+    for (int i = tid; i < kGroup; i += kRefThreads) {
+        const bool in = i < M;
+        S.x[i] = in ? px[base + i] : qn;
+        S.y[i] = in ? py[base + i] : qn;
+        S.z[i] = in ? pz[base + i] : qn;
+        S.o[i] = in ? orig[base + i] : 0xffffffffu;
+        S.perm[i] = (unsigned short)i;
+    }
+    __syncthreads();
+    for (int lev = 0; lev < kGroupLevels; ++lev) {
+        const int seg_size = kGroup >> lev, nseg = 1 << lev, seg_shift = 13 - lev;
+        for (int i = tid; i < nseg * 6; i += kRefThreads) S.bb[i / 6][i % 6] = (i % 6) < 3 ? 0x7fffffff : (int)0x80000000;
+        __syncthreads();
+        for (int i = tid; i < kGroup; i += kRefThreads) {
+            const int p = S.perm[i];
+            const float x = S.x[p];
+            if (x == x) {
+                const int sg = i >> seg_shift;
+                atomicMin(&S.bb[sg][0], f2ord(x)); atomicMax(&S.bb[sg][3], f2ord(x));
+                atomicMin(&S.bb[sg][1], f2ord(S.y[p])); atomicMax(&S.bb[sg][4], f2ord(S.y[p]));
+                atomicMin(&S.bb[sg][2], f2ord(S.z[p])); atomicMax(&S.bb[sg][5], f2ord(S.z[p]));
+            }
+        }
+        __syncthreads();
+        if (tid < nseg) {
+            int ax = 0;
+            if (S.bb[tid][0] <= S.bb[tid][3]) {  // at least one real point
+                float e[3];
+                for (int a = 0; a < 3; ++a) {
+                    const int lo = S.bb[tid][a], hi = S.bb[tid][3 + a];
+                    const float fl = __int_as_float(lo >= 0 ? lo : lo ^ 0x7fffffff), fh = __int_as_float(hi >= 0 ? hi : hi ^ 0x7fffffff);
+                    e[a] = fh - fl;
+                }
+                if (e[1] > e[ax]) ax = 1;
+                if (e[2] > e[ax]) ax = 2;
+            }
+            S.axis[tid] = (unsigned char)ax;
+        }
+        __syncthreads();
+        for (int i = tid; i < kGroup; i += kRefThreads) {
+            const int p = S.perm[i], ax = S.axis[i >> seg_shift];
+            const float v = ax == 0 ? S.x[p] : (ax == 1 ? S.y[p] : S.z[p]);
+            S.key[i] = (v == v) ? v : INFINITY;
+        }
+        __syncthreads();
+        // all-ascending bitonic network, independent inside every aligned block of seg_size
+        for (int k = 2; k <= seg_size; k <<= 1) {
+            const int hk = k >> 1;
+            for (int p = tid; p < kGroup / 2; p += kRefThreads) {  // flip step: i <-> i ^ (k - 1)
+                const int i = (p / hk) * k + (p % hk);
+                cmp_swap(S, i, i ^ (k - 1));
+            }
+            __syncthreads();
+            for (int j = hk >> 1; j > 0; j >>= 1) {  // disperse steps: i <-> i + j
+                for (int p = tid; p < kGroup / 2; p += kRefThreads) {
+                    const int i = (p / j) * 2 * j + (p % j);
+                    cmp_swap(S, i, i + j);
+                }
+                __syncthreads();
+            }
+        }
+    }
+    for (int i = tid; i < M; i += kRefThreads) {
+        const int p = S.perm[i];
+        px[base + i] = S.x[p]; py[base + i] = S.y[p]; pz[base + i] = S.z[p];
+        orig[base + i] = S.o[p];
+    }
+}
+
 __device__ __forceinline__ void warp_box(float4 &lo, float4 &hi) {
     for (int o = 16; o; o >>= 1) {
         lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o));
@@ -195,6 +306,15 @@ cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int
         const int tiles = (max_pad + 256 * 8 - 1) / (256 * 8);
         k_scatter<<<dim3(tiles > 0 ? tiles : 1, nkf), 256, 0, st>>>(d_raw, d_off, d_vals2, pack.kf, kf_begin, pack.px, pack.py, pack.pz,
                                                                     pack.orig);
+        if (max_pad > 0) {
+            static bool configured = false;
+            if (!configured) {
+                STL_TRY(cudaFuncSetAttribute(k_kd_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RefineSmem)));
+                configured = true;
+            }
+            k_kd_refine<<<dim3((max_pad + kGroup - 1) / kGroup, nkf), kRefThreads, sizeof(RefineSmem), st>>>(pack.kf, kf_begin, pack.px, pack.py,
+                                                                                                          pack.pz, pack.orig);
+        }
         k_leaf_aabb<<<dim3((max_n0 + 7) / 8, nkf), 256, 0, st>>>(pack.kf, kf_begin, pack.px, pack.py, pack.pz, pack.node_lo, pack.node_hi);
         k_inner_aabb<<<dim3((max_n1 + 7) / 8, nkf), 256, 0, st>>>(pack.kf, kf_begin, 1, pack.node_lo, pack.node_hi);
         k_inner_aabb<<<dim3(4, nkf), 256, 0, st>>>(pack.kf, kf_begin, 2, pack.node_lo, pack.node_hi);

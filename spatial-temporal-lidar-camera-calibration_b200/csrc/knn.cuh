@@ -38,15 +38,35 @@ __device__ __forceinline__ ScanView make_view(const DevPack &pk, const DevKf &K)
     return v;
 }
 
-__device__ __forceinline__ unsigned order_key(double lb) { return __float_as_uint(__double2float_rd(lb)); }
+// float32 lower bound of the reference's fp64 squared distance to any point of a box.
+// Every operation rounds toward the safe side (query rounded outward, differences / squares /
+// sums rounded down) and the result is shrunk by 2^-22, far more than the <= 4*2^-53 relative
+// rounding of the fp64 distance itself: lbf <= dist3e(q, p) for every p in the box, so pruning
+// on it never changes the exact result.  Bounds of the sinks are kept rounded UP in float32.
+struct QueryF { float xl, xh, yl, yh, zl, zh; };
+__device__ __forceinline__ QueryF make_queryf(double x, double y, double z) {
+    QueryF q;
+    q.xl = __double2float_rd(x); q.xh = __double2float_ru(x);
+    q.yl = __double2float_rd(y); q.yh = __double2float_ru(y);
+    q.zl = __double2float_rd(z); q.zh = __double2float_ru(z);
+    return q;
+}
+__device__ __forceinline__ float box_lbf(const QueryF &q, float4 lo, float4 hi) {
+    const float dx = fmaxf(fmaxf(__fsub_rd(lo.x, q.xh), __fsub_rd(q.xl, hi.x)), 0.f);
+    const float dy = fmaxf(fmaxf(__fsub_rd(lo.y, q.yh), __fsub_rd(q.yl, hi.y)), 0.f);
+    const float dz = fmaxf(fmaxf(__fsub_rd(lo.z, q.zh), __fsub_rd(q.zl, hi.z)), 0.f);
+    const float s = __fadd_rd(__fadd_rd(__fmul_rd(dx, dx), __fmul_rd(dy, dy)), __fmul_rd(dz, dz));
+    return __fmul_rd(s, 0.99999976f);
+}
 
 // ---- result sinks ---------------------------------------------------------------
 // 1-NN: (d2, orig) lexicographic minimum.  All members are warp-uniform.
 struct Sink1 {
     int n_iter = 0, n_visit = 0, n_ins = 0;
     double d = DBL_MAX;
+    float df = 3.402823466e+38f;  // d rounded up to float32
     uint32_t oi = 0xffffffffu, pos = 0xffffffffu;
-    __device__ __forceinline__ bool may_contain(double lb) const { return lb <= d; }
+    __device__ __forceinline__ bool may_contain(float lb) const { return lb <= df; }
     __device__ __forceinline__ void visit(const ScanView &S, int leaf, double qx, double qy, double qz, int lane) {
         ++n_visit;
         const int g = leaf * kLeaf + lane;
@@ -64,6 +84,7 @@ struct Sink1 {
         if (cd < d || (cd == d && mo < oi)) {
             const int src = __ffs(__ballot_sync(kFull, tie && o == mo)) - 1;
             d = cd; oi = mo; pos = (uint32_t)(leaf * kLeaf + src);
+            df = __double2float_ru(cd);
         }
     }
 };
@@ -75,12 +96,16 @@ struct SinkK {
     uint32_t ki = 0xffffffffu, kpos = 0xffffffffu;
     int count = 0, k;          // uniform
     double r2, wd;             // uniform: radius^2, current worst d2 when full
+    float r2f, wdf;            // the same, rounded up to float32 (box pruning)
     uint32_t wi = 0xffffffffu; // uniform: its index
-    __device__ __forceinline__ SinkK(int k_, double r2_) : k(k_), r2(r2_), wd(r2_) {}
+    __device__ __forceinline__ SinkK(int k_, double r2_) : k(k_), r2(r2_), wd(r2_) {
+        r2f = r2_ < 3.0e38 ? __double2float_ru(r2_) : 3.402823466e+38f;
+        wdf = r2f;
+    }
     __device__ __forceinline__ bool accept(double d, uint32_t i) const {
         return d < r2 && (count < k || d < wd || (d == wd && i < wi));
     }
-    __device__ __forceinline__ bool may_contain(double lb) const { return lb < r2 && (count < k || lb <= wd); }
+    __device__ __forceinline__ bool may_contain(float lb) const { return lb <= r2f && (count < k || lb <= wdf); }
     __device__ __forceinline__ void visit(const ScanView &S, int leaf, double qx, double qy, double qz, int lane) {
         const int g = leaf * kLeaf + lane;
         const double dd = dist3e(qx, qy, qz, (double)S.px[g], (double)S.py[g], (double)S.pz[g]);
@@ -89,6 +114,11 @@ struct SinkK {
         unsigned mask = __ballot_sync(kFull, pre);
         if (!mask) return;
         const uint32_t o = pre ? S.orig[g] : 0xffffffffu;
+        if (__popc(mask) >= (count == 0 ? 6 : 16)) {
+            bulk_merge(pre ? dd : (double)INFINITY, o, (uint32_t)g, lane);
+            n_ins += __popc(mask);
+            return;
+        }
         while (mask) {
             const int src = __ffs(mask) - 1;
             mask &= mask - 1;
@@ -103,8 +133,45 @@ struct SinkK {
             if (lane > at) { kd = sd; ki = si; kpos = sp; }
             else if (lane == at) { kd = cd; ki = ci; kpos = (uint32_t)(leaf * kLeaf + src); }
             if (count < k) ++count;
-            if (count == k) { wd = __shfl_sync(kFull, kd, k - 1); wi = __shfl_sync(kFull, ki, k - 1); }
+            if (count == k) { wd = __shfl_sync(kFull, kd, k - 1); wi = __shfl_sync(kFull, ki, k - 1); wdf = __double2float_ru(wd); }
         }
+    }
+
+    // compare-exchange with the lane `lane ^ j`; keep the smaller (d, i) if keep_min
+    __device__ __forceinline__ static void cx(double &d, uint32_t &i, uint32_t &p, int j, bool keep_min) {
+        const double od = __shfl_xor_sync(kFull, d, j);
+        const uint32_t oi = __shfl_xor_sync(kFull, i, j), op = __shfl_xor_sync(kFull, p, j);
+        const bool other_less = od < d || (od == d && oi < i);
+        const bool other_more = od > d || (od == d && oi > i);
+        if (keep_min ? other_less : other_more) { d = od; i = oi; p = op; }
+    }
+
+    // Many candidates at once (typically the first leaves): bitonic-sort the 32 candidates of the
+    // leaf across the warp, then bitonic-merge them with the sorted list — ~300 warp instructions
+    // whatever the number of accepted points, against ~30 per serial insertion.
+    __device__ __forceinline__ void bulk_merge(double cd, uint32_t ci, uint32_t cp, int lane) {
+#pragma unroll
+        for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
+                cx(cd, ci, cp, j, lower == up);
+            }
+        }
+        if (count == 0) {  // first leaf: the sorted candidates ARE the list
+            kd = cd; ki = ci; kpos = cp;
+        } else {
+            if (lane >= count) { kd = (double)INFINITY; ki = 0xffffffffu; }
+            // reversed candidates against the list: element-wise minimum holds the 32 smallest, bitonic
+            const double rd = __shfl_sync(kFull, cd, 31 - lane);
+            const uint32_t ri = __shfl_sync(kFull, ci, 31 - lane), rp = __shfl_sync(kFull, cp, 31 - lane);
+            if (rd < kd || (rd == kd && ri < ki)) { kd = rd; ki = ri; kpos = rp; }
+#pragma unroll
+            for (int j = 16; j > 0; j >>= 1) cx(kd, ki, kpos, j, (lane & j) == 0);
+        }
+        const int nvalid = __popc(__ballot_sync(kFull, kd < (double)INFINITY));
+        count = nvalid < k ? nvalid : k;
+        if (count == k) { wd = __shfl_sync(kFull, kd, k - 1); wi = __shfl_sync(kFull, ki, k - 1); wdf = __double2float_ru(wd); }
     }
 };
 
@@ -113,8 +180,9 @@ template <class Sink>
 __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy, double qz, Sink &sink, int lane) {
     const float4 *lo2 = S.lo + S.n0 + S.n1, *hi2 = S.hi + S.n0 + S.n1;
     const float4 *lo1 = S.lo + S.n0, *hi1 = S.hi + S.n0;
-    const double lb2 = box_lb(qx, qy, qz, lo2[lane], hi2[lane]);  // empty slots: +inf
-    const unsigned key2 = order_key(lb2);
+    const QueryF qf = make_queryf(qx, qy, qz);
+    const float lb2 = box_lbf(qf, lo2[lane], hi2[lane]);  // empty slots: +inf
+    const unsigned key2 = __float_as_uint(lb2);
     unsigned done2 = 0;
     for (;;) {
         ++sink.n_iter;
@@ -124,8 +192,8 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
         const int s2 = __ffs(__ballot_sync(kFull, c2 && key2 == m2)) - 1;
         done2 |= 1u << s2;
         const int n1i = s2 * 32 + lane;
-        const double lb1 = box_lb(qx, qy, qz, lo1[n1i], hi1[n1i]);
-        const unsigned key1 = order_key(lb1);
+        const float lb1 = box_lbf(qf, lo1[n1i], hi1[n1i]);
+        const unsigned key1 = __float_as_uint(lb1);
         unsigned done1 = 0;
         for (;;) {
             ++sink.n_iter;
@@ -135,8 +203,8 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
             const int s1 = __ffs(__ballot_sync(kFull, c1 && key1 == m1)) - 1;
             done1 |= 1u << s1;
             const int n0i = (s2 * 32 + s1) * 32 + lane;
-            const double lb0 = box_lb(qx, qy, qz, S.lo[n0i], S.hi[n0i]);
-            const unsigned key0 = order_key(lb0);
+            const float lb0 = box_lbf(qf, S.lo[n0i], S.hi[n0i]);
+            const unsigned key0 = __float_as_uint(lb0);
             unsigned done0 = 0;
             for (;;) {
                 ++sink.n_iter;
@@ -159,8 +227,14 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
 // redundantly, so there is no cross-lane reduction-order effect.
 struct PlaneOut { V3 n; double reg; int m; bool gates_ok; };
 
+constexpr int kPlaneSmemDoubles = 32 * 9;  // per-warp scratch of plane_from_knn
+
+// `wsm`: per-warp shared scratch of kPlaneSmemDoubles doubles.  Each lane forms the nine
+// products of ITS neighbour once; nine lanes then add them up in neighbour order (the
+// reference's running sums), so the covariance is bit-identical to the serial loop at a
+// fraction of the warp instructions.
 __device__ __forceinline__ PlaneOut plane_from_knn(const ScanView &S, const SinkK &kn, double cx, double cy, double cz,
-                                                   const DevParams &pr, int lane) {
+                                                   const DevParams &pr, int lane, double *wsm) {
     PlaneOut out;
     out.m = kn.count;
     out.n = {0.0, 0.0, 0.0};
@@ -169,28 +243,37 @@ __device__ __forceinline__ PlaneOut plane_from_knn(const ScanView &S, const Sink
     const int m = kn.count;
     if (m == 0) return out;
     const double last = __shfl_sync(kFull, kn.kd, m - 1);
-    const bool gate = !(last < pr.min_diff2) && !(m < pr.min_pts);
-    float fx = 0.f, fy = 0.f, fz = 0.f;
-    if (lane < m) { fx = S.px[kn.kpos]; fy = S.py[kn.kpos]; fz = S.pz[kn.kpos]; }
-    if (!gate) return out;
+    if ((last < pr.min_diff2) || (m < pr.min_pts)) return out;
     out.gates_ok = true;
-    double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0;
-    for (int j = 0; j < m; ++j) {
-        const double x = (double)__shfl_sync(kFull, fx, j), y = (double)__shfl_sync(kFull, fy, j), z = (double)__shfl_sync(kFull, fz, j);
-        c0 += x; c1 += y; c2 += z;
-        c3 += x * x; c4 += x * y; c5 += x * z;
-        c6 += y * y; c7 += y * z; c8 += z * z;
+    double x = 0, y = 0, z = 0;
+    if (lane < m) { x = (double)S.px[kn.kpos]; y = (double)S.py[kn.kpos]; z = (double)S.pz[kn.kpos]; }
+    __syncwarp();
+    {
+        double *w = wsm + lane * 9;
+        w[0] = x; w[1] = y; w[2] = z;
+        w[3] = x * x; w[4] = x * y; w[5] = x * z;
+        w[6] = y * y; w[7] = y * z; w[8] = z * z;
     }
-    const double dm = (double)m;
-    c0 /= dm; c1 /= dm; c2 /= dm; c3 /= dm; c4 /= dm; c5 /= dm; c6 /= dm; c7 /= dm; c8 /= dm;
+    __syncwarp();
+    double acc = 0;
+    if (lane < 9) {
+        for (int j = 0; j < m; ++j) acc += wsm[j * 9 + lane];
+        acc /= (double)m;
+    }
+    const double c0 = __shfl_sync(kFull, acc, 0), c1 = __shfl_sync(kFull, acc, 1), c2 = __shfl_sync(kFull, acc, 2);
+    const double c3 = __shfl_sync(kFull, acc, 3), c4 = __shfl_sync(kFull, acc, 4), c5 = __shfl_sync(kFull, acc, 5);
+    const double c6 = __shfl_sync(kFull, acc, 6), c7 = __shfl_sync(kFull, acc, 7), c8 = __shfl_sync(kFull, acc, 8);
     const double cov[6] = {c3 - c0 * c0, c4 - c0 * c1, c5 - c0 * c2, c6 - c1 * c1, c7 - c1 * c2, c8 - c2 * c2};
     const V3 n = normalized(smallest_eigvec(cov));
+    // regression error: |(p_j - c) . n| per lane, summed in neighbour order
+    const V3 d = {x - cx, y - cy, z - cz};
+    __syncwarp();
+    wsm[lane] = fabs(dot(d, n));
+    __syncwarp();
     double reg = 0;
-    for (int j = 0; j < m; ++j) {
-        const double x = (double)__shfl_sync(kFull, fx, j), y = (double)__shfl_sync(kFull, fy, j), z = (double)__shfl_sync(kFull, fz, j);
-        const V3 d = {x - cx, y - cy, z - cz};
-        reg += fabs(dot(d, n));
-    }
+    if (lane == 0)
+        for (int j = 0; j < m; ++j) reg += wsm[j];
+    reg = __shfl_sync(kFull, reg, 0);
     out.n = n;
     out.reg = reg / (double)(m - 1);
     return out;

@@ -16,7 +16,7 @@ namespace {
 
 constexpr int kWarps = 8;
 
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 3)
 k_align3d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, const int debug) {
     const int sub = wk.sub;
     const int j = blockIdx.x % sub;
@@ -26,6 +26,7 @@ k_align3d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
     const int nq = wk.n_q[rec];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ double red[5][kWarps];
+    __shared__ double plane_sm[kWarps][kPlaneSmemDoubles];
     double s3d = 0, v3d = 0, c3d = 0, vpl = 0, vpt = 0;
     if (nq > 0) {
         const DevKf K = pk.kf[f];
@@ -63,7 +64,7 @@ k_align3d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
                 SinkK kn(pr.k, pr.radius2);
                 traverse(S, nx, ny, nz, kn, lane);
                 stat_k[0] = kn.n_iter; stat_k[1] = kn.n_visit; stat_k[2] = kn.n_ins;
-                const PlaneOut po = plane_from_knn(S, kn, nx, ny, nz, pr, lane);
+                const PlaneOut po = plane_from_knn(S, kn, nx, ny, nz, pr, lane, plane_sm[warp]);
                 m = po.m;
                 if (po.gates_ok && !(po.reg > pr.reg_thr)) {
                     is_plane = 1;

@@ -37,6 +37,7 @@ k_lm_associate(const DevPack pk, const DevWork wk, const DevParams pr, LmState l
     const int nc = wk.n_corr[f];
     if (nc < pr.num_min_corr) return;  // iba_local.cpp:192
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ double plane_sm[kWarps][kPlaneSmemDoubles];
     const DevKf K = pk.kf[f];
     const DevCand &c0 = wk.cand[0];
     const ScanView S = make_view(pk, K);
@@ -46,18 +47,21 @@ k_lm_associate(const DevPack pk, const DevWork wk, const DevParams pr, LmState l
         const long long slot = K.kp_off + i;
         const uint32_t kp = wk.corr_kp[slot], sp = wk.corr_sp[slot];
         const double cx = (double)S.px[sp], cy = (double)S.py[sp], cz = (double)S.pz[sp];
-        // ComputeLocalNeighbor around the scan point
-        SinkK kn(pr.k, pr.radius2);
-        traverse(S, cx, cy, cz, kn, lane);
-        const PlaneOut po = plane_from_knn(S, kn, cx, cy, cz, pr, lane);
-        if (!po.gates_ok) continue;  // m < min_pts || d2[m-1] < min_diff^2
+        // The reference runs ComputeLocalNeighbor for every correspondence and only then drops the
+        // ones without a map point (iba_local.cpp:207-213) or without a covisible observation
+        // (:259); both tests are independent of the neighbour search, so they come first here.
         const float *mp = pk.kp_mp + (K.kp_off + kp) * 3;
         if (isnan(mp[0])) continue;  // iba_local.cpp:213
-        const bool valid_plane = po.reg < pr.reg_thr;  // strict '<' (iba_local.cpp:231)
         int ncov = 0;
         for (int s = 0; s < C; ++s)
             if (pk.covis_valid[f * C + s] && !isnan(pk.covis_uv[(K.kp_off + kp) * C + s].x)) ++ncov;
         if (ncov == 0) continue;  // iba_local.cpp:259
+        // ComputeLocalNeighbor around the scan point
+        SinkK kn(pr.k, pr.radius2);
+        traverse(S, cx, cy, cz, kn, lane);
+        const PlaneOut po = plane_from_knn(S, kn, cx, cy, cz, pr, lane, plane_sm[warp]);
+        if (!po.gates_ok) continue;  // m < min_pts || d2[m-1] < min_diff^2
+        const bool valid_plane = po.reg < pr.reg_thr;  // strict '<' (iba_local.cpp:231)
         if (lane == 0) {
             lm.slot_kf[slot] = f;
             lm.slot_kp[slot] = kp;
@@ -78,9 +82,12 @@ k_lm_associate(const DevPack pk, const DevWork wk, const DevParams pr, LmState l
         traverse(S, qx, qy, qz, nn, lane);
         if (nn.d > pr.max_3d_dist2) continue;  // iba_local.cpp:289
         const double nx = (double)S.px[nn.pos], ny = (double)S.py[nn.pos], nz = (double)S.pz[nn.pos];
-        SinkK kn2(pr.k, pr.radius2);
-        traverse(S, nx, ny, nz, kn2, lane);
-        const PlaneOut p2 = plane_from_knn(S, kn2, nx, ny, nz, pr, lane);
+        PlaneOut p2 = po;  // the map point's neighbour is very often the associated scan point itself
+        if (nn.pos != sp) {
+            SinkK kn2(pr.k, pr.radius2);
+            traverse(S, nx, ny, nz, kn2, lane);
+            p2 = plane_from_knn(S, kn2, nx, ny, nz, pr, lane, plane_sm[warp]);
+        }
         const bool state = p2.gates_ok && p2.reg < pr.reg_thr;
         if (lane == 0) {
             double *g = lm.geo3d + slot * 9;
