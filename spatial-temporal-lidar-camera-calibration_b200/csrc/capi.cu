@@ -108,7 +108,7 @@ void free_pack(stl_ctx *c) {
 void free_work(stl_ctx *c) {
     DevWork &w = c->wk;
     dfree(w.cand); dfree(w.corr_kp); dfree(w.corr_pt); dfree(w.corr_sp); dfree(w.q_corr); dfree(w.n_corr); dfree(w.n_q);
-    dfree(w.frame); dfree(w.align); dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn); dfree(w.dbg_stats);
+    dfree(w.frame); dfree(w.align); dfree(w.nn_pos); dfree(w.nb); dfree(w.nb_m); dfree(w.nb_last); dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn); dfree(w.dbg_stats);
     dfree(w.overflow);
     w = DevWork();
     c->wk_cap = 0;
@@ -166,7 +166,7 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
     if (ctx->wk_cap == 0) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        const size_t per_cand = (size_t)pk.n_kp_total * 16 + (size_t)pk.n_kf * (sizeof(FrameRec) + 4 * sizeof(AlignRec) + 8) + sizeof(DevCand);
+        const size_t per_cand = (size_t)pk.n_kp_total * 16 + (size_t)pk.n_mp_total * (4 * kMaxK + 16) + (size_t)pk.n_kf * (sizeof(FrameRec) + 4 * sizeof(AlignRec) + 8) + sizeof(DevCand);
         size_t budget = std::min<size_t>((size_t)4 << 30, free_b / 4);
         int cap = (int)std::max<size_t>(1, std::min<size_t>(budget / std::max<size_t>(per_cand, 1), 256));
         DevWork &w = ctx->wk;
@@ -177,6 +177,10 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
         CK(cudaMalloc(&w.corr_kp, 4 * nk)); CK(cudaMalloc(&w.corr_pt, 4 * nk)); CK(cudaMalloc(&w.corr_sp, 4 * nk)); CK(cudaMalloc(&w.q_corr, 4 * nk));
         CK(cudaMalloc(&w.n_corr, 4 * nf)); CK(cudaMalloc(&w.n_q, 4 * nf));
         CK(cudaMalloc(&w.frame, sizeof(FrameRec) * nf)); CK(cudaMalloc(&w.align, sizeof(AlignRec) * nf * w.sub));
+        {
+            const size_t nm = (size_t)std::max<long long>(pk.n_mp_total, 1) * cap;
+            CK(cudaMalloc(&w.nn_pos, 4 * nm)); CK(cudaMalloc(&w.nb, 4 * nm * kMaxK)); CK(cudaMalloc(&w.nb_m, 4 * nm)); CK(cudaMalloc(&w.nb_last, 8 * nm));
+        }
         CK(cudaMalloc(&w.overflow, 4));
         CK(cudaMemset(w.overflow, 0, 4));
         ctx->wk_cap = cap;
@@ -219,7 +223,7 @@ stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, c
         { StageTimer t(ctx, STL_STAGE_ASSOC2D, st); CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_smem, st)); }
         { StageTimer t(ctx, STL_STAGE_KNN3D, st); CK(launch_align3d(ctx->pk, ctx->wk, ctx->dpr, nb, debug ? 1 : 0, st)); }
         { StageTimer t(ctx, STL_STAGE_REDUCE, st); CK(launch_reduce(ctx->pk, ctx->wk, ctx->dpr, nb, d_out + (size_t)c0 * STL_EVAL_NSUMS, st)); }
-        ctx->launches += 3;
+        ctx->launches += 4;  // K1, K2a, K2b, K3
     }
     CK(cudaEventRecord(ctx->h2d_done, st));
     ctx->counters[0] = (double)ctx->n_pts_total * B;
@@ -330,7 +334,7 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     // ---- per-keyframe metadata
     std::vector<DevKf> &hk = ctx->h_kf;
     hk.assign(F, DevKf());
-    long long pt = 0, nodes = 0, bmw = 0, gcells = 0;
+    long long pt = 0, nodes = 0, bmw = 0, gcells = 0, mp_total = 0;
     int max_kp = 0, max_bm = 0;
     for (int f = 0; f < F; ++f) {
         DevKf &K = hk[f];
@@ -358,6 +362,10 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
         K.gh = std::max(1, (K.H + kGridCell - 1) / kGridCell);
         K.grid_off = gcells; gcells += (long long)K.gw * K.gh + 1;
         K.he_valid = p->he_valid[f] ? 1 : 0;
+        K.mp_off = mp_total;
+        K.n_mp = 0;
+        for (long long k = 0; k < nk; ++k) K.n_mp += !(p->kp_mappoint[(K.kp_off + k) * 3] != p->kp_mappoint[(K.kp_off + k) * 3]);
+        mp_total += K.n_mp;
         K.pmax = 1.f;
         max_kp = std::max(max_kp, K.n_kp);
         max_bm = std::max(max_bm, K.bm_wpr * K.bm_rows);
@@ -405,7 +413,7 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
 
     // ---- device allocation + small uploads
     DevPack &pk = ctx->pk;
-    pk.n_kf = F; pk.n_covis = C; pk.n_pad_total = pt; pk.n_nodes_total = nodes; pk.n_kp_total = NK;
+    pk.n_kf = F; pk.n_covis = C; pk.n_pad_total = pt; pk.n_nodes_total = nodes; pk.n_kp_total = NK; pk.n_mp_total = mp_total;
     ctx->n_pts_total = p->scan_offset[F];
     const size_t npt = (size_t)std::max<long long>(pt, 4), nkk = (size_t)std::max<long long>(NK, 1);
     CK(cudaMalloc(&pk.kf, sizeof(DevKf) * F));
@@ -623,7 +631,7 @@ stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[3]
     cudaError_t e;
     { StageTimer t(ctx, 5, st); e = lm_associate(ctx->pk, ctx->wk, ctx->dpr, ctx->lm, st); }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "associate: %s", cudaGetErrorString(e));
-    ctx->launches += 2 + (ctx->lm.n3d > 0 ? 1 : 0);  // K1, k_lm_associate, k_count_types (cub select kernels not counted)
+    ctx->launches += 5 + (ctx->lm.n3d > 0 ? 1 : 0);  // K1, four association kernels, k_count_types (cub select kernels not counted)
     if (n_blocks) { n_blocks[0] = ctx->lm.n_blocks[0]; n_blocks[1] = ctx->lm.n_blocks[1]; n_blocks[2] = ctx->lm.n_blocks[2]; }
     ctx->dbg_b = -1;
     ctx->last_x.clear();

@@ -28,6 +28,9 @@ struct DevKf {
     long long kp_off;
     long long bm_off;
     long long grid_off;
+    long long mp_off;  // first slot of this keyframe in the map-point-indexed query lists
+    int n_mp;          // keypoints that carry a map point (upper bound of the 3-D queries)
+    int pad0_;
     int n_pts, n_pad;
     int n0, n1, n2;
     int n_kp;

@@ -11,7 +11,7 @@ namespace stl {
 // Device-resident pack (all pointers are device memory owned by the context).
 struct DevPack {
     int n_kf = 0, n_covis = 0;
-    long long n_pad_total = 0, n_nodes_total = 0, n_kp_total = 0;
+    long long n_pad_total = 0, n_nodes_total = 0, n_kp_total = 0, n_mp_total = 0;
     DevKf *kf = nullptr;
     float *px = nullptr, *py = nullptr, *pz = nullptr;
     uint32_t *orig = nullptr;
@@ -42,6 +42,11 @@ struct DevWork {
     int *n_q = nullptr;           // [Bc][n_kf]
     FrameRec *frame = nullptr;    // [Bc][n_kf]
     AlignRec *align = nullptr;    // [Bc][n_kf][sub]
+    // neighbour lists of the 3-D queries, slot = b * n_mp_total + mp_off[f] + qi
+    uint32_t *nn_pos = nullptr;   // [Bc][n_mp_total] sorted position of the 1-NN
+    uint32_t *nb = nullptr;       // [Bc][n_mp_total][32] sorted positions of the k-NN, distance order
+    int *nb_m = nullptr;          // [Bc][n_mp_total] neighbours kept (d2 < radius^2)
+    double *nb_last = nullptr;    // [Bc][n_mp_total] d2 of the last kept neighbour
     // optional per-query debug (allocated on demand, Bc_dbg = 1)
     uint32_t *dbg_nn = nullptr;   // [n_kp_total]
     int *dbg_m = nullptr;
@@ -63,6 +68,7 @@ cudaError_t assoc2d_configure(size_t smem);
 cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, cudaStream_t st);
 
 // ---- K2 (knn3d.cu) ---------------------------------------------------------------
+// K2a (traversal: 1-NN + k-NN, warp per query) then K2b (plane fit + distance, thread per query)
 cudaError_t launch_align3d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, int debug, cudaStream_t st);
 cudaError_t launch_knn3d(const DevPack &pk, int kf, const double *d_q, int nq, int k, double radius2, uint32_t *d_idx, double *d_d2,
                          int *d_cnt, cudaStream_t st);

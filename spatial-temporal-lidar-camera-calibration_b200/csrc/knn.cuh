@@ -62,13 +62,11 @@ __device__ __forceinline__ float box_lbf(const QueryF &q, float4 lo, float4 hi) 
 // ---- result sinks ---------------------------------------------------------------
 // 1-NN: (d2, orig) lexicographic minimum.  All members are warp-uniform.
 struct Sink1 {
-    int n_iter = 0, n_visit = 0, n_ins = 0;
     double d = DBL_MAX;
     float df = 3.402823466e+38f;  // d rounded up to float32
     uint32_t oi = 0xffffffffu, pos = 0xffffffffu;
     __device__ __forceinline__ bool may_contain(float lb) const { return lb <= df; }
     __device__ __forceinline__ void visit(const ScanView &S, int leaf, double qx, double qy, double qz, int lane) {
-        ++n_visit;
         const int g = leaf * kLeaf + lane;
         const double dd = dist3e(qx, qy, qz, (double)S.px[g], (double)S.py[g], (double)S.pz[g]);  // NaN for pads
         const bool q = dd <= d;
@@ -91,7 +89,6 @@ struct Sink1 {
 
 // k-NN (k <= 32) restricted to d2 < r2: lane j holds the j-th best (d2, orig, pos).
 struct SinkK {
-    int n_iter = 0, n_visit = 0, n_ins = 0;
     double kd = DBL_MAX;       // per lane
     uint32_t ki = 0xffffffffu, kpos = 0xffffffffu;
     int count = 0, k;          // uniform
@@ -110,13 +107,11 @@ struct SinkK {
         const int g = leaf * kLeaf + lane;
         const double dd = dist3e(qx, qy, qz, (double)S.px[g], (double)S.py[g], (double)S.pz[g]);
         const bool pre = dd < r2 && (count < k || dd <= wd);
-        ++n_visit;
         unsigned mask = __ballot_sync(kFull, pre);
         if (!mask) return;
         const uint32_t o = pre ? S.orig[g] : 0xffffffffu;
         if (__popc(mask) >= (count == 0 ? 6 : 16)) {
             bulk_merge(pre ? dd : (double)INFINITY, o, (uint32_t)g, lane);
-            n_ins += __popc(mask);
             return;
         }
         while (mask) {
@@ -125,7 +120,6 @@ struct SinkK {
             const double cd = __shfl_sync(kFull, dd, src);
             const uint32_t ci = __shfl_sync(kFull, o, src);
             if (!accept(cd, ci)) continue;
-            ++n_ins;
             const bool less = lane < count && (kd < cd || (kd == cd && ki < ci));
             const int at = __popc(__ballot_sync(kFull, less));
             const double sd = __shfl_up_sync(kFull, kd, 1);
@@ -150,9 +144,9 @@ struct SinkK {
     // leaf across the warp, then bitonic-merge them with the sorted list — ~300 warp instructions
     // whatever the number of accepted points, against ~30 per serial insertion.
     __device__ __forceinline__ void bulk_merge(double cd, uint32_t ci, uint32_t cp, int lane) {
-#pragma unroll
+#pragma unroll 1
         for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
+#pragma unroll 1
             for (int j = kk >> 1; j > 0; j >>= 1) {
                 const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
                 cx(cd, ci, cp, j, lower == up);
@@ -166,7 +160,7 @@ struct SinkK {
             const double rd = __shfl_sync(kFull, cd, 31 - lane);
             const uint32_t ri = __shfl_sync(kFull, ci, 31 - lane), rp = __shfl_sync(kFull, cp, 31 - lane);
             if (rd < kd || (rd == kd && ri < ki)) { kd = rd; ki = ri; kpos = rp; }
-#pragma unroll
+#pragma unroll 1
             for (int j = 16; j > 0; j >>= 1) cx(kd, ki, kpos, j, (lane & j) == 0);
         }
         const int nvalid = __popc(__ballot_sync(kFull, kd < (double)INFINITY));
@@ -185,7 +179,6 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
     const unsigned key2 = __float_as_uint(lb2);
     unsigned done2 = 0;
     for (;;) {
-        ++sink.n_iter;
         const bool c2 = !((done2 >> lane) & 1u) && sink.may_contain(lb2);
         const unsigned m2 = __reduce_min_sync(kFull, c2 ? key2 : 0xffffffffu);
         if (m2 == 0xffffffffu) break;
@@ -196,8 +189,7 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
         const unsigned key1 = __float_as_uint(lb1);
         unsigned done1 = 0;
         for (;;) {
-            ++sink.n_iter;
-            const bool c1 = !((done1 >> lane) & 1u) && sink.may_contain(lb1);
+                const bool c1 = !((done1 >> lane) & 1u) && sink.may_contain(lb1);
             const unsigned m1 = __reduce_min_sync(kFull, c1 ? key1 : 0xffffffffu);
             if (m1 == 0xffffffffu) break;
             const int s1 = __ffs(__ballot_sync(kFull, c1 && key1 == m1)) - 1;
@@ -207,8 +199,7 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
             const unsigned key0 = __float_as_uint(lb0);
             unsigned done0 = 0;
             for (;;) {
-                ++sink.n_iter;
-                const bool c0 = !((done0 >> lane) & 1u) && sink.may_contain(lb0);
+                        const bool c0 = !((done0 >> lane) & 1u) && sink.may_contain(lb0);
                 const unsigned m0 = __reduce_min_sync(kFull, c0 ? key0 : 0xffffffffu);
                 if (m0 == 0xffffffffu) break;
                 const int s0 = __ffs(__ballot_sync(kFull, c0 && key0 == m0)) - 1;
@@ -219,61 +210,41 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
     }
 }
 
-// ---- local plane around a scan point -------------------------------------------------
-// Given the k-NN of `c` (a scan point) held one per lane in (d2, index) order, evaluates
-// the gates and the PCA plane exactly as ComputeAlignmentDist (iba_global.cpp:130-148):
-// returns true and the unit normal if the neighbourhood is a valid plane.  Sums run
-// serially in neighbour order (ComputeCovariance pointcloud.h:126-158), every lane
-// redundantly, so there is no cross-lane reduction-order effect.
+// ---- local plane around a scan point (one THREAD per neighbourhood) ---------------------
+// Given the neighbour list of scan point c (sorted positions in (d2, index) order, m entries,
+// `last` = d2 of the m-th), evaluates the gates and the PCA plane exactly as
+// ComputeAlignmentDist (iba_global.cpp:130-148) / ComputeLocalNormalSingleThre
+// (pointcloud.h:651-666): running sums in neighbour order (ComputeCovariance,
+// pointcloud.h:126-158), closed-form smallest eigenvector, regression error.
 struct PlaneOut { V3 n; double reg; int m; bool gates_ok; };
 
-constexpr int kPlaneSmemDoubles = 32 * 9;  // per-warp scratch of plane_from_knn
-
-// `wsm`: per-warp shared scratch of kPlaneSmemDoubles doubles.  Each lane forms the nine
-// products of ITS neighbour once; nine lanes then add them up in neighbour order (the
-// reference's running sums), so the covariance is bit-identical to the serial loop at a
-// fraction of the warp instructions.
-__device__ __forceinline__ PlaneOut plane_from_knn(const ScanView &S, const SinkK &kn, double cx, double cy, double cz,
-                                                   const DevParams &pr, int lane, double *wsm) {
+__device__ __forceinline__ PlaneOut plane_thread(const ScanView &S, const uint32_t *__restrict__ nb, int m, double last, double cx,
+                                                 double cy, double cz, const DevParams &pr) {
     PlaneOut out;
-    out.m = kn.count;
+    out.m = m;
     out.n = {0.0, 0.0, 0.0};
     out.reg = 0;
     out.gates_ok = false;
-    const int m = kn.count;
-    if (m == 0) return out;
-    const double last = __shfl_sync(kFull, kn.kd, m - 1);
-    if ((last < pr.min_diff2) || (m < pr.min_pts)) return out;
+    if (m == 0 || (last < pr.min_diff2) || (m < pr.min_pts)) return out;
     out.gates_ok = true;
-    double x = 0, y = 0, z = 0;
-    if (lane < m) { x = (double)S.px[kn.kpos]; y = (double)S.py[kn.kpos]; z = (double)S.pz[kn.kpos]; }
-    __syncwarp();
-    {
-        double *w = wsm + lane * 9;
-        w[0] = x; w[1] = y; w[2] = z;
-        w[3] = x * x; w[4] = x * y; w[5] = x * z;
-        w[6] = y * y; w[7] = y * z; w[8] = z * z;
+    double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0;
+    for (int j = 0; j < m; ++j) {
+        const uint32_t p = nb[j];
+        const double x = (double)S.px[p], y = (double)S.py[p], z = (double)S.pz[p];
+        c0 += x; c1 += y; c2 += z;
+        c3 += x * x; c4 += x * y; c5 += x * z;
+        c6 += y * y; c7 += y * z; c8 += z * z;
     }
-    __syncwarp();
-    double acc = 0;
-    if (lane < 9) {
-        for (int j = 0; j < m; ++j) acc += wsm[j * 9 + lane];
-        acc /= (double)m;
-    }
-    const double c0 = __shfl_sync(kFull, acc, 0), c1 = __shfl_sync(kFull, acc, 1), c2 = __shfl_sync(kFull, acc, 2);
-    const double c3 = __shfl_sync(kFull, acc, 3), c4 = __shfl_sync(kFull, acc, 4), c5 = __shfl_sync(kFull, acc, 5);
-    const double c6 = __shfl_sync(kFull, acc, 6), c7 = __shfl_sync(kFull, acc, 7), c8 = __shfl_sync(kFull, acc, 8);
+    const double dm = (double)m;
+    c0 /= dm; c1 /= dm; c2 /= dm; c3 /= dm; c4 /= dm; c5 /= dm; c6 /= dm; c7 /= dm; c8 /= dm;
     const double cov[6] = {c3 - c0 * c0, c4 - c0 * c1, c5 - c0 * c2, c6 - c1 * c1, c7 - c1 * c2, c8 - c2 * c2};
     const V3 n = normalized(smallest_eigvec(cov));
-    // regression error: |(p_j - c) . n| per lane, summed in neighbour order
-    const V3 d = {x - cx, y - cy, z - cz};
-    __syncwarp();
-    wsm[lane] = fabs(dot(d, n));
-    __syncwarp();
     double reg = 0;
-    if (lane == 0)
-        for (int j = 0; j < m; ++j) reg += wsm[j];
-    reg = __shfl_sync(kFull, reg, 0);
+    for (int j = 0; j < m; ++j) {
+        const uint32_t p = nb[j];
+        const V3 d = {(double)S.px[p] - cx, (double)S.py[p] - cy, (double)S.pz[p] - cz};
+        reg += fabs(dot(d, n));
+    }
     out.n = n;
     out.reg = reg / (double)(m - 1);
     return out;

@@ -1,4 +1,4 @@
-// knn3d.cu — K2: 3-D/3-D alignment term, one warp per (candidate, keyframe, map point).
+// knn3d.cu — K2: 3-D/3-D alignment term of BAError.
 //
 // Replaces, per 2-D correspondence that carries a map point:
 //   map point -> LiDAR frame        src/examples/iba_global.cpp:231-234
@@ -7,6 +7,13 @@
 //      gates :136-139, ComputeCovariance + FastEigen3x3_EV :140-143, regression
 //      gate and point-to-plane / point-to-point distance :144-154)
 //   thresholded accumulation        src/examples/iba_global.cpp:239-251
+//
+// Two kernels, so that each stays small enough for the instruction cache and uses the
+// machine the way its work is shaped (profiles/r01_k2_*.txt):
+//   K2a k_nn_knn     one WARP per query: exact 1-NN, then exact k-NN around that neighbour;
+//                    writes the neighbour list (sorted positions, distance order).
+//   K2b k_plane_dist one THREAD per query: gates, ordered covariance, closed-form eigenvector,
+//                    regression gate, distance; fixed-order CTA reduction per (candidate, keyframe).
 // plus the stand-alone k-NN entry used by the parity tests.
 #include "kernels.h"
 #include "knn.cuh"
@@ -15,91 +22,118 @@ namespace stl {
 namespace {
 
 constexpr int kWarps = 8;
+constexpr int kPlaneThreads = 128;
 
-__global__ void __launch_bounds__(kWarps * 32, 3)
-k_align3d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, const int debug) {
+// the map point of correspondence `kp` in the LiDAR frame of candidate c (iba_global.cpp:231-234)
+__device__ __forceinline__ void map_point_lidar(const DevPack &pk, const DevKf &K, const DevCand &c, int f, uint32_t kp, double &qx,
+                                                double &qy, double &qz) {
+    const float *Tcw = pk.Tcw + (long long)f * 12;
+    const float *mp = pk.kp_mp + (K.kp_off + kp) * 3;
+    // GetWorldPos()*scale evaluated in float32, then widened (iba_global.cpp:232)
+    const double wx = (double)__fmul_rn(mp[0], c.sf), wy = (double)__fmul_rn(mp[1], c.sf), wz = (double)__fmul_rn(mp[2], c.sf);
+    // TcwRS = Tcw with the translation scaled (iba_global.cpp:206-208)
+    const double cxm = dadd(dot3e((double)Tcw[0], (double)Tcw[1], (double)Tcw[2], wx, wy, wz), dmul((double)Tcw[3], c.s));
+    const double cym = dadd(dot3e((double)Tcw[4], (double)Tcw[5], (double)Tcw[6], wx, wy, wz), dmul((double)Tcw[7], c.s));
+    const double czm = dadd(dot3e((double)Tcw[8], (double)Tcw[9], (double)Tcw[10], wx, wy, wz), dmul((double)Tcw[11], c.s));
+    xform(c.Ri, c.ti, cxm, cym, czm, qx, qy, qz);  // Tcl.inverse() * P
+}
+
+// K2a — grid: (candidate, keyframe, sub-block), one warp per query
+__global__ void __launch_bounds__(kWarps * 32, 4)
+k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
     const int sub = wk.sub;
     const int j = blockIdx.x % sub;
     const int bf = blockIdx.x / sub;
     const int f = bf / B, b = bf - f * B;
+    const int nq = wk.n_q[(long long)b * pk.n_kf + f];
+    if (nq <= 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const DevKf K = pk.kf[f];
+    const DevCand &c = wk.cand[b];
+    const ScanView S = make_view(pk, K);
+    const long long cbase = (long long)b * pk.n_kp_total + K.kp_off;
+    const long long qbase = (long long)b * pk.n_mp_total + K.mp_off;
+    for (int qi = j * kWarps + warp; qi < nq; qi += sub * kWarps) {
+        const uint32_t kp = wk.corr_kp[cbase + wk.q_corr[cbase + qi]];
+        double qx, qy, qz;
+        map_point_lidar(pk, K, c, f, kp, qx, qy, qz);
+        Sink1 nn;
+        traverse(S, qx, qy, qz, nn, lane);
+        if (lane == 0) wk.nn_pos[qbase + qi] = nn.pos;
+        if (pr.use_plane) {
+            const double nx = (double)S.px[nn.pos], ny = (double)S.py[nn.pos], nz = (double)S.pz[nn.pos];
+            SinkK kn(pr.k, pr.radius2);
+            traverse(S, nx, ny, nz, kn, lane);
+            wk.nb[(qbase + qi) * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
+            const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
+            if (lane == 0) { wk.nb_m[qbase + qi] = kn.count; wk.nb_last[qbase + qi] = last; }
+        }
+    }
+}
+
+// K2b — grid: (candidate, keyframe), one thread per query
+__global__ void __launch_bounds__(kPlaneThreads)
+k_plane_dist(const DevPack pk, const DevWork wk, const DevParams pr, const int B, const int debug) {
+    const int f = blockIdx.x / B, b = blockIdx.x - f * B;
     const long long rec = (long long)b * pk.n_kf + f;
     const int nq = wk.n_q[rec];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ double red[5][kWarps];
-    __shared__ double plane_sm[kWarps][kPlaneSmemDoubles];
     double s3d = 0, v3d = 0, c3d = 0, vpl = 0, vpt = 0;
     if (nq > 0) {
         const DevKf K = pk.kf[f];
         const DevCand &c = wk.cand[b];
         const ScanView S = make_view(pk, K);
-        const long long base = (long long)b * pk.n_kp_total + K.kp_off;
-        const float *Tcw = pk.Tcw + (long long)f * 12;
-        double Rcw[9], tcw[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-#pragma unroll
-            for (int a = 0; a < 3; ++a) Rcw[i * 3 + a] = (double)Tcw[i * 4 + a];
-            tcw[i] = dmul((double)Tcw[i * 4 + 3], c.s);  // TcwRS.topRightCorner *= scale (iba_global.cpp:208)
-        }
-        for (int qi = j * kWarps + warp; qi < nq; qi += sub * kWarps) {
-            const uint32_t ci = wk.q_corr[base + qi];
-            const uint32_t kp = wk.corr_kp[base + ci];
-            const float *mp = pk.kp_mp + (K.kp_off + kp) * 3;
-            // GetWorldPos()*scale evaluated in float32, then widened (iba_global.cpp:232)
-            const double wx = (double)__fmul_rn(mp[0], c.sf), wy = (double)__fmul_rn(mp[1], c.sf), wz = (double)__fmul_rn(mp[2], c.sf);
-            const double cxm = dadd(dot3e(Rcw[0], Rcw[1], Rcw[2], wx, wy, wz), tcw[0]);
-            const double cym = dadd(dot3e(Rcw[3], Rcw[4], Rcw[5], wx, wy, wz), tcw[1]);
-            const double czm = dadd(dot3e(Rcw[6], Rcw[7], Rcw[8], wx, wy, wz), tcw[2]);
+        const long long cbase = (long long)b * pk.n_kp_total + K.kp_off;
+        const long long qbase = (long long)b * pk.n_mp_total + K.mp_off;
+        for (int qi = threadIdx.x; qi < nq; qi += kPlaneThreads) {
+            const uint32_t kp = wk.corr_kp[cbase + wk.q_corr[cbase + qi]];
             double qx, qy, qz;
-            xform(c.Ri, c.ti, cxm, cym, czm, qx, qy, qz);  // Tcl.inverse() * P
-
-            Sink1 nn;
-            traverse(S, qx, qy, qz, nn, lane);
-            const double nx = (double)S.px[nn.pos], ny = (double)S.py[nn.pos], nz = (double)S.pz[nn.pos];
+            map_point_lidar(pk, K, c, f, kp, qx, qy, qz);
+            const uint32_t np = wk.nn_pos[qbase + qi];
+            const double nx = (double)S.px[np], ny = (double)S.py[np], nz = (double)S.pz[np];
             const double dx = dsub(nx, qx), dy = dsub(ny, qy), dz = dsub(nz, qz);
-            double dist = sqrt(dot3e(dx, dy, dz, dx, dy, dz));  // pt2pt
+            double dist = sqrt(dot3e(dx, dy, dz, dx, dy, dz));  // pt2pt (iba_global.cpp:122)
             int is_plane = 0, m = 0;
-            int stat_k[3] = {0, 0, 0};
             if (pr.use_plane) {
-                SinkK kn(pr.k, pr.radius2);
-                traverse(S, nx, ny, nz, kn, lane);
-                stat_k[0] = kn.n_iter; stat_k[1] = kn.n_visit; stat_k[2] = kn.n_ins;
-                const PlaneOut po = plane_from_knn(S, kn, nx, ny, nz, pr, lane, plane_sm[warp]);
-                m = po.m;
-                if (po.gates_ok && !(po.reg > pr.reg_thr)) {
+                m = wk.nb_m[qbase + qi];
+                const PlaneOut po = plane_thread(S, wk.nb + (qbase + qi) * kMaxK, m, wk.nb_last[qbase + qi], nx, ny, nz, pr);
+                if (po.gates_ok && !(po.reg > pr.reg_thr)) {  // iba_global.cpp:147
                     is_plane = 1;
                     dist = fabs(dot3e(dx, dy, dz, po.n.x, po.n.y, po.n.z));
                 }
-                if (debug) {
-                    if (lane < kMaxK) wk.dbg_knn[(K.kp_off + qi) * kMaxK + lane] = lane < m ? kn.ki : 0xffffffffu;
-                }
             }
-            if (dist < pr.thr3d) {
+            if (dist < pr.thr3d) {  // iba_global.cpp:241-249
                 s3d += dist; v3d += 1.0;
                 if (is_plane) vpl += 1.0; else vpt += 1.0;
             }
             c3d += 1.0;
-            if (debug && lane == 0) {
-                atomicAdd(&wk.dbg_stats[0], 1ull);
-                atomicAdd(&wk.dbg_stats[1], (unsigned long long)nn.n_iter);
-                atomicAdd(&wk.dbg_stats[2], (unsigned long long)nn.n_visit);
-                atomicAdd(&wk.dbg_stats[3], (unsigned long long)stat_k[0]);
-                atomicAdd(&wk.dbg_stats[4], (unsigned long long)stat_k[1]);
-                atomicAdd(&wk.dbg_stats[5], (unsigned long long)stat_k[2]);
-                atomicAdd(&wk.dbg_stats[6], (unsigned long long)m);
-                wk.dbg_nn[K.kp_off + qi] = nn.oi;
-                wk.dbg_m[K.kp_off + qi] = m;
-                wk.dbg_plane[K.kp_off + qi] = is_plane;
-                wk.dbg_dist[K.kp_off + qi] = dist;
+            if (debug) {
+                const long long o = K.kp_off + qi;
+                wk.dbg_nn[o] = S.orig[np];
+                wk.dbg_m[o] = m;
+                wk.dbg_plane[o] = is_plane;
+                wk.dbg_dist[o] = dist;
+                for (int t = 0; t < kMaxK; ++t) {
+                    const uint32_t p = (pr.use_plane && t < m) ? wk.nb[(qbase + qi) * kMaxK + t] : 0xffffffffu;
+                    wk.dbg_knn[o * kMaxK + t] = p == 0xffffffffu ? 0xffffffffu : S.orig[p];
+                }
             }
         }
+    }
+    // fixed-order CTA reduction
+    __shared__ double red[5][kPlaneThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 16; o; o >>= 1) {
+        s3d += __shfl_down_sync(0xffffffffu, s3d, o); v3d += __shfl_down_sync(0xffffffffu, v3d, o);
+        c3d += __shfl_down_sync(0xffffffffu, c3d, o); vpl += __shfl_down_sync(0xffffffffu, vpl, o);
+        vpt += __shfl_down_sync(0xffffffffu, vpt, o);
     }
     if (lane == 0) { red[0][warp] = s3d; red[1][warp] = v3d; red[2][warp] = c3d; red[3][warp] = vpl; red[4][warp] = vpt; }
     __syncthreads();
     if (threadIdx.x == 0) {
         AlignRec r = {0, 0, 0, 0, 0};
-        for (int w = 0; w < kWarps; ++w) { r.s3d += red[0][w]; r.v3d += red[1][w]; r.c3d += red[2][w]; r.vpl += red[3][w]; r.vpt += red[4][w]; }
-        wk.align[rec * sub + j] = r;
+        for (int w = 0; w < kPlaneThreads / 32; ++w) { r.s3d += red[0][w]; r.v3d += red[1][w]; r.c3d += red[2][w]; r.vpl += red[3][w]; r.vpt += red[4][w]; }
+        wk.align[rec * wk.sub] = r;
+        for (int s = 1; s < wk.sub; ++s) wk.align[rec * wk.sub + s] = AlignRec{0, 0, 0, 0, 0};
     }
 }
 
@@ -125,7 +159,10 @@ k_knn3d(const DevPack pk, const int kf, const double *__restrict__ q, const int 
 
 cudaError_t launch_align3d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, int debug, cudaStream_t st) {
     if (B <= 0 || pk.n_kf <= 0) return cudaSuccess;
-    k_align3d<<<(unsigned)(pk.n_kf * B * wk.sub), kWarps * 32, 0, st>>>(pk, wk, pr, B, debug);
+    k_nn_knn<<<(unsigned)(pk.n_kf * B * wk.sub), kWarps * 32, 0, st>>>(pk, wk, pr, B);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_plane_dist<<<(unsigned)(pk.n_kf * B), kPlaneThreads, 0, st>>>(pk, wk, pr, B, debug);
     return cudaGetLastError();
 }
 

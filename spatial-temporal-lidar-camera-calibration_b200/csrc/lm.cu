@@ -30,72 +30,163 @@ constexpr int kAssocSub = 8;
 constexpr int kLinVals = 40;  // cost, g[7], H upper 28, n2d, npt, npl, nres
 constexpr int kLinThreads = 128;
 
-// ------------------------------------------------------------------ K4a
-__global__ void __launch_bounds__(kWarps * 32)
-k_lm_associate(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
-    const int j = blockIdx.x % kAssocSub, f = blockIdx.x / kAssocSub;
-    const int nc = wk.n_corr[f];
-    if (nc < pr.num_min_corr) return;  // iba_local.cpp:192
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ double plane_sm[kWarps][kPlaneSmemDoubles];
-    const DevKf K = pk.kf[f];
-    const DevCand &c0 = wk.cand[0];
-    const ScanView S = make_view(pk, K);
+// ------------------------------------------------------------------ K4a (four small kernels)
+// All four walk the correspondences that carry a map point (the query list K1 wrote), keyframe by
+// keyframe; list slot = mp_off[f] + qi.  Traversals are warp-per-item, plane fits thread-per-item.
+
+__device__ __forceinline__ bool lm_frame_active(const DevWork &wk, const DevParams &pr, int f, int &nq) {
+    nq = wk.n_q[f];
+    return wk.n_corr[f] >= pr.num_min_corr && nq > 0;  // iba_local.cpp:192
+}
+
+// map point in the reference camera frame, no scale (iba_local.cpp:239-240)
+__device__ __forceinline__ void lm_map_point(const DevPack &pk, const DevKf &K, int f, uint32_t kp, double &Mx, double &My, double &Mz) {
     const float *Tcw = pk.Tcw + (long long)f * 12;
+    const float *mp = pk.kp_mp + (K.kp_off + kp) * 3;
+    const double a = (double)mp[0], b = (double)mp[1], c = (double)mp[2];
+    Mx = dadd(dot3e((double)Tcw[0], (double)Tcw[1], (double)Tcw[2], a, b, c), (double)Tcw[3]);
+    My = dadd(dot3e((double)Tcw[4], (double)Tcw[5], (double)Tcw[6], a, b, c), (double)Tcw[7]);
+    Mz = dadd(dot3e((double)Tcw[8], (double)Tcw[9], (double)Tcw[10], a, b, c), (double)Tcw[11]);
+}
+
+// L1: ComputeLocalNeighbor around the associated scan point (pointcloud.h:733-760, iba_local.cpp:207).
+// The reference searches for every correspondence and only afterwards drops those without a map
+// point (:213) or without a covisible observation (:259); neither test depends on the search, so
+// they come first here.
+__global__ void __launch_bounds__(kWarps * 32, 4)
+k_lm_knn_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
+    const int j = blockIdx.x % kAssocSub, f = blockIdx.x / kAssocSub;
+    int nq;
+    if (!lm_frame_active(wk, pr, f, nq)) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const DevKf K = pk.kf[f];
+    const ScanView S = make_view(pk, K);
     const int C = pk.n_covis;
-    for (int i = j * kWarps + warp; i < nc; i += kAssocSub * kWarps) {
-        const long long slot = K.kp_off + i;
-        const uint32_t kp = wk.corr_kp[slot], sp = wk.corr_sp[slot];
-        const double cx = (double)S.px[sp], cy = (double)S.py[sp], cz = (double)S.pz[sp];
-        // The reference runs ComputeLocalNeighbor for every correspondence and only then drops the
-        // ones without a map point (iba_local.cpp:207-213) or without a covisible observation
-        // (:259); both tests are independent of the neighbour search, so they come first here.
-        const float *mp = pk.kp_mp + (K.kp_off + kp) * 3;
-        if (isnan(mp[0])) continue;  // iba_local.cpp:213
+    for (int qi = j * kWarps + warp; qi < nq; qi += kAssocSub * kWarps) {
+        const uint32_t ci = wk.q_corr[K.kp_off + qi];
+        const uint32_t kp = wk.corr_kp[K.kp_off + ci], sp = wk.corr_sp[K.kp_off + ci];
+        const long long slot = K.mp_off + qi;
         int ncov = 0;
         for (int s = 0; s < C; ++s)
             if (pk.covis_valid[f * C + s] && !isnan(pk.covis_uv[(K.kp_off + kp) * C + s].x)) ++ncov;
-        if (ncov == 0) continue;  // iba_local.cpp:259
-        // ComputeLocalNeighbor around the scan point
-        SinkK kn(pr.k, pr.radius2);
-        traverse(S, cx, cy, cz, kn, lane);
-        const PlaneOut po = plane_from_knn(S, kn, cx, cy, cz, pr, lane, plane_sm[warp]);
-        if (!po.gates_ok) continue;  // m < min_pts || d2[m-1] < min_diff^2
-        const bool valid_plane = po.reg < pr.reg_thr;  // strict '<' (iba_local.cpp:231)
-        if (lane == 0) {
-            lm.slot_kf[slot] = f;
-            lm.slot_kp[slot] = kp;
-            if (valid_plane) {
-                double *g = lm.geo2d + slot * 6;
-                g[0] = cx; g[1] = cy; g[2] = cz; g[3] = po.n.x; g[4] = po.n.y; g[5] = po.n.z;
-                lm.flag2d[slot] = 1;
-            }
+        if (ncov == 0) {  // iba_local.cpp:259
+            if (lane == 0) wk.nb_m[slot] = -1;
+            continue;
         }
-        // MapPoint = Tcw * Pw in fp64, no scale (iba_local.cpp:239-240)
-        const double a = (double)mp[0], b = (double)mp[1], cc = (double)mp[2];
-        const double Mx = dadd(dot3e((double)Tcw[0], (double)Tcw[1], (double)Tcw[2], a, b, cc), (double)Tcw[3]);
-        const double My = dadd(dot3e((double)Tcw[4], (double)Tcw[5], (double)Tcw[6], a, b, cc), (double)Tcw[7]);
-        const double Mz = dadd(dot3e((double)Tcw[8], (double)Tcw[9], (double)Tcw[10], a, b, cc), (double)Tcw[11]);
-        double qx, qy, qz;
+        SinkK kn(pr.k, pr.radius2);
+        traverse(S, (double)S.px[sp], (double)S.py[sp], (double)S.pz[sp], kn, lane);
+        wk.nb[slot * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
+        const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
+        if (lane == 0) { wk.nb_m[slot] = kn.count; wk.nb_last[slot] = last; }
+    }
+}
+
+// L2: plane at the scan point (iba_local.cpp:218-231) -> 3-D/2-D block; decides whether the 3-D search runs
+__global__ void __launch_bounds__(128)
+k_lm_plane_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
+    const int f = blockIdx.x;
+    int nq;
+    if (!lm_frame_active(wk, pr, f, nq)) return;
+    const DevKf K = pk.kf[f];
+    const ScanView S = make_view(pk, K);
+    for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) {
+        const long long slot = K.mp_off + qi;
+        const int m = wk.nb_m[slot];
+        lm.stage[slot] = 0;
+        if (m < 0) continue;
+        const uint32_t ci = wk.q_corr[K.kp_off + qi];
+        const uint32_t kp = wk.corr_kp[K.kp_off + ci], sp = wk.corr_sp[K.kp_off + ci];
+        const double cx = (double)S.px[sp], cy = (double)S.py[sp], cz = (double)S.pz[sp];
+        const PlaneOut po = plane_thread(S, wk.nb + slot * kMaxK, m, wk.nb_last[slot], cx, cy, cz, pr);
+        if (!po.gates_ok) continue;  // m < min_pts || d2[m-1] < min_diff^2 (pointcloud.h:754)
+        const long long cs = K.kp_off + ci;  // block slot = correspondence slot
+        lm.slot_kf[cs] = f;
+        lm.slot_kp[cs] = kp;
+        double *pa = lm.plane_a + slot * 4;
+        pa[0] = po.n.x; pa[1] = po.n.y; pa[2] = po.n.z; pa[3] = po.reg;
+        if (po.reg < pr.reg_thr) {  // strict '<' (iba_local.cpp:231)
+            double *g = lm.geo2d + cs * 6;
+            g[0] = cx; g[1] = cy; g[2] = cz; g[3] = po.n.x; g[4] = po.n.y; g[5] = po.n.z;
+            lm.flag2d[cs] = 1;
+        }
+        lm.stage[slot] = 1;
+    }
+}
+
+// L3: map point -> LiDAR frame with the association extrinsic, 1-NN gate, neighbourhood of that point
+// (iba_local.cpp:283-295)
+__global__ void __launch_bounds__(kWarps * 32, 4)
+k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
+    const int j = blockIdx.x % kAssocSub, f = blockIdx.x / kAssocSub;
+    int nq;
+    if (!lm_frame_active(wk, pr, f, nq)) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const DevKf K = pk.kf[f];
+    const DevCand &c0 = wk.cand[0];
+    const ScanView S = make_view(pk, K);
+    for (int qi = j * kWarps + warp; qi < nq; qi += kAssocSub * kWarps) {
+        const long long slot = K.mp_off + qi;
+        if (lm.stage[slot] != 1) continue;
+        const uint32_t ci = wk.q_corr[K.kp_off + qi];
+        const uint32_t kp = wk.corr_kp[K.kp_off + ci], sp = wk.corr_sp[K.kp_off + ci];
+        double Mx, My, Mz, qx, qy, qz;
+        lm_map_point(pk, K, f, kp, Mx, My, Mz);
         xform(c0.Ri, c0.ti, dmul(Mx, c0.s), dmul(My, c0.s), dmul(Mz, c0.s), qx, qy, qz);  // initSE3.inverse() * (MapPoint * init_scale)
         Sink1 nn;
         traverse(S, qx, qy, qz, nn, lane);
-        if (nn.d > pr.max_3d_dist2) continue;  // iba_local.cpp:289
-        const double nx = (double)S.px[nn.pos], ny = (double)S.py[nn.pos], nz = (double)S.pz[nn.pos];
-        PlaneOut p2 = po;  // the map point's neighbour is very often the associated scan point itself
-        if (nn.pos != sp) {
-            SinkK kn2(pr.k, pr.radius2);
-            traverse(S, nx, ny, nz, kn2, lane);
-            p2 = plane_from_knn(S, kn2, nx, ny, nz, pr, lane, plane_sm[warp]);
+        if (nn.d > pr.max_3d_dist2) {  // iba_local.cpp:289
+            if (lane == 0) lm.nnb_pos[slot] = 0xffffffffu;
+            continue;
         }
-        const bool state = p2.gates_ok && p2.reg < pr.reg_thr;
-        if (lane == 0) {
-            double *g = lm.geo3d + slot * 9;
-            g[0] = Mx; g[1] = My; g[2] = Mz; g[3] = nx; g[4] = ny; g[5] = nz;
-            g[6] = p2.gates_ok ? p2.n.x : 0.0; g[7] = p2.gates_ok ? p2.n.y : 0.0; g[8] = p2.gates_ok ? p2.n.z : 1.0;
-            lm.type3d[slot] = state ? 2 : 1;  // Point2Plane_Factor : Point2Point_Factor (iba_local.cpp:300-309)
-            lm.flag3d[slot] = 1;
+        if (lane == 0) lm.nnb_pos[slot] = nn.pos;
+        if (nn.pos == sp) {  // very often the associated scan point itself: its plane is already known
+            if (lane == 0) lm.nbb_m[slot] = -2;
+            continue;
         }
+        SinkK kn(pr.k, pr.radius2);
+        traverse(S, (double)S.px[nn.pos], (double)S.py[nn.pos], (double)S.pz[nn.pos], kn, lane);
+        lm.nbb[slot * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
+        const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
+        if (lane == 0) { lm.nbb_m[slot] = kn.count; lm.nbb_last[slot] = last; }
+    }
+}
+
+// L4: ComputeLocalNormalSingleThre at the map point's neighbour (pointcloud.h:699-717,651-666) -> 3-D/3-D block
+__global__ void __launch_bounds__(128)
+k_lm_plane_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
+    const int f = blockIdx.x;
+    int nq;
+    if (!lm_frame_active(wk, pr, f, nq)) return;
+    const DevKf K = pk.kf[f];
+    const ScanView S = make_view(pk, K);
+    for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) {
+        const long long slot = K.mp_off + qi;
+        if (lm.stage[slot] != 1) continue;
+        const uint32_t np = lm.nnb_pos[slot];
+        if (np == 0xffffffffu) continue;
+        const uint32_t ci = wk.q_corr[K.kp_off + qi];
+        const uint32_t kp = wk.corr_kp[K.kp_off + ci];
+        const long long cs = K.kp_off + ci;
+        const double nx = (double)S.px[np], ny = (double)S.py[np], nz = (double)S.pz[np];
+        bool gates_ok, state;
+        double n3[3];
+        const int m = lm.nbb_m[slot];
+        if (m == -2) {
+            const double *pa = lm.plane_a + slot * 4;
+            gates_ok = true; n3[0] = pa[0]; n3[1] = pa[1]; n3[2] = pa[2];
+            state = pa[3] < pr.reg_thr;
+        } else {
+            const PlaneOut p2 = plane_thread(S, lm.nbb + slot * kMaxK, m, lm.nbb_last[slot], nx, ny, nz, pr);
+            gates_ok = p2.gates_ok; n3[0] = p2.n.x; n3[1] = p2.n.y; n3[2] = p2.n.z;
+            state = p2.gates_ok && p2.reg < pr.reg_thr;
+        }
+        double Mx, My, Mz;
+        lm_map_point(pk, K, f, kp, Mx, My, Mz);
+        double *g = lm.geo3d + cs * 9;
+        g[0] = Mx; g[1] = My; g[2] = Mz; g[3] = nx; g[4] = ny; g[5] = nz;
+        g[6] = gates_ok ? n3[0] : 0.0; g[7] = gates_ok ? n3[1] : 0.0; g[8] = gates_ok ? n3[2] : 1.0;
+        lm.type3d[cs] = state ? 2 : 1;  // Point2Plane_Factor : Point2Point_Factor (iba_local.cpp:300-309)
+        lm.flag3d[cs] = 1;
     }
 }
 
@@ -288,6 +379,7 @@ template <class T> void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
 
 void lm_free(LmState &lm) {
     dfree(lm.slot_kf); dfree(lm.slot_kp); dfree(lm.flag2d); dfree(lm.type3d); dfree(lm.flag3d); dfree(lm.geo2d); dfree(lm.geo3d);
+    dfree(lm.stage); dfree(lm.plane_a); dfree(lm.nnb_pos); dfree(lm.nbb); dfree(lm.nbb_m); dfree(lm.nbb_last);
     dfree(lm.idx2d); dfree(lm.idx3d); dfree(lm.d_counts); dfree(lm.d_tmp); dfree(lm.partial); dfree(lm.d_cand);
     if (lm.h_cand) cudaFreeHost(lm.h_cand);
     if (lm.h2d_done) cudaEventDestroy(lm.h2d_done);
@@ -306,6 +398,9 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
         TRY(cudaMalloc(&lm.geo2d, 48 * ns)); TRY(cudaMalloc(&lm.geo3d, 72 * ns));
         TRY(cudaMalloc(&lm.idx2d, 4 * ns)); TRY(cudaMalloc(&lm.idx3d, 4 * ns));
         TRY(cudaMalloc(&lm.d_counts, 16));
+        const long long nm = pk.n_mp_total > 0 ? pk.n_mp_total : 1;
+        TRY(cudaMalloc(&lm.stage, nm)); TRY(cudaMalloc(&lm.plane_a, 32 * nm)); TRY(cudaMalloc(&lm.nnb_pos, 4 * nm));
+        TRY(cudaMalloc(&lm.nbb, 4 * nm * kMaxK)); TRY(cudaMalloc(&lm.nbb_m, 4 * nm)); TRY(cudaMalloc(&lm.nbb_last, 8 * nm));
         size_t tb = 0;
         cub::CountingInputIterator<int> it(0);
         TRY(cub::DeviceSelect::Flagged(nullptr, tb, it, lm.flag2d, lm.idx2d, lm.d_counts, (int)ns, st));
@@ -317,7 +412,10 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
     TRY(cudaMemsetAsync(lm.type3d, 0, ns, st));
     TRY(cudaMemsetAsync(lm.flag3d, 0, ns, st));
     TRY(cudaMemsetAsync(lm.d_counts, 0, 16, st));
-    k_lm_associate<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
+    k_lm_knn_a<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
+    k_lm_plane_a<<<(unsigned)pk.n_kf, 128, 0, st>>>(pk, wk, pr, lm);
+    k_lm_knn_b<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
+    k_lm_plane_b<<<(unsigned)pk.n_kf, 128, 0, st>>>(pk, wk, pr, lm);
     TRY(cudaGetLastError());
     cub::CountingInputIterator<int> it(0);
     size_t tb = lm.tmp_bytes;

@@ -19,6 +19,13 @@ struct LmState {
     uint8_t *flag3d = nullptr;    // [n_slots] type3d != 0
     double *geo2d = nullptr;      // [n_slots][6]  p0 (scan point, LiDAR frame), n0 (normal)
     double *geo3d = nullptr;      // [n_slots][9]  map point (camera frame, unscaled), query point, normal
+    // association scratch, one slot per map-point-carrying correspondence (mp_off[f] + qi)
+    uint8_t *stage = nullptr;     // 1 = plane at the scan point passed the gates, 3-D search pending
+    double *plane_a = nullptr;    // [n_mp][4] normal + regression error at the scan point
+    uint32_t *nnb_pos = nullptr;  // [n_mp] 1-NN of the map point (0xffffffff = beyond max_3d_dist)
+    uint32_t *nbb = nullptr;      // [n_mp][32] neighbour list of that point
+    int *nbb_m = nullptr;         // [n_mp] (-2 = same point as the associated one)
+    double *nbb_last = nullptr;
     int *idx2d = nullptr, *idx3d = nullptr;  // [n_slots] dense slot lists
     int *d_counts = nullptr;      // [2]
     int n2d = 0, n3d = 0;
