@@ -1,0 +1,64 @@
+"""include/stlcalib_host.hpp (the C++ mirror of BAError / BALoss / BuildProblem) compiles against the
+C-ABI, fails loudly without a GPU, and on the GPU box returns the same numbers as the ctypes path."""
+import importlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import PKG, ROOT, has_cuda
+
+PKGDIR = os.path.join(ROOT, PKG)
+EXE = os.path.join(ROOT, "tests", "cpp", "host_shim_test")
+
+
+def _build():
+    src = os.path.join(ROOT, "tests", "cpp", "host_shim_test.cpp")
+    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(src), os.path.getmtime(os.path.join(ROOT, "include", "stlcalib_host.hpp"))):
+        return
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), src, "-o", EXE,
+           "-L" + PKGDIR, "-l:libstlcalib.so", "-l:libstlsynth.so", "-Wl,-rpath," + PKGDIR,
+           "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_cpp_shim_compiles_and_links():
+    _build()
+    assert os.path.exists(EXE)
+
+
+@pytest.mark.skipif(has_cuda(), reason="only meaningful without a GPU")
+def test_cpp_shim_fails_loudly_without_gpu():
+    _build()
+    r = subprocess.run([EXE, "1"], capture_output=True, text=True)
+    assert r.returncode == 3 and "sm_100" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_shim_matches_ctypes_path(pkg, synth):
+    _build()
+    r = subprocess.run([EXE, "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    capi = importlib.import_module(PKG + ".capi")
+    host = importlib.import_module(PKG + ".host")
+    pack, x_gt, _ = synth.generate(n_kf=3, beams=32, az_steps=900, n_kp=500, seed=21)
+    X = synth.candidates(x_gt, 3, 0.4)
+    with capi.Context() as ctx:
+        ctx.upload(pack)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("BA ")]
+        assert len(lines) == 3
+        for b, ln in enumerate(lines):
+            left, right = ln.split("|")
+            f = left.split()
+            ba = host.BAError(X[b], ctx)
+            assert (float(f[2]), float(f[3]), float(f[4]), int(f[5]), int(f[6])) == ba
+            bb = right.split()
+            assert bb[1:3] == ["1", "1"]
+            assert np.array_equal(np.array([float(v) for v in bb[3:7]]), np.array(ctx.bbo(ba)))
+        nb = ctx.associate(X[0])
+        L = ctx.linearize(X[1])[0]
+        lm = [ln for ln in r.stdout.splitlines() if ln.startswith("LM ")][0].split()
+        assert [int(v) for v in lm[1:4]] == nb.tolist()
+        assert (float(lm[4]), float(lm[5]), float(lm[6])) == (L[0], L[1], L[8])
