@@ -8,15 +8,16 @@
 //   hand-eye term                  src/examples/iba_global.cpp:264-276
 //   covisible re-projection term   src/examples/iba_global.cpp:291-328
 //
-// One CTA per (candidate, keyframe).  No index is ever built over the projected
-// points (the reference rebuilds a KD-tree per candidate and keyframe): only points
-// within max_pixel_dist of a keypoint can become a correspondence, so the scan is
-// STREAMED once (SoA float4, 12 B/point) through a float32 pre-cull against a
-// shared-memory occupancy bitmap of the dilated keypoints; the ~1-2 % survivors are
-// re-evaluated in the reference's exact fp64 arithmetic and min-reduced per keypoint
-// with (distance, original index) order — the result equals the KD-tree 1-NN +
-// threshold whenever no exact distance tie exists (index-order tie-break otherwise).
-// Bound: HBM: 12 B x points + 16 B x keypoints per launch unit.
+// One CTA per (candidate, keyframe).  No index is ever built over the projected points (the
+// reference rebuilds a KD-tree per candidate and keyframe): only points within max_pixel_dist
+// of a keypoint can become a correspondence, so the scan is STREAMED (SoA float4, 12 B/point)
+// through a float32 pre-cull against a shared-memory occupancy bitmap of the dilated keypoints.
+// The scan is KD-ordered (K0), so whole cells that cannot project into the image are skipped
+// from their bounding boxes without being loaded.  The ~2 % survivors are re-evaluated in the
+// reference's exact fp64 arithmetic against the keypoints of their 8 px grid cells (grid and
+// keypoints staged in shared memory) and min-reduced per keypoint with (distance, original
+// index) order — the KD-tree 1-NN + threshold whenever no exact distance tie exists.
+// Bound: HBM for the stream, latency for the exact part.
 #include "kernels.h"
 #include "se3.cuh"
 
@@ -24,7 +25,8 @@ namespace stl {
 namespace {
 
 constexpr int kThreads = 512;
-constexpr int kSurvCap = 6144;
+constexpr int kSurvCap = 4096;
+constexpr int kMatchCache = 8;  // matches a thread remembers between the two exact passes
 constexpr unsigned long long kInf64 = 0x7ff0000000000000ull;  // +inf bits
 constexpr unsigned long long kNoKey = 0xffffffffffffffffull;
 
@@ -32,7 +34,9 @@ struct Smem {  // fixed part; dynamic arrays follow
     float mu[4], mv[4], mz[4];  // fast projection rows: u*z, v*z, z
     float zmin, ub_u, ub_v, ez;
     float u_hi, v_hi;
-    int n_surv, overflow;
+    float4 plane[5];   // conservative half-spaces of "may pass the pre-cull": a.xyz . p + a.w >= thr
+    float thr[5];
+    int n_surv, overflow, n_groups, recheck;
     int warp_cnt[16], warp_q[16];
     int base_corr, base_q;
     double red[3][16];
@@ -47,7 +51,6 @@ __device__ __forceinline__ bool exact_project(const DevCand &c, double fx, doubl
     v = ddiv(dadd(dmul(fx, yc), dmul(cy, zc)), zc);  // fx, not fy (iba_global.cpp:73)
     return (0.0 <= u && u < W && 0.0 <= v && v < H);
 }
-
 
 // hand-eye term ||log(Tcl*Tl) - log(Tc*Tcl)|| of one keyframe (iba_global.cpp:264-276); kept out of
 // line so that its 4x4 temporaries do not inflate the streaming kernel's register budget
@@ -69,10 +72,43 @@ __device__ __noinline__ double hand_eye_term(const DevPack &pk, const DevCand &c
     return sqrt(ss);
 }
 
-// phase 1: atomicMin of d2 per keypoint; phase 2: atomicMin of (orig, sorted) among the d2 ties
-template <int PHASE>
-__device__ __forceinline__ void exact_point(const DevPack &pk, const DevKf &K, const DevCand &c, const DevParams &pr, uint32_t si,
-                                            unsigned long long *best_d2, unsigned long long *best_key) {
+// Can any point of the box satisfy all five half-spaces?  max over the box of a.p + w is
+// a.c + |a|.e + w (c = centre, e = half extent); float32 evaluation error is covered by a relative
+// slack of 2^-16 on the magnitude of the terms.  Empty boxes (lo > hi) are never visible.
+__device__ __forceinline__ bool box_visible(const Smem &S, float4 lo, float4 hi) {
+    if (!(lo.x <= hi.x)) return false;
+    const float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
+    const float ex = 0.5f * (hi.x - lo.x), ey = 0.5f * (hi.y - lo.y), ez = 0.5f * (hi.z - lo.z);
+    bool vis = true;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const float4 a = S.plane[i];
+        const float ax = fabsf(a.x), ay = fabsf(a.y), az = fabsf(a.z);
+        const float spread = fmaf(ax, ex, fmaf(ay, ey, az * ez));
+        const float centre = fmaf(a.x, cx, fmaf(a.y, cy, fmaf(a.z, cz, a.w)));
+        const float mag = fmaf(ax, fabsf(cx), fmaf(ay, fabsf(cy), fmaf(az, fabsf(cz), fabsf(a.w)))) + spread;
+        vis = vis && (centre + spread + 1.52587890625e-05f * mag >= S.thr[i]);
+    }
+    return vis;
+}
+
+// shared-memory views of the per-keyframe tables
+struct Tables {
+    unsigned long long *best_d2, *best_key;  // [n_kp]
+    float2 *kp;                              // [n_kp]
+    unsigned short *gstart, *gkp;            // [gw*gh+1], [n_kp]
+    uint32_t *surv;                          // [kSurvCap]
+    unsigned short *groups;                  // [n_pad/128]
+    uint32_t *bm;                            // bitmap
+};
+
+// Exact fp64 evaluation of one surviving scan point against the keypoints around its projection.
+// PASS 1: atomicMin of the squared distance per keypoint, remembering the matches in `cache`;
+// PASS 2 (only when some thread's cache overflowed): ties -> atomicMin of (original index, position).
+template <int PASS>
+__device__ __forceinline__ void exact_point(const DevPack &pk, const DevKf &K, const DevCand &c, const DevParams &pr, const Tables &T,
+                                            uint32_t si, int &n_cache, unsigned short *ckp, uint32_t *csi, unsigned long long *cbits,
+                                            int *recheck) {
     const long long g = K.pt_off + si;
     const float xf = pk.px[g], yf = pk.py[g], zf = pk.pz[g];
     double u, v;
@@ -81,22 +117,21 @@ __device__ __forceinline__ void exact_point(const DevPack &pk, const DevKf &K, c
     int gx0 = (int)floor((u - rp) * (1.0 / kGridCell)), gx1 = (int)floor((u + rp) * (1.0 / kGridCell));
     int gy0 = (int)floor((v - rp) * (1.0 / kGridCell)), gy1 = (int)floor((v + rp) * (1.0 / kGridCell));
     gx0 = max(gx0, 0); gy0 = max(gy0, 0); gx1 = min(gx1, K.gw - 1); gy1 = min(gy1, K.gh - 1);
-    const uint32_t *gs = pk.grid_start + K.grid_off;
-    const uint32_t *gk = pk.grid_kp + K.kp_off;
-    const float2 *kp = pk.kp_xy + K.kp_off;
     for (int gy = gy0; gy <= gy1; ++gy) {
-        const uint32_t a = gs[gy * K.gw + gx0], b = gs[gy * K.gw + gx1 + 1];  // cells of one row are contiguous
-        for (uint32_t j = a; j < b; ++j) {
-            const uint32_t k = gk[j];
-            const float2 q = kp[k];
+        const int a = T.gstart[gy * K.gw + gx0], b = T.gstart[gy * K.gw + gx1 + 1];  // cells of one row are contiguous
+        for (int j = a; j < b; ++j) {
+            const int k = T.gkp[j];
+            const float2 q = T.kp[k];
             const double dx = dsub((double)q.x, u), dy = dsub((double)q.y, v);
             const double d2 = dadd(dmul(dx, dx), dmul(dy, dy));  // nanoflann.hpp:524-535, query - data
             if (d2 <= pr.max_pixel_dist2) {
                 const unsigned long long bits = (unsigned long long)__double_as_longlong(d2);
-                if (PHASE == 1) {
-                    atomicMin(&best_d2[k], bits);
-                } else if (bits == best_d2[k]) {
-                    atomicMin(&best_key[k], ((unsigned long long)pk.orig[g] << 32) | si);
+                if (PASS == 1) {
+                    atomicMin(&T.best_d2[k], bits);
+                    if (n_cache < kMatchCache) { ckp[n_cache] = (unsigned short)k; csi[n_cache] = si; cbits[n_cache] = bits; ++n_cache; }
+                    else *recheck = 1;
+                } else if (bits == T.best_d2[k]) {
+                    atomicMin(&T.best_key[k], ((unsigned long long)pk.orig[g] << 32) | si);
                 }
             }
         }
@@ -110,13 +145,25 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
     const DevKf K = pk.kf[f];
     const DevCand &c = wk.cand[b];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
-    unsigned long long *best_d2 = reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(Smem) + 15) & ~size_t(15)));
-    unsigned long long *best_key = best_d2 + K.n_kp;
-    uint32_t *surv = reinterpret_cast<uint32_t *>(best_key + K.n_kp);
-    uint32_t *bm = surv + kSurvCap;
+    const int ncell = K.gw * K.gh;
+    Tables T;
+    {
+        unsigned char *p = smem_raw + ((sizeof(Smem) + 15) & ~size_t(15));
+        T.best_d2 = reinterpret_cast<unsigned long long *>(p); p += 8 * (size_t)K.n_kp;
+        T.best_key = reinterpret_cast<unsigned long long *>(p); p += 8 * (size_t)K.n_kp;
+        T.kp = reinterpret_cast<float2 *>(p); p += 8 * (size_t)K.n_kp;
+        T.surv = reinterpret_cast<uint32_t *>(p); p += 4 * (size_t)kSurvCap;
+        T.bm = reinterpret_cast<uint32_t *>(p); p += 4 * (size_t)K.bm_wpr * K.bm_rows;
+        T.gstart = reinterpret_cast<unsigned short *>(p); p += 2 * (size_t)((ncell + 2) & ~1);
+        T.gkp = reinterpret_cast<unsigned short *>(p); p += 2 * (size_t)((K.n_kp + 1) & ~1);
+        T.groups = reinterpret_cast<unsigned short *>(p);
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long clk[8];
+    const bool timing = wk.k1_clk != nullptr && tid == 0;
+    if (timing) clk[0] = clock64();
 
-    // ---- prologue: fast rows, error bounds, bitmap, per-keypoint minima
+    // ---- prologue: fast rows, error bounds, culling half-spaces; tables into shared memory
     if (tid == 0) {
         const double fx = K.fx, cx = K.cx, cy = K.cy;
         double ru[4], rv[4], rz[4];
@@ -129,7 +176,7 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
         rv[3] = fx * c.t[1] + cy * c.t[2];
         rz[3] = c.t[2];
         for (int j = 0; j < 4; ++j) { S.mu[j] = (float)ru[j]; S.mv[j] = (float)rv[j]; S.mz[j] = (float)rz[j]; }
-        // float32 error model of the fast path (DESIGN.md §K1-precull): 3 FMAs + rounded matrix entries
+        // float32 error model of the fast path (DESIGN.md §K1): 3 FMAs + rounded matrix entries
         const double eps = 1.1920928955078125e-07, pm = K.pmax;
         const double Az = (fabs(rz[0]) + fabs(rz[1]) + fabs(rz[2])) * pm + fabs(rz[3]);
         const double Au = (fabs(ru[0]) + fabs(ru[1]) + fabs(ru[2])) * pm + fabs(ru[3]);
@@ -144,20 +191,62 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
         S.u_hi = (float)(kBmCell * (K.bm_wpr * 32 - 1));  // never index past the row
         S.u_hi = fminf(S.u_hi, (float)(K.W + kBmCell));
         S.v_hi = (float)(K.H + kBmCell);
-        S.n_surv = 0;
-        S.overflow = 0;
-        S.base_corr = 0;
-        S.base_q = 0;
+        // Half-spaces every point that can pass the pre-cull satisfies (main case g_i >= 0; points of
+        // the thin slab z <= zmin only satisfy g_i >= -m, so -m is the threshold).
+        {
+            const float uh = S.u_hi, vh = S.v_hi, two = (float)kBmCell;
+            const float rzx = S.mz[0], rzy = S.mz[1], rzz = S.mz[2], rzw = S.mz[3];
+            S.plane[0] = make_float4(rzx, rzy, rzz, rzw);
+            S.plane[1] = make_float4(S.mu[0] + two * rzx, S.mu[1] + two * rzy, S.mu[2] + two * rzz, S.mu[3] + two * rzw);
+            S.plane[2] = make_float4(uh * rzx - S.mu[0], uh * rzy - S.mu[1], uh * rzz - S.mu[2], uh * rzw - S.mu[3]);
+            S.plane[3] = make_float4(S.mv[0] + two * rzx, S.mv[1] + two * rzy, S.mv[2] + two * rzz, S.mv[3] + two * rzw);
+            S.plane[4] = make_float4(vh * rzx - S.mv[0], vh * rzy - S.mv[1], vh * rzz - S.mv[2], vh * rzw - S.mv[3]);
+            const float mslab_u = S.ub_u + (uh + two) * (S.ez + S.zmin), mslab_v = S.ub_v + (vh + two) * (S.ez + S.zmin);
+            S.thr[0] = -S.ez;
+            S.thr[1] = -mslab_u; S.thr[2] = -mslab_u;
+            S.thr[3] = -mslab_v; S.thr[4] = -mslab_v;
+        }
+        S.n_surv = 0; S.overflow = 0; S.n_groups = 0; S.recheck = 0;
+        S.base_corr = 0; S.base_q = 0;
     }
-    for (int k = tid; k < K.n_kp; k += kThreads) { best_d2[k] = kInf64; best_key[k] = kNoKey; }
     {
+        const float2 *kpg = pk.kp_xy + K.kp_off;
+        const uint32_t *gkg = pk.grid_kp + K.kp_off, *gsg = pk.grid_start + K.grid_off, *bmg = pk.bitmap + K.bm_off;
+        for (int k = tid; k < K.n_kp; k += kThreads) {
+            T.best_d2[k] = kInf64; T.best_key[k] = kNoKey;
+            T.kp[k] = kpg[k];
+            T.gkp[k] = (unsigned short)gkg[k];
+        }
+        for (int i = tid; i <= ncell; i += kThreads) T.gstart[i] = (unsigned short)gsg[i];
         const int nw = K.bm_wpr * K.bm_rows;
-        const uint32_t *src = pk.bitmap + K.bm_off;
-        for (int i = tid; i < nw; i += kThreads) bm[i] = src[i];
+        for (int i = tid; i < nw; i += kThreads) T.bm[i] = bmg[i];
+    }
+    __syncthreads();
+    if (timing) clk[1] = clock64();
+
+    // ---- phase A1: which 128-point groups can hold a visible point?  One warp per level-1 cell
+    // (1024 points): test the cell, then its 32 leaf boxes, one per lane.
+    {
+        const float4 *nlo = pk.node_lo + K.node_off, *nhi = pk.node_hi + K.node_off;
+        const int n_l1 = (K.n_pad + 1023) >> 10;
+        for (int node = warp; node < n_l1; node += kThreads / 32) {
+            if (!box_visible(S, nlo[K.n0 + node], nhi[K.n0 + node])) continue;
+            const bool lv = box_visible(S, nlo[node * 32 + lane], nhi[node * 32 + lane]);
+            const unsigned lmask = __ballot_sync(0xffffffffu, lv);
+            // lane g < 8 owns group g of the cell (leaves 4g .. 4g+3)
+            const bool need = lane < 8 && ((lmask >> (4 * lane)) & 0xfu) && (node * 8 + lane) * 128 < K.n_pad;
+            const unsigned gm = __ballot_sync(0xffffffffu, need);
+            if (gm) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&S.n_groups, __popc(gm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (need) T.groups[base + __popc(gm & ((1u << lane) - 1))] = (unsigned short)(node * 8 + lane);
+            }
+        }
     }
     __syncthreads();
 
-    // ---- phase A: stream the scan (SoA float4 loads, 12 B/point), float32 pre-cull
+    // ---- phase A2: stream the visible groups (SoA float4 loads, 12 B/point), float32 pre-cull
     {
         const float mu0 = S.mu[0], mu1 = S.mu[1], mu2 = S.mu[2], mu3 = S.mu[3];
         const float mv0 = S.mv[0], mv1 = S.mv[1], mv2 = S.mv[2], mv3 = S.mv[3];
@@ -167,9 +256,10 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
         const float4 *X = reinterpret_cast<const float4 *>(pk.px + K.pt_off);
         const float4 *Y = reinterpret_cast<const float4 *>(pk.py + K.pt_off);
         const float4 *Z = reinterpret_cast<const float4 *>(pk.pz + K.pt_off);
-        const int n4 = K.n_pad >> 2;
+        const int ng = S.n_groups;
 #pragma unroll 2
-        for (int i = tid; i < n4; i += kThreads) {
+        for (int w = warp; w < ng; w += kThreads / 32) {
+            const int i = (int)T.groups[w] * 32 + lane;  // float4 index
             const float4 x4 = ld_stream_f4(X + i), y4 = ld_stream_f4(Y + i), z4 = ld_stream_f4(Z + i);
             const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
@@ -179,12 +269,12 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
                 const float vz = fmaf(mv0, xs[e], fmaf(mv1, ys[e], fmaf(mv2, zs[e], mv3)));
                 bool pass = false;
                 if (zc > zmin) {
-                    // inside the apron-extended image?  (no division for the ~87 % that are not)
+                    // inside the apron-extended image?  (no division for the points that are not)
                     if (uz >= lo * zc && uz < u_hi * zc && vz >= lo * zc && vz < v_hi * zc) {
                         const float inv = __frcp_rn(zc);
                         const int cu = min(max((int)floorf(uz * inv * (1.0f / kBmCell)) + 1, 0), cu_max);
                         const int cv = min(max((int)floorf(vz * inv * (1.0f / kBmCell)) + 1, 0), cv_max);
-                        pass = (bm[cv * wpr + (cu >> 5)] >> (cu & 31)) & 1u;
+                        pass = (T.bm[cv * wpr + (cu >> 5)] >> (cu & 31)) & 1u;
                     }
                 } else if (zc > -S.ez) {
                     // thin slab in front of the camera plane where the float32 bound does not hold: exact path decides
@@ -192,24 +282,42 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
                 }
                 if (pass) {
                     const int pos = atomicAdd(&S.n_surv, 1);
-                    if (pos < kSurvCap) surv[pos] = (uint32_t)(i * 4 + e);
+                    if (pos < kSurvCap) T.surv[pos] = (uint32_t)(i * 4 + e);
                     else S.overflow = 1;
                 }
             }
         }
     }
     __syncthreads();
+    if (timing) clk[2] = clock64();
 
     // ---- phases B/C: exact fp64 re-evaluation of the survivors, (d2, original index) minimum per keypoint
     const bool ovf = S.overflow != 0;
     const int ns = ovf ? K.n_pts : min(S.n_surv, kSurvCap);
-    for (int s = tid; s < ns; s += kThreads) exact_point<1>(pk, K, c, pr, ovf ? (uint32_t)s : surv[s], best_d2, best_key);
-    __syncthreads();
-    for (int s = tid; s < ns; s += kThreads) exact_point<2>(pk, K, c, pr, ovf ? (uint32_t)s : surv[s], best_d2, best_key);
+    {
+        unsigned short ckp[kMatchCache];
+        uint32_t csi[kMatchCache];
+        unsigned long long cbits[kMatchCache];
+        int n_cache = 0;
+        for (int s = tid; s < ns; s += kThreads)
+            exact_point<1>(pk, K, c, pr, T, ovf ? (uint32_t)s : T.surv[s], n_cache, ckp, csi, cbits, &S.recheck);
+        __syncthreads();
+        if (timing) clk[3] = clock64();
+        if (!S.recheck) {  // the usual case: every match is still in its thread's cache
+            for (int i = 0; i < n_cache; ++i)
+                if (cbits[i] == T.best_d2[ckp[i]])
+                    atomicMin(&T.best_key[ckp[i]], ((unsigned long long)pk.orig[K.pt_off + csi[i]] << 32) | csi[i]);
+        } else {
+            for (int s = tid; s < ns; s += kThreads)
+                exact_point<2>(pk, K, c, pr, T, ovf ? (uint32_t)s : T.surv[s], n_cache, ckp, csi, cbits, &S.recheck);
+        }
+    }
     __syncthreads();
     if (ovf && tid == 0 && wk.overflow) atomicAdd(wk.overflow, 1);
+    if (timing) clk[4] = clock64();
 
     // ---- phase D: corrset in keypoint order (block scan), query list = correspondences with a map point
+    unsigned long long *best_key = T.best_key;
     const long long out_base = (long long)b * pk.n_kp_total + K.kp_off;
     const float *mp = pk.kp_mp + K.kp_off * 3;
     for (int k0 = 0; k0 < K.n_kp; k0 += kThreads) {
@@ -239,6 +347,7 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
         }
         __syncthreads();
     }
+    if (timing) clk[5] = clock64();
     const int ncorr = S.base_corr, nq = S.base_q;
     const bool kept = ncorr >= pr.num_min_corr;  // iba_global.cpp:203
 
@@ -279,6 +388,7 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
     }
     if (lane == 0) { S.red[0][warp] = s2d; S.red[1][warp] = v2d; S.red[2][warp] = c2d; }
     __syncthreads();
+    if (timing) clk[6] = clock64();
     if (tid == 0) {
         FrameRec r;
         r.s2d = r.v2d = r.c2d = 0;
@@ -291,13 +401,20 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
         wk.frame[(long long)b * pk.n_kf + f] = r;
         wk.n_corr[(long long)b * pk.n_kf + f] = ncorr;
         wk.n_q[(long long)b * pk.n_kf + f] = kept ? nq : 0;
+        if (timing) {
+            clk[7] = clock64();
+            long long *o = wk.k1_clk + (long long)blockIdx.x * 8;
+            for (int i = 0; i < 7; ++i) o[i] = clk[i + 1] - clk[i];
+            o[7] = S.n_surv;
+        }
     }
 }
 
 }  // namespace
 
-size_t assoc2d_smem_bytes(int max_kp, int max_bm_words) {
-    return ((sizeof(Smem) + 15) & ~size_t(15)) + (size_t)max_kp * 16 + (size_t)kSurvCap * 4 + (size_t)max_bm_words * 4;
+size_t assoc2d_smem_bytes(int max_kp, int max_bm_words, int max_cells, int max_groups) {
+    return ((sizeof(Smem) + 15) & ~size_t(15)) + (size_t)max_kp * 24 + (size_t)kSurvCap * 4 + (size_t)max_bm_words * 4 +
+           2 * (size_t)((max_cells + 2) & ~1) + 2 * (size_t)((max_kp + 1) & ~1) + 2 * (size_t)max_groups + 16;
 }
 
 // The opt-in dynamic shared-memory limit is a per-function, per-device attribute shared by every

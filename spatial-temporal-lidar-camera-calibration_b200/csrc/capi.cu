@@ -109,7 +109,7 @@ void free_work(stl_ctx *c) {
     DevWork &w = c->wk;
     dfree(w.cand); dfree(w.corr_kp); dfree(w.corr_pt); dfree(w.corr_sp); dfree(w.q_corr); dfree(w.n_corr); dfree(w.n_q);
     dfree(w.frame); dfree(w.align); dfree(w.nn_pos); dfree(w.nb); dfree(w.nb_m); dfree(w.nb_last); dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn); dfree(w.dbg_stats);
-    dfree(w.overflow);
+    dfree(w.overflow); dfree(w.k1_clk);
     w = DevWork();
     c->wk_cap = 0;
     c->dbg_alloc = false;
@@ -181,6 +181,7 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
             const size_t nm = (size_t)std::max<long long>(pk.n_mp_total, 1) * cap;
             CK(cudaMalloc(&w.nn_pos, 4 * nm)); CK(cudaMalloc(&w.nb, 4 * nm * kMaxK)); CK(cudaMalloc(&w.nb_m, 4 * nm)); CK(cudaMalloc(&w.nb_last, 8 * nm));
         }
+        if (getenv("STL_K1_CLK")) { CK(cudaMalloc(&w.k1_clk, 64 * nf)); CK(cudaMemset(w.k1_clk, 0, 64 * nf)); }
         CK(cudaMalloc(&w.overflow, 4));
         CK(cudaMemset(w.overflow, 0, 4));
         ctx->wk_cap = cap;
@@ -372,7 +373,10 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     }
     const long long NK = p->kp_offset[F];
     ctx->max_kp = max_kp; ctx->max_bm_words = max_bm;
-    ctx->k1_smem = assoc2d_smem_bytes(max_kp, max_bm);
+    int max_cells = 0, max_groups = 0;
+    for (int f = 0; f < F; ++f) { max_cells = std::max(max_cells, hk[f].gw * hk[f].gh); max_groups = std::max(max_groups, hk[f].n_pad / 128); }
+    if (max_kp > 65535) return fail(ctx, STL_ERR_CAPACITY, "more than 65535 keypoints in a keyframe");
+    ctx->k1_smem = assoc2d_smem_bytes(max_kp, max_bm, max_cells, max_groups);
     int smem_optin = 0;
     CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     if (ctx->k1_smem > (size_t)smem_optin)
@@ -578,10 +582,17 @@ stl_status_t stl_debug_frame(stl_ctx_t *ctx, int32_t b, int32_t kf, double out[1
     CK(cudaMemcpy(a.data(), ctx->wk.align + (size_t)kf * ctx->wk.sub, sizeof(AlignRec) * ctx->wk.sub, cudaMemcpyDeviceToHost));
     out[0] = r.s2d; out[1] = r.v2d; out[2] = r.c2d; out[3] = r.she; out[4] = r.che; out[5] = r.kept; out[6] = r.ncorr; out[7] = r.nq;
     for (int i = 8; i < 13; ++i) out[i] = 0;
+    if (ctx->wk.k1_clk) {
+        std::vector<long long> h((size_t)ctx->pk.n_kf * 8);
+        cudaMemcpy(h.data(), ctx->wk.k1_clk, 64 * (size_t)ctx->pk.n_kf, cudaMemcpyDeviceToHost);
+        double a[8] = {0};
+        for (int f = 0; f < ctx->pk.n_kf; ++f) for (int i = 0; i < 8; ++i) a[i] += (double)h[(size_t)f * 8 + i] / ctx->pk.n_kf;
+        fprintf(stderr, "[stl] K1 mean clocks/unit: prologue %.0f | stream %.0f | exact-1 %.0f | exact-2 %.0f | compact %.0f | covis %.0f | epilogue %.0f | survivors %.0f\n", a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+    }
     if (getenv("STL_DEBUG_STATS")) {
         unsigned long long st[8];
         cudaMemcpy(st, ctx->wk.dbg_stats, 64, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[stl] traversal stats (cumulative): queries %llu | 1-NN iters %.1f visits %.1f | k-NN iters %.1f visits %.1f inserts %.1f m %.1f\n",
+        if (st[0]) fprintf(stderr, "[stl] traversal stats (cumulative): queries %llu | 1-NN iters %.1f visits %.1f | k-NN iters %.1f visits %.1f inserts %.1f m %.1f\n",
                 st[0], (double)st[1] / st[0], (double)st[2] / st[0], (double)st[3] / st[0], (double)st[4] / st[0], (double)st[5] / st[0], (double)st[6] / st[0]);
     }
     for (auto &x : a) { out[8] += x.s3d; out[9] += x.v3d; out[10] += x.c3d; out[11] += x.vpl; out[12] += x.vpt; }

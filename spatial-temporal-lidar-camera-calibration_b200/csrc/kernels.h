@@ -54,6 +54,7 @@ struct DevWork {
     double *dbg_dist = nullptr;
     uint32_t *dbg_knn = nullptr;  // [n_kp_total][32]
     unsigned long long *dbg_stats = nullptr;  // [8] traversal statistics (debug runs)
+    long long *k1_clk = nullptr;  // optional [units][8] phase clocks of K1 (diagnostic, STL_K1_CLK=1)
     int *overflow = nullptr;      // K1 survivor-list overflow counter (diagnostic)
 };
 
@@ -63,7 +64,7 @@ cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int
                              DevPack &pack, cudaStream_t st);
 
 // ---- K1 (assoc2d.cu) ------------------------------------------------------------
-size_t assoc2d_smem_bytes(int max_kp, int max_bm_words);
+size_t assoc2d_smem_bytes(int max_kp, int max_bm_words, int max_cells, int max_groups);
 cudaError_t assoc2d_configure(size_t smem);
 cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, cudaStream_t st);
 
