@@ -71,6 +71,15 @@ typedef struct stl_params {
     int32_t norm_max_pts;         /* 30    k of the k-NN (<= 32)                     */
     int32_t norm_min_pts;         /* 5                                               */
     int32_t use_plane;            /* 1                                               */
+    /* LM path, depth by Gaussian-process regression for non-planar neighbourhoods
+     * (IBA_GPRFactor, IBACalib2.hpp:427-564; call site iba_local.cpp:272-280, commented
+     * out in the reference, hence off by default).  Hyper-parameters are fixed per problem
+     * (GPRParams.optimize = false); the per-factor L-BFGS fit (GPR::fit, GPR.hpp:350-387)
+     * needs Ceres and stays on the host. */
+    int32_t use_gpr;              /* 0                                               */
+    double gpr_sigma;             /* 10    init_sigma  (IBACalib2.hpp:128)           */
+    double gpr_l;                 /* 10    init_l                                    */
+    double gpr_sigma_noise;       /* 1e-10 sigma_noise                               */
 } stl_params_t;
 
 /*
@@ -149,8 +158,9 @@ typedef struct stl_lin_sums {
     double n_blocks_pt; /* Point2Point_Factor blocks           */
     double n_blocks_pl; /* Point2Plane_Factor blocks           */
     double n_residuals; /* total scalar residuals              */
+    double n_blocks_gpr; /* IBA_GPRFactor blocks               */
 } stl_lin_sums_t;
-#define STL_LIN_NSUMS 61
+#define STL_LIN_NSUMS 62
 
 typedef struct stl_ctx stl_ctx_t;
 
@@ -200,8 +210,8 @@ void stl_bbo(const stl_params_t *params, const stl_ba_error_t *e, double bbo[4])
 
 /* BuildProblem (iba_local.cpp:145-323): associates at x0[7] and freezes the
  * residual blocks (plane / point-to-point / point-to-plane) on the device.
- * n_blocks[3] (optional) receives the block counts {2d, pt, pl} of this pack. */
-stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[3]);
+ * n_blocks[4] (optional) receives the block counts {plane 2d, pt, pl, gpr 2d} of this pack. */
+stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[4]);
 
 /* Evaluates the frozen blocks at B parameter vectors: cost, J^T r, J^T J
  * (Ceres semantics: Huber via residual/Jacobian rescaling). */

@@ -45,8 +45,8 @@ class Context {
         check(stl_eval_batch(ctx_, x, B, out.data()), "stl_eval_batch");
         return out;
     }
-    std::array<int64_t, 3> associate(const double *x0) {
-        std::array<int64_t, 3> n{};
+    std::array<int64_t, 4> associate(const double *x0) {
+        std::array<int64_t, 4> n{};
         check(stl_associate(ctx_, x0, n.data()), "stl_associate");
         return n;
     }
@@ -115,7 +115,7 @@ class BALoss {
 class LMProblem {
   public:
     explicit LMProblem(Context &ctx) : ctx_(ctx) {}
-    std::array<int64_t, 3> build(const double x0[7]) { return ctx_.associate(x0); }
+    std::array<int64_t, 4> build(const double x0[7]) { return ctx_.associate(x0); }
     stl_lin_sums_t evaluate(const double x[7]) { return ctx_.linearize(x, 1)[0]; }
 
   private:

@@ -176,7 +176,7 @@ class Oracle:
 
     def associate(self, x0, strict: bool = False):
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
-        nb = np.zeros(3, np.int64)
+        nb = np.zeros(4, np.int64)
         ties = np.zeros(3, np.int64)
         self.lib.orc_associate(self.h, _d(x0), int(strict), nb.ctypes.data_as(_i64p), ties.ctypes.data_as(_i64p))
         return nb, ties

@@ -55,7 +55,7 @@ struct FrameDebug {
 
 // Residual block frozen by BuildProblem (iba_local.cpp:263-309)
 struct Block {
-    int type;  // 0 = IBA_PlaneFactor, 1 = Point2Point_Factor, 2 = Point2Plane_Factor
+    int type;  // 0 = IBA_PlaneFactor, 1 = Point2Point_Factor, 2 = Point2Plane_Factor, 3 = IBA_GPRFactor
     int kf;
     uint32_t kp;
     // plane factor
@@ -64,6 +64,10 @@ struct Block {
     double R[STL_MAX_COVIS][9], t[STL_MAX_COVIS][3], u1[STL_MAX_COVIS], v1[STL_MAX_COVIS];
     // 3-D factors
     double map_pt[3], query_pt[3], normal[3];
+    // GPR factor: neighbour points (LiDAR frame, distance order, the scan point itself first) and hyper-parameters
+    int gm;
+    double gpts[32][3];
+    double sigma, l, sigma_noise;
 };
 
 template <class Tree2, class Tree3>
@@ -442,6 +446,17 @@ class Oracle {
                     b.u0 = pk_.kp_xy[(k0 + c.kp) * 2]; b.v0 = pk_.kp_xy[(k0 + c.kp) * 2 + 1];
                     for (int i = 0; i < 3; ++i) { b.p0[i] = nn_pt[i]; b.n0[i] = nrm[i]; }
                     per[f].push_back(b);
+                } else if (pr_.use_gpr) {
+                    // the branch the reference keeps commented out (iba_local.cpp:272-280): depth of the
+                    // keypoint by GP regression over the neighbour points, fixed hyper-parameters
+                    b.type = 3;
+                    b.fx = pk_.intrinsics[f * 4]; b.fy = pk_.intrinsics[f * 4 + 1]; b.cx = pk_.intrinsics[f * 4 + 2]; b.cy = pk_.intrinsics[f * 4 + 3];
+                    b.u0 = pk_.kp_xy[(k0 + c.kp) * 2]; b.v0 = pk_.kp_xy[(k0 + c.kp) * 2 + 1];
+                    b.gm = (int)m;
+                    for (size_t i = 0; i < m; ++i)
+                        for (int a = 0; a < 3; ++a) b.gpts[i][a] = PL[(size_t)idx[i] * 3 + a];
+                    b.sigma = pr_.gpr_sigma; b.l = pr_.gpr_l; b.sigma_noise = pr_.gpr_sigma_noise;
+                    per[f].push_back(b);
                 }
                 // 3-D term (iba_local.cpp:283-309)
                 double Ms[3] = {MapPoint[0] * s0, MapPoint[1] * s0, MapPoint[2] * s0}, Ml[3];
@@ -516,6 +531,75 @@ class Oracle {
             }
             return 2 * b.ncov;
         }
+        if (b.type == 3) {  // IBA_GPRFactor::operator() (IBACalib2.hpp:472-507) + TGPR::fit_predict (GPR.hpp:449-491)
+            T R[9], t[3], s;
+            Sim3Exp<T>(x, R, t, s);
+            const T fx(b.fx), fy(b.fy), cx(b.cx), cy(b.cy), u0(b.u0), v0(b.v0);
+            const int n = b.gm;
+            std::vector<T> X(2 * n), y(n), K((size_t)n * n), alpha(n), ks(n);
+            for (int j = 0; j < n; ++j) {
+                const T p[3] = {T(b.gpts[j][0]), T(b.gpts[j][1]), T(b.gpts[j][2])};
+                T tf[3];
+                matvec3(R, p, tf);
+                for (int a = 0; a < 3; ++a) tf[a] = tf[a] + t[a];
+                X[2 * j] = fx * tf[0] / tf[2] + cx;
+                X[2 * j + 1] = fy * tf[1] / tf[2] + cy;
+                y[j] = tf[2];
+            }
+            const T sigma(b.sigma), l(b.l);
+            const T sigma2 = sigma * sigma, coef = T(-0.5) / (l * l);
+            // self_pdist (GPR.hpp:41-54) + computeCovariance (GPR.hpp:464-467) + sigma_noise * I
+            for (int r = 0; r < n; ++r) {
+                K[(size_t)r * n + r] = sigma2 * exp(coef * T(0.0)) + T(b.sigma_noise);
+                for (int c2 = r + 1; c2 < n; ++c2) {
+                    const T dx = X[2 * r] - X[2 * c2], dy = X[2 * r + 1] - X[2 * c2 + 1];
+                    const T kv = sigma2 * exp(coef * (dx * dx + dy * dy));
+                    K[(size_t)r * n + c2] = kv;
+                    K[(size_t)c2 * n + r] = kv;
+                }
+            }
+            // Eigen::LLT, unblocked lower Cholesky (size < 32), then the two triangular solves
+            for (int k = 0; k < n; ++k) {
+                T xk = K[(size_t)k * n + k];
+                for (int j = 0; j < k; ++j) xk = xk - K[(size_t)k * n + j] * K[(size_t)k * n + j];
+                xk = sqrt(xk);
+                K[(size_t)k * n + k] = xk;
+                for (int i = k + 1; i < n; ++i) {
+                    T v = K[(size_t)i * n + k];
+                    for (int j = 0; j < k; ++j) v = v - K[(size_t)i * n + j] * K[(size_t)k * n + j];
+                    K[(size_t)i * n + k] = v / xk;
+                }
+            }
+            for (int i = 0; i < n; ++i) {
+                T v = y[i];
+                for (int j = 0; j < i; ++j) v = v - K[(size_t)i * n + j] * alpha[j];
+                alpha[i] = v / K[(size_t)i * n + i];
+            }
+            for (int i = n - 1; i >= 0; --i) {
+                T v = alpha[i];
+                for (int j = i + 1; j < n; ++j) v = v - K[(size_t)j * n + i] * alpha[j];
+                alpha[i] = v / K[(size_t)i * n + i];
+            }
+            // Kstar = rbf_kernel_2d(train_x, {test_x}) (GPR.hpp:57-63), mu = Kstar^T alpha
+            const T inv_l2 = T(1.0) / (l * l);
+            T z(0.0);
+            for (int j = 0; j < n; ++j) {
+                const T dx = X[2 * j] - u0, dy = X[2 * j + 1] - v0;
+                ks[j] = sigma2 * exp(T(-0.5) * inv_l2 * (dx * dx + dy * dy));
+                z = z + ks[j] * alpha[j];
+            }
+            const T P0[3] = {z * (u0 - cx) / fx, z * (v0 - cy) / fy, z};
+            for (int i = 0; i < b.ncov; ++i) {
+                T Rm[9], tv[3], P1[3];
+                for (int a = 0; a < 9; ++a) Rm[a] = T(b.R[i][a]);
+                for (int a = 0; a < 3; ++a) tv[a] = T(b.t[i][a]) * s;
+                matvec3(Rm, P0, P1);
+                for (int a = 0; a < 3; ++a) P1[a] = P1[a] + tv[a];
+                e[2 * i] = (fx * P1[0] / P1[2] + cx) - T(b.u1[i]);
+                e[2 * i + 1] = (fy * P1[1] / P1[2] + cy) - T(b.v1[i]);
+            }
+            return 2 * b.ncov;
+        }
         // Point2Point_Factor / Point2Plane_Factor (IBACalib2.hpp:570-584,611-625)
         const T inv[6] = {-x[0], -x[1], -x[2], -x[3], -x[4], -x[5]};
         T Rlc[9], tlc[3];
@@ -547,7 +631,7 @@ class Oracle {
             const int nr = block_residuals<D>(b, xd, e);
             double sq = 0;
             for (int i = 0; i < nr; ++i) sq += e[i].a * e[i].a;
-            const double delta = b.type == 0 ? pr_.robust_kernel_delta : pr_.robust_kernel_3ddelta;
+            const double delta = (b.type == 0 || b.type == 3) ? pr_.robust_kernel_delta : pr_.robust_kernel_3ddelta;
             double rho0, rho1;  // ceres::HuberLoss::Evaluate
             if (sq > delta * delta) { const double r = std::sqrt(sq); rho0 = 2 * delta * r - delta * delta; rho1 = std::max(std::numeric_limits<double>::min(), delta / r); }
             else { rho0 = sq; rho1 = 1.0; }
@@ -563,7 +647,7 @@ class Oracle {
                 }
             }
             out->n_residuals += nr;
-            if (b.type == 0) out->n_blocks_2d += 1; else if (b.type == 1) out->n_blocks_pt += 1; else out->n_blocks_pl += 1;
+            if (b.type == 0) out->n_blocks_2d += 1; else if (b.type == 1) out->n_blocks_pt += 1; else if (b.type == 2) out->n_blocks_pl += 1; else out->n_blocks_gpr += 1;
         }
     }
 

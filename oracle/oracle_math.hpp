@@ -48,6 +48,9 @@ template <int N> inline Dual<N> cos(const Dual<N> &f) { Dual<N> h; h.a = std::co
 template <int N> inline Dual<N> sin(const Dual<N> &f) { Dual<N> h; h.a = std::sin(f.a); const double t = std::cos(f.a); for (int i = 0; i < N; ++i) h.v[i] = t * f.v[i]; return h; }
 // Jet pow(f, double p): (f.a^p, p*f.a^(p-1) * f.v)
 template <int N> inline Dual<N> pow(const Dual<N> &f, double p) { Dual<N> h; h.a = std::pow(f.a, p); const double t = p * std::pow(f.a, p - 1.0); for (int i = 0; i < N; ++i) h.v[i] = t * f.v[i]; return h; }
+// Jet exp(f): (e^a, e^a * f.v)
+template <int N> inline Dual<N> exp(const Dual<N> &f) { Dual<N> h; h.a = std::exp(f.a); for (int i = 0; i < N; ++i) h.v[i] = h.a * f.v[i]; return h; }
+inline double exp(double x) { return std::exp(x); }
 inline double sqrt(double x) { return std::sqrt(x); }
 inline double cos(double x) { return std::cos(x); }
 inline double sin(double x) { return std::sin(x); }

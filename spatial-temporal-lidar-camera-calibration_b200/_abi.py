@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 STL_MAX_COVIS = 10
 STL_EVAL_NSUMS = 12
-STL_LIN_NSUMS = 61
+STL_LIN_NSUMS = 62
 STL_NSTAGES = 8
 STAGE_NAMES = ("assoc2d", "knn3d", "reduce", "linearize", "build", "assoc_lm", "s6", "s7")
 
@@ -46,6 +46,10 @@ class Params(C.Structure):
         ("norm_max_pts", C.c_int32),
         ("norm_min_pts", C.c_int32),
         ("use_plane", C.c_int32),
+        ("use_gpr", C.c_int32),
+        ("gpr_sigma", C.c_double),
+        ("gpr_l", C.c_double),
+        ("gpr_sigma_noise", C.c_double),
     ]
 
 
@@ -85,7 +89,7 @@ class BAErrorOut(C.Structure):
 class LinSums(C.Structure):
     _fields_ = [("cost", C.c_double), ("g", C.c_double * 7), ("H", C.c_double * 49),
                 ("n_blocks_2d", C.c_double), ("n_blocks_pt", C.c_double),
-                ("n_blocks_pl", C.c_double), ("n_residuals", C.c_double)]
+                ("n_blocks_pl", C.c_double), ("n_residuals", C.c_double), ("n_blocks_gpr", C.c_double)]
 
 
 class SynthCfg(C.Structure):

@@ -89,7 +89,7 @@ class Context:
     # -- LM path -------------------------------------------------------------
     def associate(self, x0):
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
-        nb = np.zeros(3, np.int64)
+        nb = np.zeros(4, np.int64)
         _check(self.lib, self.h, self.lib.stl_associate(self.h, x0.ctypes.data_as(_dp), nb.ctypes.data_as(_abi._i64p)))
         return nb
 

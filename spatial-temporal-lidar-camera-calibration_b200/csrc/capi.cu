@@ -133,6 +133,8 @@ void set_dev_params(stl_ctx *c) {
     d.k = p.norm_max_pts;
     d.min_pts = p.norm_min_pts;
     d.use_plane = p.use_plane;
+    d.use_gpr = p.use_gpr; d.pad_ = 0;
+    d.gpr_sigma = p.gpr_sigma; d.gpr_l = p.gpr_l; d.gpr_noise = p.gpr_sigma_noise;
 }
 
 struct StageTimer {
@@ -267,6 +269,7 @@ void stl_default_params(stl_params_t *p) {
     p->he_threshold = 0.094; p->valid_rate = 0.95;
     p->max_3d_dist = 1.0; p->robust_kernel_delta = 2.98; p->robust_kernel_3ddelta = 1.0;
     p->num_min_corr = 30; p->norm_max_pts = 30; p->norm_min_pts = 5; p->use_plane = 1;
+    p->use_gpr = 0; p->gpr_sigma = 10.0; p->gpr_l = 10.0; p->gpr_sigma_noise = 1e-10;
 }
 
 stl_status_t stl_create(const stl_params_t *params, int32_t device, stl_ctx_t **out) {
@@ -623,7 +626,7 @@ stl_status_t stl_knn3d(stl_ctx_t *ctx, int32_t kf, const double *q, int32_t nq, 
 
 // ---- LM path -------------------------------------------------------------------
 
-stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[3]) {
+stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[4]) {
     if (!ctx || !x0) return STL_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!ctx->has_pack) return fail(ctx, STL_ERR_STATE, "stl_upload_pack has not been called");
@@ -643,7 +646,7 @@ stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[3]
     { StageTimer t(ctx, 5, st); e = lm_associate(ctx->pk, ctx->wk, ctx->dpr, ctx->lm, st); }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "associate: %s", cudaGetErrorString(e));
     ctx->launches += 5 + (ctx->lm.n3d > 0 ? 1 : 0);  // K1, four association kernels, k_count_types (cub select kernels not counted)
-    if (n_blocks) { n_blocks[0] = ctx->lm.n_blocks[0]; n_blocks[1] = ctx->lm.n_blocks[1]; n_blocks[2] = ctx->lm.n_blocks[2]; }
+    if (n_blocks) for (int i = 0; i < 4; ++i) n_blocks[i] = ctx->lm.n_blocks[i];
     ctx->dbg_b = -1;
     ctx->last_x.clear();
     return STL_OK;
@@ -654,7 +657,7 @@ static stl_status_t lin_enqueue(stl_ctx *ctx, const double *x, int B, double *d_
     cudaError_t e;
     { StageTimer t(ctx, STL_STAGE_LINEARIZE, st); e = lm_linearize(ctx->pk, ctx->dpr, ctx->lm, x, B, d_out, st); }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "linearize: %s", cudaGetErrorString(e));
-    ctx->launches += 2;  // k_linearize, k_lin_finish
+    ctx->launches += 2 + (ctx->lm.nG > 0 ? 1 : 0);  // k_linearize, (k_linearize_gpr,) k_lin_finish
     return STL_OK;
 }
 

@@ -68,6 +68,8 @@ struct DevParams {
     double max_3d_dist2, delta2d, delta3d;
     double w0, w1;
     int num_min_corr, k, min_pts, use_plane;
+    int use_gpr, pad_;
+    double gpr_sigma, gpr_l, gpr_noise;
 };
 
 // ---- exact fp64 (no FMA contraction; IEEE div/sqrt) ----------------------------

@@ -27,7 +27,8 @@ namespace {
 
 constexpr int kWarps = 8;
 constexpr int kAssocSub = 8;
-constexpr int kLinVals = 40;  // cost, g[7], H upper 28, n2d, npt, npl, nres
+constexpr int kLinVals = 41;  // cost, g[7], H upper 28, n2d, npt, npl, nres, ngpr
+constexpr int kGprWarps = 3;
 constexpr int kLinThreads = 128;
 
 // ------------------------------------------------------------------ K4a (four small kernels)
@@ -108,6 +109,13 @@ k_lm_plane_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
             double *g = lm.geo2d + cs * 6;
             g[0] = cx; g[1] = cy; g[2] = cz; g[3] = po.n.x; g[4] = po.n.y; g[5] = po.n.z;
             lm.flag2d[cs] = 1;
+        } else if (pr.use_gpr) {
+            // non-planar neighbourhood: IBA_GPRFactor over the neighbour points (iba_local.cpp:272-280);
+            // the list is copied because the evaluation workspace is reused by later calls
+            for (int t = 0; t < kMaxK; ++t) lm.gpr_nb[slot * kMaxK + t] = wk.nb[slot * kMaxK + t];
+            lm.gpr_m[slot] = m;
+            lm.slot_mp[cs] = (int)slot;
+            lm.flagG[cs] = 1;
         }
         lm.stage[slot] = 1;
     }
@@ -234,7 +242,8 @@ __device__ __forceinline__ void mv3(const D7 *M, const D7 *p, D7 *o) {
 
 // grid (chunks, B)
 __global__ void __launch_bounds__(kLinThreads)
-k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand *__restrict__ cands, double *__restrict__ partial) {
+k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand *__restrict__ cands, double *__restrict__ partial,
+            int partial_stride) {
     __shared__ LmCand c;
     {
         const double *src = reinterpret_cast<const double *>(cands + blockIdx.y);
@@ -348,7 +357,186 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
     if (threadIdx.x < kLinVals) {
         double x = 0.0;
         for (int w = 0; w < kLinThreads / 32; ++w) x += red[w][threadIdx.x];
-        partial[((long long)blockIdx.y * gridDim.x + blockIdx.x) * kLinVals + threadIdx.x] = x;
+        partial[((long long)blockIdx.y * partial_stride + blockIdx.x) * kLinVals + threadIdx.x] = x;
+    }
+}
+
+
+// ------------------------------------------------------------------ K4b': IBA_GPRFactor blocks
+// IBACalib2.hpp:472-507 + TGPR::fit_predict (GPR.hpp:449-491): the neighbours are projected with the
+// CURRENT extrinsic, K = sigma^2 exp(-D/2l^2) + sigma_n I, alpha = K^-1 y (LLT), z = k*^T alpha, the
+// keypoint is back-projected at depth z and re-projected into the covisible keyframes.
+// One warp per block, lane j <-> neighbour j, matrices in shared memory.  The reference
+// differentiates through the Cholesky with Jets; here the same derivative is formed by the adjoint
+// identity  dz = dk*^T alpha + beta^T (dy - dK alpha),  beta = K^-1 k*  (no dual-number matrices).
+struct GprSmem {
+    double K[32][33];
+    double xu[32], xv[32], y[32], alpha[32], beta[32], ks[32];
+    double dxu[7][32], dxv[7][32], dy[7][32];
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// solves L L^T x = rhs in place (L = lower triangle of S.K incl. diagonal); lane i owns x[i]
+__device__ __forceinline__ double chol_solve(const GprSmem &S, double rhs, int n, int lane) {
+    double v = rhs;
+    for (int i = 0; i < n; ++i) {  // forward: L w = rhs
+        const double wi = __shfl_sync(0xffffffffu, v, i) / S.K[i][i];
+        if (lane == i) v = wi;
+        else if (lane > i && lane < n) v -= S.K[lane][i] * wi;
+    }
+    for (int i = n - 1; i >= 0; --i) {  // backward: L^T x = w
+        const double xi = __shfl_sync(0xffffffffu, v, i) / S.K[i][i];
+        if (lane == i) v = xi;
+        else if (lane < i) v -= S.K[i][lane] * xi;
+    }
+    return v;
+}
+
+// grid (chunks, B)
+__global__ void __launch_bounds__(kGprWarps * 32)
+k_linearize_gpr(const DevPack pk, const DevParams pr, const LmState lm, const LmCand *__restrict__ cands, double *__restrict__ partial,
+                int partial_stride, int partial_off) {
+    __shared__ GprSmem SM[kGprWarps];
+    __shared__ LmCand c;
+    {
+        const double *src = reinterpret_cast<const double *>(cands + blockIdx.y);
+        double *dst = reinterpret_cast<double *>(&c);
+        for (int i = threadIdx.x; i < (int)(sizeof(LmCand) / 8); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    GprSmem &S = SM[warp];
+    Acc A;
+#pragma unroll
+    for (int i = 0; i < kLinVals; ++i) A.v[i] = 0.0;
+    const int C = pk.n_covis;
+    const double sigma2 = pr.gpr_sigma * pr.gpr_sigma, coef = -0.5 / (pr.gpr_l * pr.gpr_l);
+    for (int it = blockIdx.x * kGprWarps + warp; it < lm.nG; it += gridDim.x * kGprWarps) {
+        const int cs = lm.idxG[it];
+        const int f = lm.slot_kf[cs];
+        const uint32_t kp = lm.slot_kp[cs];
+        const long long ms = lm.slot_mp[cs];
+        const int n = lm.gpr_m[ms];
+        const DevKf &K = pk.kf[f];
+        const double fx = K.fx, fy = K.fy, cx = K.cx, cy = K.cy;
+        const float2 kxy = pk.kp_xy[K.kp_off + kp];
+        const double u0 = kxy.x, v0 = kxy.y;
+        __syncwarp();
+        // 1. neighbour j -> camera frame with the candidate (duals), pixel coordinates and depth
+        if (lane < n) {
+            const uint32_t p = lm.gpr_nb[ms * kMaxK + lane];
+            const double px = (double)pk.px[K.pt_off + p], py = (double)pk.py[K.pt_off + p], pz = (double)pk.pz[K.pt_off + p];
+            D7 tf[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) tf[i] = ((c.R[i * 3] * px + c.R[i * 3 + 1] * py) + c.R[i * 3 + 2] * pz) + c.t[i];
+            const D7 xu = (tf[0] * fx) / tf[2] + cx, xv = (tf[1] * fy) / tf[2] + cy;
+            S.xu[lane] = xu.a; S.xv[lane] = xv.a; S.y[lane] = tf[2].a;
+#pragma unroll
+            for (int q = 0; q < 7; ++q) { S.dxu[q][lane] = xu.v[q]; S.dxv[q][lane] = xv.v[q]; S.dy[q][lane] = tf[2].v[q]; }
+        }
+        __syncwarp();
+        // 2. kernel matrix (both triangles; the strict upper one survives the factorisation)
+        const double mxu = lane < n ? S.xu[lane] : 0.0, mxv = lane < n ? S.xv[lane] : 0.0;
+        for (int r = 0; r < n; ++r) {
+            if (lane < n) {
+                const double dx = S.xu[r] - mxu, dy = S.xv[r] - mxv;
+                S.K[r][lane] = (r == lane) ? sigma2 + pr.gpr_noise : sigma2 * exp(coef * (dx * dx + dy * dy));
+            }
+        }
+        __syncwarp();
+        // 3. left-looking Cholesky, lower triangle in place (Eigen::LLT unblocked order)
+        for (int k = 0; k < n; ++k) {
+            double v = 0.0;
+            if (lane >= k && lane < n) {
+                v = S.K[lane][k];
+                for (int j = 0; j < k; ++j) v -= S.K[lane][j] * S.K[k][j];
+            }
+            const double d = sqrt(__shfl_sync(0xffffffffu, v, k));
+            if (lane == k) S.K[k][k] = d;
+            else if (lane > k && lane < n) S.K[lane][k] = v / d;
+            __syncwarp();
+        }
+        // 4. alpha = K^-1 y, k*, beta = K^-1 k*, z
+        const double alpha = chol_solve(S, lane < n ? S.y[lane] : 0.0, n, lane);
+        double ks = 0.0;
+        if (lane < n) { const double dx = mxu - u0, dy = mxv - v0; ks = sigma2 * exp(coef * (dx * dx + dy * dy)); }
+        const double beta = chol_solve(S, ks, n, lane);
+        if (lane < n) { S.alpha[lane] = alpha; S.beta[lane] = beta; S.ks[lane] = ks; }
+        __syncwarp();
+        D7 z;
+        z.a = warp_sum(lane < n ? ks * alpha : 0.0);
+        // 5. derivatives by the adjoint identity
+        double w[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) w[q] = 0.0;
+        if (lane < n) {
+            double acc[7];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) acc[q] = 0.0;
+            for (int k = 0; k < n; ++k) {
+                if (k == lane) continue;
+                const double kv = lane < k ? S.K[lane][k] : S.K[k][lane];  // original kernel value (strict upper triangle)
+                const double ex = mxu - S.xu[k], ey = mxv - S.xv[k];
+                const double g = kv * coef * 2.0 * S.alpha[k];
+#pragma unroll
+                for (int q = 0; q < 7; ++q) acc[q] += g * (ex * (S.dxu[q][lane] - S.dxu[q][k]) + ey * (S.dxv[q][lane] - S.dxv[q][k]));
+            }
+            const double gs = ks * coef * 2.0 * alpha, ex0 = mxu - u0, ey0 = mxv - v0;
+#pragma unroll
+            for (int q = 0; q < 7; ++q)
+                w[q] = gs * (ex0 * S.dxu[q][lane] + ey0 * S.dxv[q][lane]) + beta * (S.dy[q][lane] - acc[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 7; ++q) z.v[q] = warp_sum(w[q]);
+        // 6. back-projection at depth z, covisible re-projection, Huber, normal equations (lane 0)
+        if (lane == 0) {
+            const D7 P0[3] = {z * ((u0 - cx) / fx), z * ((v0 - cy) / fy), z};
+            double sq = 0.0;
+            int nres = 0;
+            for (int s = 0; s < C; ++s) {
+                if (!pk.covis_valid[f * C + s]) continue;
+                const float2 uv = pk.covis_uv[(K.kp_off + kp) * C + s];
+                if (isnan(uv.x)) continue;
+                const float *rp = pk.relpose + ((long long)f * C + s) * 12;
+                double P1[3];
+                for (int i = 0; i < 3; ++i)
+                    P1[i] = (((double)rp[i * 4] * P0[0].a + (double)rp[i * 4 + 1] * P0[1].a) + (double)rp[i * 4 + 2] * P0[2].a) + (double)rp[i * 4 + 3] * c.s.a;
+                const double eu = (fx * P1[0] / P1[2] + cx) - (double)uv.x, ev = (fy * P1[1] / P1[2] + cy) - (double)uv.y;
+                sq += eu * eu;
+                sq += ev * ev;
+                nres += 2;
+            }
+            double rho0, sr;
+            huber(sq, pr.delta2d, rho0, sr);
+            A.v[0] += 0.5 * rho0;
+            A.v[40] += 1.0;
+            A.v[39] += (double)nres;
+            for (int s = 0; s < C; ++s) {
+                if (!pk.covis_valid[f * C + s]) continue;
+                const float2 uv = pk.covis_uv[(K.kp_off + kp) * C + s];
+                if (isnan(uv.x)) continue;
+                const float *rp = pk.relpose + ((long long)f * C + s) * 12;
+                D7 P1[3];
+                for (int i = 0; i < 3; ++i)
+                    P1[i] = ((P0[0] * (double)rp[i * 4] + P0[1] * (double)rp[i * 4 + 1]) + P0[2] * (double)rp[i * 4 + 2]) + c.s * (double)rp[i * 4 + 3];
+                accumulate(A, ((P1[0] * fx) / P1[2] + cx) - (double)uv.x, sr);
+                accumulate(A, ((P1[1] * fy) / P1[2] + cy) - (double)uv.y, sr);
+            }
+        }
+    }
+    // per-CTA partial: only lane 0 of every warp holds data
+    __shared__ double red[kGprWarps][kLinVals];
+    if (lane == 0)
+        for (int i = 0; i < kLinVals; ++i) red[warp][i] = A.v[i];
+    __syncthreads();
+    if (threadIdx.x < kLinVals) {
+        double x = 0.0;
+        for (int w2 = 0; w2 < kGprWarps; ++w2) x += red[w2][threadIdx.x];
+        partial[((long long)blockIdx.y * partial_stride + partial_off + blockIdx.x) * kLinVals + threadIdx.x] = x;
     }
 }
 
@@ -369,7 +557,7 @@ __global__ void k_lin_finish(const double *__restrict__ partial, int nchunks, do
         int h = 8;
         for (int a = 0; a < 7; ++a)
             for (int c = a; c < 7; ++c) { o[8 + a * 7 + c] = tot[h]; o[8 + c * 7 + a] = tot[h]; ++h; }
-        o[57] = tot[36]; o[58] = tot[37]; o[59] = tot[38]; o[60] = tot[39];
+        o[57] = tot[36]; o[58] = tot[37]; o[59] = tot[38]; o[60] = tot[39]; o[61] = tot[40];
     }
 }
 
@@ -379,6 +567,7 @@ template <class T> void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
 
 void lm_free(LmState &lm) {
     dfree(lm.slot_kf); dfree(lm.slot_kp); dfree(lm.flag2d); dfree(lm.type3d); dfree(lm.flag3d); dfree(lm.geo2d); dfree(lm.geo3d);
+    dfree(lm.flagG); dfree(lm.idxG); dfree(lm.slot_mp); dfree(lm.gpr_nb); dfree(lm.gpr_m);
     dfree(lm.stage); dfree(lm.plane_a); dfree(lm.nnb_pos); dfree(lm.nbb); dfree(lm.nbb_m); dfree(lm.nbb_last);
     dfree(lm.idx2d); dfree(lm.idx3d); dfree(lm.d_counts); dfree(lm.d_tmp); dfree(lm.partial); dfree(lm.d_cand);
     if (lm.h_cand) cudaFreeHost(lm.h_cand);
@@ -401,6 +590,8 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
         const long long nm = pk.n_mp_total > 0 ? pk.n_mp_total : 1;
         TRY(cudaMalloc(&lm.stage, nm)); TRY(cudaMalloc(&lm.plane_a, 32 * nm)); TRY(cudaMalloc(&lm.nnb_pos, 4 * nm));
         TRY(cudaMalloc(&lm.nbb, 4 * nm * kMaxK)); TRY(cudaMalloc(&lm.nbb_m, 4 * nm)); TRY(cudaMalloc(&lm.nbb_last, 8 * nm));
+        TRY(cudaMalloc(&lm.flagG, ns)); TRY(cudaMalloc(&lm.idxG, 4 * ns)); TRY(cudaMalloc(&lm.slot_mp, 4 * ns));
+        if (pr.use_gpr) { TRY(cudaMalloc(&lm.gpr_nb, 4 * nm * kMaxK)); TRY(cudaMalloc(&lm.gpr_m, 4 * nm)); }
         size_t tb = 0;
         cub::CountingInputIterator<int> it(0);
         TRY(cub::DeviceSelect::Flagged(nullptr, tb, it, lm.flag2d, lm.idx2d, lm.d_counts, (int)ns, st));
@@ -411,6 +602,7 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
     TRY(cudaMemsetAsync(lm.flag2d, 0, ns, st));
     TRY(cudaMemsetAsync(lm.type3d, 0, ns, st));
     TRY(cudaMemsetAsync(lm.flag3d, 0, ns, st));
+    TRY(cudaMemsetAsync(lm.flagG, 0, ns, st));
     TRY(cudaMemsetAsync(lm.d_counts, 0, 16, st));
     k_lm_knn_a<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
     k_lm_plane_a<<<(unsigned)pk.n_kf, 128, 0, st>>>(pk, wk, pr, lm);
@@ -422,10 +614,14 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
     TRY(cub::DeviceSelect::Flagged(lm.d_tmp, tb, it, lm.flag2d, lm.idx2d, lm.d_counts, (int)ns, st));
     tb = lm.tmp_bytes;
     TRY(cub::DeviceSelect::Flagged(lm.d_tmp, tb, it, lm.flag3d, lm.idx3d, lm.d_counts + 1, (int)ns, st));
-    int h[2] = {0, 0};
-    TRY(cudaMemcpyAsync(h, lm.d_counts, 8, cudaMemcpyDeviceToHost, st));
+    if (pr.use_gpr) {
+        tb = lm.tmp_bytes;
+        TRY(cub::DeviceSelect::Flagged(lm.d_tmp, tb, it, lm.flagG, lm.idxG, lm.d_counts + 3, (int)ns, st));
+    }
+    int h[4] = {0, 0, 0, 0};
+    TRY(cudaMemcpyAsync(h, lm.d_counts, 16, cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
-    lm.n2d = h[0]; lm.n3d = h[1];
+    lm.n2d = h[0]; lm.n3d = h[1]; lm.nG = pr.use_gpr ? h[3] : 0;
     int npt = 0;
     if (lm.n3d > 0) {
         k_count_types<<<64, 256, 0, st>>>(lm.type3d, lm.idx3d, lm.n3d, lm.d_counts + 2);
@@ -433,7 +629,7 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
         TRY(cudaMemcpyAsync(&npt, lm.d_counts + 2, 4, cudaMemcpyDeviceToHost, st));
         TRY(cudaStreamSynchronize(st));
     }
-    lm.n_blocks[0] = lm.n2d; lm.n_blocks[1] = npt; lm.n_blocks[2] = lm.n3d - npt;
+    lm.n_blocks[0] = lm.n2d; lm.n_blocks[1] = npt; lm.n_blocks[2] = lm.n3d - npt; lm.n_blocks[3] = lm.nG;
     lm.ready = true;
     return cudaSuccess;
 }
@@ -458,15 +654,22 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
     int chunks = (work + kLinThreads * 2 - 1) / (kLinThreads * 2);
     if (chunks < 1) chunks = 1;
     if (chunks > 148 * 8) chunks = 148 * 8;
-    const long long need = (long long)B * chunks * kLinVals;
+    int gchunks = lm.nG > 0 ? (lm.nG + kGprWarps * 4 - 1) / (kGprWarps * 4) : 0;
+    if (gchunks > 148 * 8) gchunks = 148 * 8;
+    const int stride = chunks + gchunks;
+    const long long need = (long long)B * stride * kLinVals;
     if (need > lm.partial_cap) {
         dfree(lm.partial);
         TRY(cudaMalloc(&lm.partial, 8 * need));
         lm.partial_cap = need;
     }
-    k_linearize<<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial);
+    k_linearize<<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride);
     TRY(cudaGetLastError());
-    k_lin_finish<<<B, 64, 0, st>>>(lm.partial, chunks, d_out);
+    if (gchunks > 0) {
+        k_linearize_gpr<<<dim3(gchunks, B), kGprWarps * 32, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, chunks);
+        TRY(cudaGetLastError());
+    }
+    k_lin_finish<<<B, 64, 0, st>>>(lm.partial, stride, d_out);
     TRY(cudaGetLastError());
 #undef TRY
     return cudaSuccess;

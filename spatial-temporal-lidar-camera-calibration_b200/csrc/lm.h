@@ -10,7 +10,7 @@ namespace stl {
 // (Point2Point_Factor / Point2Plane_Factor).
 struct LmState {
     bool ready = false;
-    long long n_blocks[3] = {0, 0, 0};  // plane (3-D/2-D), point-to-point, point-to-plane
+    long long n_blocks[4] = {0, 0, 0, 0};  // plane (3-D/2-D), point-to-point, point-to-plane, GPR (3-D/2-D)
     long long n_slots = 0;
     int *slot_kf = nullptr;       // [n_slots]
     uint32_t *slot_kp = nullptr;  // [n_slots]
@@ -27,6 +27,12 @@ struct LmState {
     int *nbb_m = nullptr;         // [n_mp] (-2 = same point as the associated one)
     double *nbb_last = nullptr;
     int *idx2d = nullptr, *idx3d = nullptr;  // [n_slots] dense slot lists
+    // IBA_GPRFactor blocks (use_gpr): flag + dense list by correspondence slot, neighbour list by map-point slot
+    uint8_t *flagG = nullptr;
+    int *idxG = nullptr, *slot_mp = nullptr;
+    uint32_t *gpr_nb = nullptr;   // [n_mp][32]
+    int *gpr_m = nullptr;         // [n_mp]
+    int nG = 0;
     int *d_counts = nullptr;      // [2]
     int n2d = 0, n3d = 0;
     void *d_tmp = nullptr;        // cub scratch

@@ -157,4 +157,6 @@ def default_params() -> _abi.Params:
     p.norm_max_pts = 30
     p.norm_min_pts = 5
     p.use_plane = 1
+    p.use_gpr = 0
+    p.gpr_sigma, p.gpr_l, p.gpr_sigma_noise = 10.0, 10.0, 1e-10
     return p

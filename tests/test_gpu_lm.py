@@ -74,3 +74,24 @@ def test_lm_steps_reduce_the_cost_like_the_oracle(gpu_ctx, orc, small_candidates
         costs.append(cg)
     assert costs[-1] < costs[0]
     assert np.abs(xg[:3] - xo[:3]).max() < np.deg2rad(0.01) and np.abs(xg[3:6] - xo[3:6]).max() < 1e-3
+
+
+def test_gpr_factor_blocks(pkg, oracle_mod, small_pack, small_candidates):
+    """use_gpr: non-planar neighbourhoods get an IBA_GPRFactor (the branch the reference keeps commented
+    out, iba_local.cpp:272-280); GPU derivative by the adjoint identity vs the oracle's Jet-Cholesky."""
+    capi = importlib.import_module(PKG + ".capi")
+    p = pkg.default_params(); p.use_gpr = 1
+    pack = small_pack[0].shard(0, 3)
+    orc = oracle_mod.Oracle(pack, params=p, kind="best")
+    nb_o, _ = orc.associate(small_candidates[0])
+    want = orc.linearize(small_candidates[:3])
+    with capi.Context(params=p) as c:
+        c.upload(pack)
+        nb_g = c.associate(small_candidates[0])
+        got = c.linearize(small_candidates[:3])
+    assert np.array_equal(nb_g, nb_o) and nb_o[3] > 20
+    assert np.array_equal(got[:, 57:], want[:, 57:])
+    assert np.allclose(got[:, 0], want[:, 0], rtol=1e-8, atol=0)
+    sg = np.abs(want[:, 1:8]).max(axis=1, keepdims=True); sh = np.abs(want[:, 8:57]).max(axis=1, keepdims=True)
+    assert np.allclose(got[:, 1:8], want[:, 1:8], rtol=1e-6, atol=1e-8 * sg)
+    assert np.allclose(got[:, 8:57], want[:, 8:57], rtol=1e-6, atol=1e-8 * sh)

@@ -151,3 +151,25 @@ def test_cost_landscape_has_its_minimum_at_the_ground_truth(oracle_mod, small_pa
     s, _, _ = o.ba_error_sums(X)
     f = np.array([sum(o.finalize(r)[:2]) for r in s])
     assert f.argmin() == 0 and (f[1:] > 2 * f[0]).all()
+
+
+def test_gpr_factor_jacobian_and_depth(oracle_mod, pkg, small_pack, small_candidates):
+    """IBA_GPRFactor (IBACalib2.hpp:472-507, TGPR::fit_predict GPR.hpp:449-491): dual-number Jacobian
+    through the Cholesky solve vs central differences, and the GP depth of an on-surface keypoint."""
+    p = pkg.default_params(); p.use_gpr = 1
+    o = oracle_mod.Oracle(small_pack[0].shard(0, 2), params=p)
+    nb, _ = o.associate(small_candidates[0])
+    assert nb[3] > 10 and nb[0] > 100                     # GPR blocks only where the plane test failed
+    keys = o.block_keys()
+    x = small_candidates[1].copy()
+    for bi in np.flatnonzero(keys[:, 0] == 3)[:4]:
+        e, J = o.block_eval(int(bi), x)
+        Jn = np.zeros_like(J)
+        for a in range(7):
+            h = 1e-6 * max(1.0, abs(x[a]))
+            xp, xm = x.copy(), x.copy(); xp[a] += h; xm[a] -= h
+            ep, _ = o.block_eval(int(bi), xp, plain=True); em, _ = o.block_eval(int(bi), xm, plain=True)
+            Jn[:, a] = (ep - em) / (2 * h)
+        assert np.allclose(J, Jn, rtol=1e-4, atol=1e-5 * max(1.0, np.abs(J).max()))
+    L = o.linearize(x)[0]
+    assert L[61] == nb[3] and L[57] == nb[0]
