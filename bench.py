@@ -119,14 +119,16 @@ def oracle_sample_rate(pack, X, nthreads=0, min_seconds=8.0, want_lm=True):
     """Times the CPU oracle on `pack` (a keyframe sample): seconds per (candidate x sample) step."""
     from oracle import oracle as O
     kind = "ref" if O.have_ref() else "port"
+    if nthreads <= 0:
+        nthreads = os.cpu_count() or 1
     orc = O.Oracle(pack, kind=kind, nthreads=nthreads)
-    cores = orc.max_threads() if nthreads <= 0 else nthreads
+    cores = nthreads
     reps, t_tot, i = 0, 0.0, 0
-    orc.ba_error_sums(X[:1], mode=1, strict=True)  # warm-up
+    orc.ba_error_sums(X[:1], mode=1, strict=True, nthreads=nthreads)  # warm-up
     while t_tot < min_seconds and reps < 200:
         x = X[i % len(X)]
         t0 = time.perf_counter()
-        orc.ba_error_sums(x, mode=1, strict=True)          # BAError, OpenMP over keyframes (iba_func.cpp:203)
+        orc.ba_error_sums(x, mode=1, strict=True, nthreads=nthreads)  # BAError, OpenMP over keyframes (iba_func.cpp:203)
         if want_lm:
             orc.associate(x, strict=True)                   # BuildProblem (OpenMP over keyframes, iba_local.cpp:162)
             orc.linearize(x)                                # one evaluation of all residual blocks + Jacobians
@@ -146,11 +148,11 @@ def run_reference(args, rank, world):
     X = synth.candidates(x_gt, max(args.steps + args.warmup, 2), 0.2)
     from oracle import oracle as O
     kind = "ref" if O.have_ref() else "port"
-    orc = O.Oracle(pack, kind=kind)
-    cores = orc.max_threads()
+    cores = os.cpu_count() or 1
+    orc = O.Oracle(pack, kind=kind, nthreads=cores)
 
     def step(x):
-        orc.ba_error_sums(x, mode=1, strict=True)
+        orc.ba_error_sums(x, mode=1, strict=True, nthreads=cores)
         orc.associate(x, strict=True)
         orc.linearize(x)
     for i in range(args.warmup):
@@ -181,9 +183,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ncpu = os.cpu_count() or 8
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core (rank 0 runs alone)
+        os.environ["OMP_NUM_THREADS"] = str(ncpu)
         run_reference(args, rank, world)
         return
+    os.environ["OMP_NUM_THREADS"] = str(max(1, ncpu // max(world, 1)))  # host-side generator / pack preparation only
 
     import torch
     import torch.distributed as dist
@@ -193,8 +199,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    ncpu = os.cpu_count() or 8
-    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, ncpu // max(world, 1))))
 
     synth = importlib.import_module(PKG + ".synth")
     capi = importlib.import_module(PKG + ".capi")
