@@ -110,7 +110,7 @@ struct SinkK {
         unsigned mask = __ballot_sync(kFull, pre);
         if (!mask) return;
         const uint32_t o = pre ? S.orig[g] : 0xffffffffu;
-        if (__popc(mask) >= (count == 0 ? 6 : 16)) {
+        if (__popc(mask) >= (count == 0 ? 4 : 8)) {
             bulk_merge(pre ? dd : (double)INFINITY, o, (uint32_t)g, lane);
             return;
         }
@@ -144,12 +144,43 @@ struct SinkK {
     // leaf across the warp, then bitonic-merge them with the sorted list — ~300 warp instructions
     // whatever the number of accepted points, against ~30 per serial insertion.
     __device__ __forceinline__ void bulk_merge(double cd, uint32_t ci, uint32_t cp, int lane) {
+        // (a) sort the 32 candidates on a packed 32-bit key: float32 bits of d2 (rounded down, so the
+        //     order is monotone in d2) with the five low bits replaced by the lane — one SHFL and one
+        //     MIN/MAX per compare-exchange instead of moving the (d2, index, position) triple.
+        unsigned key = cd < (double)INFINITY ? ((__float_as_uint(__double2float_rd(cd)) & ~31u) | (unsigned)lane) : (0xffffffe0u | (unsigned)lane);
 #pragma unroll 1
         for (int kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll 1
             for (int j = kk >> 1; j > 0; j >>= 1) {
-                const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
-                cx(cd, ci, cp, j, lower == up);
+                const unsigned o = __shfl_xor_sync(kFull, key, j);
+                const bool keep_min = ((lane & kk) == 0) == ((lane & j) == 0);
+                key = keep_min ? min(key, o) : max(key, o);
+            }
+        }
+        {   // (b) fetch the payload of the element that belongs at this lane
+            const int src = (int)(key & 31u);
+            const double sd = __shfl_sync(kFull, cd, src);
+            const uint32_t si = __shfl_sync(kFull, ci, src), sp = __shfl_sync(kFull, cp, src);
+            cd = sd; ci = si; cp = sp;
+        }
+        // (c) elements whose truncated keys collide may still be out of exact (d2, index) order:
+        //     odd-even transposition on the exact key until stable (almost never entered)
+        const unsigned next_key = __shfl_down_sync(kFull, key, 1);  // every lane takes part in the shuffle
+        if (__ballot_sync(kFull, lane < 31 && (key >> 5) == (next_key >> 5) && cd < (double)INFINITY)) {
+            for (;;) {
+                bool moved = false;
+#pragma unroll 1
+                for (int parity = 0; parity < 2; ++parity) {
+                    const bool lower = (lane & 1) == parity;
+                    const int partner = lower ? lane + 1 : lane - 1;
+                    const bool ok = partner >= 0 && partner < 32;
+                    const double od = __shfl_sync(kFull, cd, ok ? partner : lane);
+                    const uint32_t oi = __shfl_sync(kFull, ci, ok ? partner : lane), op = __shfl_sync(kFull, cp, ok ? partner : lane);
+                    const bool other_less = od < cd || (od == cd && oi < ci);
+                    const bool other_more = od > cd || (od == cd && oi > ci);
+                    if (ok && (lower ? other_less : other_more)) { cd = od; ci = oi; cp = op; moved = true; }
+                }
+                if (!__any_sync(kFull, moved)) break;
             }
         }
         if (count == 0) {  // first leaf: the sorted candidates ARE the list
@@ -171,7 +202,10 @@ struct SinkK {
 
 // ---- traversal -------------------------------------------------------------------
 template <class Sink>
-__device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy, double qz, Sink &sink, int lane) {
+__device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy, double qz, Sink &sink, int lane, int first_leaf = -1) {
+    // a leaf known to hold a very close point (the query itself for the k-NN searches) is visited
+    // first, so that every box test already sees a tight bound; it is skipped in the descent
+    if (first_leaf >= 0) sink.visit(S, first_leaf, qx, qy, qz, lane);
     const float4 *lo2 = S.lo + S.n0 + S.n1, *hi2 = S.hi + S.n0 + S.n1;
     const float4 *lo1 = S.lo + S.n0, *hi1 = S.hi + S.n0;
     const QueryF qf = make_queryf(qx, qy, qz);
@@ -197,7 +231,7 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
             const int n0i = (s2 * 32 + s1) * 32 + lane;
             const float lb0 = box_lbf(qf, S.lo[n0i], S.hi[n0i]);
             const unsigned key0 = __float_as_uint(lb0);
-            unsigned done0 = 0;
+            unsigned done0 = ((s2 * 32 + s1) == (first_leaf >> 5) && first_leaf >= 0) ? (1u << (first_leaf & 31)) : 0u;
             for (;;) {
                         const bool c0 = !((done0 >> lane) & 1u) && sink.may_contain(lb0);
                 const unsigned m0 = __reduce_min_sync(kFull, c0 ? key0 : 0xffffffffu);

@@ -63,7 +63,7 @@ k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
         if (pr.use_plane) {
             const double nx = (double)S.px[nn.pos], ny = (double)S.py[nn.pos], nz = (double)S.pz[nn.pos];
             SinkK kn(pr.k, pr.radius2);
-            traverse(S, nx, ny, nz, kn, lane);
+            traverse(S, nx, ny, nz, kn, lane, (int)(nn.pos >> 5));
             wk.nb[(qbase + qi) * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
             const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
             if (lane == 0) { wk.nb_m[qbase + qi] = kn.count; wk.nb_last[qbase + qi] = last; }

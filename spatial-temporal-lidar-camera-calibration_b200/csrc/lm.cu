@@ -75,7 +75,7 @@ k_lm_knn_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
             continue;
         }
         SinkK kn(pr.k, pr.radius2);
-        traverse(S, (double)S.px[sp], (double)S.py[sp], (double)S.pz[sp], kn, lane);
+        traverse(S, (double)S.px[sp], (double)S.py[sp], (double)S.pz[sp], kn, lane, (int)(sp >> 5));
         wk.nb[slot * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
         const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
         if (lane == 0) { wk.nb_m[slot] = kn.count; wk.nb_last[slot] = last; }
@@ -152,7 +152,7 @@ k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
             continue;
         }
         SinkK kn(pr.k, pr.radius2);
-        traverse(S, (double)S.px[nn.pos], (double)S.py[nn.pos], (double)S.pz[nn.pos], kn, lane);
+        traverse(S, (double)S.px[nn.pos], (double)S.py[nn.pos], (double)S.pz[nn.pos], kn, lane, (int)(nn.pos >> 5));
         lm.nbb[slot * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
         const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
         if (lane == 0) { lm.nbb_m[slot] = kn.count; lm.nbb_last[slot] = last; }

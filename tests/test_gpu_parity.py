@@ -212,3 +212,56 @@ def test_large_shape_properties(pkg, synth):
             c.upload(pack.shard(b, e))
             acc += c.eval_sums(X)
     assert np.array_equal(acc[:, COUNTERS], full[:, COUNTERS]) and np.allclose(acc[:, :3], full[:, :3], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("variant", ["k20", "tight", "covis1"])
+def test_parameter_variants(oracle_mod, pkg, small_pack, small_candidates, variant):
+    """BASELINE config 3 (k = 20 plane variant) and other IBAGlobalParams settings: same parity bar."""
+    capi = importlib.import_module(PKG + ".capi")
+    p = pkg.default_params()
+    pack = small_pack[0].shard(1, 4)
+    if variant == "k20":
+        p.norm_max_pts = 20
+    elif variant == "tight":
+        p.max_pixel_dist = 0.8; p.norm_radius = 0.35; p.norm_min_pts = 8; p.norm_reg_threshold = 0.01
+        p.corr_3d_2d_threshold = 5.0; p.corr_3d_3d_threshold = 0.3; p.min_diff_dist = 0.1
+    else:
+        pack.covis_valid = pack.covis_valid.copy(); pack.covis_valid[:, 1:] = 0   # num_best_covis = 1
+    orc = oracle_mod.Oracle(pack, params=p, kind="best")
+    want, ties, _ = orc.ba_error_sums(small_candidates[:3], mode=0)
+    assert ties.sum() == 0
+    with capi.Context(params=p) as c:
+        c.upload(pack)
+        got = c.eval_sums(small_candidates[:3])
+        _check_sums(got, want)
+        d = orc.frame_debug(small_candidates[1], 1)
+        c.eval_sums(small_candidates[:3])
+        a = c.debug_align(1, 1)
+        assert np.array_equal(a["nn"], d["align_nn"]) and np.array_equal(a["m"], d["align_m"])
+        assert all(np.array_equal(a["knn"][i][: a["m"][i]], d["align_knn"][i][: d["align_m"][i]]) for i in range(len(a["m"])))
+        nb_o, _ = orc.associate(small_candidates[0])
+        nb_g = c.associate(small_candidates[0])
+        assert np.array_equal(nb_g, nb_o)
+        assert np.allclose(c.linearize(small_candidates[1])[:, 0], orc.linearize(small_candidates[1])[:, 0], rtol=1e-9)
+
+
+def test_config5_shape_128_beam_scans(oracle_mod, pkg, synth):
+    """BASELINE config 5 shape: 128-beam ~245k-point scans (8192 leaves, 256 level-1 cells) with the GPR
+    factor enabled; two keyframes so that the oracle finishes in seconds."""
+    capi = importlib.import_module(PKG + ".capi")
+    pack, x_gt, _ = synth.generate(n_kf=2, beams=128, az_steps=2048, elev_top_deg=15.0, elev_bottom_deg=-25.0, seed=55)
+    assert np.diff(pack.scan_offset).min() > 200_000
+    X = synth.candidates(x_gt, 2, 0.3)
+    p = pkg.default_params(); p.use_gpr = 1
+    orc = oracle_mod.Oracle(pack, params=p, kind="best")
+    want, ties, _ = orc.ba_error_sums(X, mode=0)
+    assert ties.sum() == 0
+    with capi.Context(params=p) as c:
+        c.upload(pack)
+        _check_sums(c.eval_sums(X), want)
+        d = orc.frame_debug(X[0], 0)
+        kp, pt = c.debug_corrset(0, 0)
+        assert np.array_equal(kp, d["corr_kp"]) and np.array_equal(pt, d["corr_pt"])
+        nb_o, _ = orc.associate(X[0])
+        assert np.array_equal(c.associate(X[0]), nb_o) and nb_o[3] > 0
+        assert np.allclose(c.linearize(X)[:, 0], orc.linearize(X)[:, 0], rtol=1e-6)
