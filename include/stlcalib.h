@@ -80,6 +80,13 @@ typedef struct stl_params {
     double gpr_sigma;             /* 10    init_sigma  (IBACalib2.hpp:128)           */
     double gpr_l;                 /* 10    init_l                                    */
     double gpr_sigma_noise;       /* 1e-10 sigma_noise                               */
+    /* Index option: precompute the local plane (k-NN, gates, PCA normal, regression error) of EVERY
+     * scan point in stl_upload_pack.  The plane fit of ComputeAlignmentDist / BuildProblem is a pure
+     * function of (scan, neighbour point, parameters) — it does not depend on the candidate — so it
+     * can live in the index like the reference's KD-trees do; evaluations then only look it up.
+     * Costs ~36 B per point and a longer upload; results are identical. */
+    int32_t plane_index;          /* 0                                               */
+    int32_t reserved_;
 } stl_params_t;
 
 /*

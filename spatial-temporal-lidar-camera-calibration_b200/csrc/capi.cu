@@ -100,6 +100,7 @@ template <class T> void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
 void free_pack(stl_ctx *c) {
     DevPack &p = c->pk;
     dfree(p.kf); dfree(p.px); dfree(p.py); dfree(p.pz); dfree(p.orig); dfree(p.node_lo); dfree(p.node_hi);
+    dfree(p.pl_rec); dfree(p.pl_m);
     dfree(p.bitmap); dfree(p.grid_start); dfree(p.grid_kp); dfree(p.kp_xy); dfree(p.kp_mp); dfree(p.Tcw);
     dfree(p.relpose); dfree(p.covis_valid); dfree(p.covis_uv); dfree(p.he_Tc); dfree(p.he_Tl);
     p = DevPack();
@@ -133,7 +134,7 @@ void set_dev_params(stl_ctx *c) {
     d.k = p.norm_max_pts;
     d.min_pts = p.norm_min_pts;
     d.use_plane = p.use_plane;
-    d.use_gpr = p.use_gpr; d.pad_ = 0;
+    d.use_gpr = p.use_gpr; d.plane_index = p.plane_index;
     d.gpr_sigma = p.gpr_sigma; d.gpr_l = p.gpr_l; d.gpr_noise = p.gpr_sigma_noise;
 }
 
@@ -270,6 +271,7 @@ void stl_default_params(stl_params_t *p) {
     p->max_3d_dist = 1.0; p->robust_kernel_delta = 2.98; p->robust_kernel_3ddelta = 1.0;
     p->num_min_corr = 30; p->norm_max_pts = 30; p->norm_min_pts = 5; p->use_plane = 1;
     p->use_gpr = 0; p->gpr_sigma = 10.0; p->gpr_l = 10.0; p->gpr_sigma_noise = 1e-10;
+    p->plane_index = 0; p->reserved_ = 0;
 }
 
 stl_status_t stl_create(const stl_params_t *params, int32_t device, stl_ctx_t **out) {
@@ -470,6 +472,19 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
         dfree(d_raw);
     }
     CK(cudaMemcpy(hk.data(), pk.kf, sizeof(DevKf) * F, cudaMemcpyDeviceToHost));  // pmax filled by the build
+    if (ctx->params.plane_index) {
+        CK(cudaMalloc(&pk.pl_rec, sizeof(PlaneRec) * npt));
+        CK(cudaMalloc(&pk.pl_m, 4 * npt));
+        for (int f0 = 0; f0 < F;) {  // bounded scratch: a few million points at a time
+            int f1 = f0 + 1;
+            long long pts = hk[f0].n_pad;
+            while (f1 < F && pts + hk[f1].n_pad <= (4ll << 20)) pts += hk[f1++].n_pad;
+            cudaError_t e = build_plane_index(pk, hk.data(), f0, f1 - f0, ctx->dpr, st);
+            if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "plane index: %s", cudaGetErrorString(e));
+            f0 = f1;
+        }
+        CK(cudaStreamSynchronize(st));
+    }
     cudaEventRecord(ev1, st);
     cudaEventSynchronize(ev1);
     float ms = 0;

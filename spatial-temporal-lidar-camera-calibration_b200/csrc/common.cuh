@@ -63,12 +63,17 @@ struct AlignRec {
     double s3d, v3d, c3d, vpl, vpt;
 };
 
+// precomputed local plane of one scan point (plane index, optional)
+struct PlaneRec {
+    double nx, ny, nz, reg;
+};
+
 struct DevParams {
     double max_pixel_dist2, thr2d, thr3d, radius2, reg_thr, min_diff2;
     double max_3d_dist2, delta2d, delta3d;
     double w0, w1;
     int num_min_corr, k, min_pts, use_plane;
-    int use_gpr, pad_;
+    int use_gpr, plane_index;
     double gpr_sigma, gpr_l, gpr_noise;
 };
 

@@ -16,6 +16,8 @@ struct DevPack {
     float *px = nullptr, *py = nullptr, *pz = nullptr;
     uint32_t *orig = nullptr;
     float4 *node_lo = nullptr, *node_hi = nullptr;
+    PlaneRec *pl_rec = nullptr;      // [n_pad_total] plane index (null unless params.plane_index)
+    int *pl_m = nullptr;             // [n_pad_total] neighbours kept; negative (-(m+1)) when the gates failed
     uint32_t *bitmap = nullptr;
     uint32_t *grid_start = nullptr;  // per keyframe gw*gh+1 entries
     uint32_t *grid_kp = nullptr;     // [n_kp_total] keypoint ids sorted by cell (local ids)
@@ -62,6 +64,9 @@ struct DevWork {
 // raw: [n][3] float32 device points of a chunk of keyframes; raw_off[nkf+1] host offsets.
 cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int nkf, int kf_begin, const DevKf *h_kf,
                              DevPack &pack, cudaStream_t st);
+
+// plane index (knn3d.cu): k-NN + plane of every point of keyframes [kf_begin, kf_begin + nkf)
+cudaError_t build_plane_index(const DevPack &pk, const DevKf *h_kf, int kf_begin, int nkf, const DevParams &pr, cudaStream_t st);
 
 // ---- K1 (assoc2d.cu) ------------------------------------------------------------
 size_t assoc2d_smem_bytes(int max_kp, int max_bm_words, int max_cells, int max_groups);

@@ -284,4 +284,17 @@ __device__ __forceinline__ PlaneOut plane_thread(const ScanView &S, const uint32
     return out;
 }
 
+
+// plane of scan point `pos` from the precomputed index (same PlaneOut as plane_thread)
+__device__ __forceinline__ PlaneOut plane_lookup(const DevPack &pk, const DevKf &K, uint32_t pos) {
+    const PlaneRec r = pk.pl_rec[K.pt_off + pos];
+    const int mm = pk.pl_m[K.pt_off + pos];
+    PlaneOut out;
+    out.gates_ok = mm >= 0;
+    out.m = mm >= 0 ? mm : -(mm + 1);
+    out.n = {r.nx, r.ny, r.nz};
+    out.reg = r.reg;
+    return out;
+}
+
 }  // namespace stl

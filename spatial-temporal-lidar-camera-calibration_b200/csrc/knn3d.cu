@@ -60,7 +60,7 @@ k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
         Sink1 nn;
         traverse(S, qx, qy, qz, nn, lane);
         if (lane == 0) wk.nn_pos[qbase + qi] = nn.pos;
-        if (pr.use_plane) {
+        if (pr.use_plane && !pr.plane_index) {  // with the plane index the neighbourhood of nn is already fitted
             const double nx = (double)S.px[nn.pos], ny = (double)S.py[nn.pos], nz = (double)S.pz[nn.pos];
             SinkK kn(pr.k, pr.radius2);
             traverse(S, nx, ny, nz, kn, lane, (int)(nn.pos >> 5));
@@ -94,8 +94,9 @@ k_plane_dist(const DevPack pk, const DevWork wk, const DevParams pr, const int B
             double dist = sqrt(dot3e(dx, dy, dz, dx, dy, dz));  // pt2pt (iba_global.cpp:122)
             int is_plane = 0, m = 0;
             if (pr.use_plane) {
-                m = wk.nb_m[qbase + qi];
-                const PlaneOut po = plane_thread(S, wk.nb + (qbase + qi) * kMaxK, m, wk.nb_last[qbase + qi], nx, ny, nz, pr);
+                const PlaneOut po = pr.plane_index ? plane_lookup(pk, K, np)
+                                                   : plane_thread(S, wk.nb + (qbase + qi) * kMaxK, wk.nb_m[qbase + qi], wk.nb_last[qbase + qi], nx, ny, nz, pr);
+                m = po.m;
                 if (po.gates_ok && !(po.reg > pr.reg_thr)) {  // iba_global.cpp:147
                     is_plane = 1;
                     dist = fabs(dot3e(dx, dy, dz, po.n.x, po.n.y, po.n.z));
@@ -113,7 +114,7 @@ k_plane_dist(const DevPack pk, const DevWork wk, const DevParams pr, const int B
                 wk.dbg_plane[o] = is_plane;
                 wk.dbg_dist[o] = dist;
                 for (int t = 0; t < kMaxK; ++t) {
-                    const uint32_t p = (pr.use_plane && t < m) ? wk.nb[(qbase + qi) * kMaxK + t] : 0xffffffffu;
+                    const uint32_t p = (pr.use_plane && !pr.plane_index && t < m) ? wk.nb[(qbase + qi) * kMaxK + t] : 0xffffffffu;
                     wk.dbg_knn[o * kMaxK + t] = p == 0xffffffffu ? 0xffffffffu : S.orig[p];
                 }
             }
@@ -155,7 +156,65 @@ k_knn3d(const DevPack pk, const int kf, const double *__restrict__ q, const int 
     if (lane == 0) out_cnt[qi] = kn.count;
 }
 
+// ---- plane index: local plane of every scan point, computed once per pack ---------------------
+// grid (blocks, nkf): one warp per point of the keyframe range; lists go to a scratch buffer
+__global__ void __launch_bounds__(kWarps * 32, 4)
+k_index_knn(const DevPack pk, const int kf_begin, const DevParams pr, const long long first_pt, uint32_t *__restrict__ nb,
+            int *__restrict__ nb_m, double *__restrict__ nb_last) {
+    const DevKf K = pk.kf[kf_begin + blockIdx.y];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const ScanView S = make_view(pk, K);
+    for (int p = blockIdx.x * kWarps + warp; p < K.n_pts; p += gridDim.x * kWarps) {
+        SinkK kn(pr.k, pr.radius2);
+        traverse(S, (double)S.px[p], (double)S.py[p], (double)S.pz[p], kn, lane, p >> 5);
+        const long long o = K.pt_off - first_pt + p;
+        nb[o * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
+        const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
+        if (lane == 0) { nb_m[o] = kn.count; nb_last[o] = last; }
+    }
+}
+
+__global__ void __launch_bounds__(kPlaneThreads)
+k_index_plane(const DevPack pk, const int kf_begin, const DevParams pr, const long long first_pt, const uint32_t *__restrict__ nb,
+              const int *__restrict__ nb_m, const double *__restrict__ nb_last) {
+    const DevKf K = pk.kf[kf_begin + blockIdx.y];
+    const ScanView S = make_view(pk, K);
+    for (int p = blockIdx.x * kPlaneThreads + threadIdx.x; p < K.n_pad; p += gridDim.x * kPlaneThreads) {
+        PlaneRec r = {0.0, 0.0, 0.0, 0.0};
+        int mm = -1;
+        if (p < K.n_pts) {
+            const long long o = K.pt_off - first_pt + p;
+            const PlaneOut po = plane_thread(S, nb + o * kMaxK, nb_m[o], nb_last[o], (double)S.px[p], (double)S.py[p], (double)S.pz[p], pr);
+            r.nx = po.n.x; r.ny = po.n.y; r.nz = po.n.z; r.reg = po.reg;
+            mm = po.gates_ok ? po.m : -(po.m + 1);
+        }
+        pk.pl_rec[K.pt_off + p] = r;
+        pk.pl_m[K.pt_off + p] = mm;
+    }
+}
+
 }  // namespace
+
+cudaError_t build_plane_index(const DevPack &pk, const DevKf *h_kf, int kf_begin, int nkf, const DevParams &pr, cudaStream_t st) {
+    const long long first = h_kf[kf_begin].pt_off;
+    const long long npts = h_kf[kf_begin + nkf - 1].pt_off + h_kf[kf_begin + nkf - 1].n_pad - first;
+    if (npts <= 0) return cudaSuccess;
+    int max_pts = 0;
+    for (int f = 0; f < nkf; ++f) max_pts = max_pts > h_kf[kf_begin + f].n_pad ? max_pts : h_kf[kf_begin + f].n_pad;
+    uint32_t *nb = nullptr; int *m = nullptr; double *last = nullptr;
+    cudaError_t e = cudaMalloc(&nb, 4 * (size_t)npts * kMaxK);
+    if (e == cudaSuccess) e = cudaMalloc(&m, 4 * (size_t)npts);
+    if (e == cudaSuccess) e = cudaMalloc(&last, 8 * (size_t)npts);
+    if (e == cudaSuccess) {
+        const int bx = (max_pts + kWarps * 16 - 1) / (kWarps * 16);  // ~16 points per warp
+        k_index_knn<<<dim3(bx, nkf), kWarps * 32, 0, st>>>(pk, kf_begin, pr, first, nb, m, last);
+        k_index_plane<<<dim3((max_pts + kPlaneThreads * 4 - 1) / (kPlaneThreads * 4), nkf), kPlaneThreads, 0, st>>>(pk, kf_begin, pr, first, nb, m, last);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    cudaFree(nb); cudaFree(m); cudaFree(last);
+    return e;
+}
 
 cudaError_t launch_align3d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, int debug, cudaStream_t st) {
     if (B <= 0 || pk.n_kf <= 0) return cudaSuccess;

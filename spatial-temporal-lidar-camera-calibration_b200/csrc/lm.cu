@@ -74,6 +74,10 @@ k_lm_knn_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
             if (lane == 0) wk.nb_m[slot] = -1;
             continue;
         }
+        if (pr.plane_index && !pr.use_gpr) {  // the plane of the scan point comes from the index
+            if (lane == 0) wk.nb_m[slot] = 0;
+            continue;
+        }
         SinkK kn(pr.k, pr.radius2);
         traverse(S, (double)S.px[sp], (double)S.py[sp], (double)S.pz[sp], kn, lane, (int)(sp >> 5));
         wk.nb[slot * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
@@ -98,7 +102,8 @@ k_lm_plane_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
         const uint32_t ci = wk.q_corr[K.kp_off + qi];
         const uint32_t kp = wk.corr_kp[K.kp_off + ci], sp = wk.corr_sp[K.kp_off + ci];
         const double cx = (double)S.px[sp], cy = (double)S.py[sp], cz = (double)S.pz[sp];
-        const PlaneOut po = plane_thread(S, wk.nb + slot * kMaxK, m, wk.nb_last[slot], cx, cy, cz, pr);
+        const PlaneOut po = (pr.plane_index && !pr.use_gpr) ? plane_lookup(pk, K, sp)
+                                                             : plane_thread(S, wk.nb + slot * kMaxK, m, wk.nb_last[slot], cx, cy, cz, pr);
         if (!po.gates_ok) continue;  // m < min_pts || d2[m-1] < min_diff^2 (pointcloud.h:754)
         const long long cs = K.kp_off + ci;  // block slot = correspondence slot
         lm.slot_kf[cs] = f;
@@ -113,7 +118,7 @@ k_lm_plane_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
             // non-planar neighbourhood: IBA_GPRFactor over the neighbour points (iba_local.cpp:272-280);
             // the list is copied because the evaluation workspace is reused by later calls
             for (int t = 0; t < kMaxK; ++t) lm.gpr_nb[slot * kMaxK + t] = wk.nb[slot * kMaxK + t];
-            lm.gpr_m[slot] = m;
+            lm.gpr_m[slot] = po.m;
             lm.slot_mp[cs] = (int)slot;
             lm.flagG[cs] = 1;
         }
@@ -151,6 +156,10 @@ k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
             if (lane == 0) lm.nbb_m[slot] = -2;
             continue;
         }
+        if (pr.plane_index) {  // looked up by k_lm_plane_b
+            if (lane == 0) lm.nbb_m[slot] = -3;
+            continue;
+        }
         SinkK kn(pr.k, pr.radius2);
         traverse(S, (double)S.px[nn.pos], (double)S.py[nn.pos], (double)S.pz[nn.pos], kn, lane, (int)(nn.pos >> 5));
         lm.nbb[slot * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
@@ -184,7 +193,7 @@ k_lm_plane_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
             gates_ok = true; n3[0] = pa[0]; n3[1] = pa[1]; n3[2] = pa[2];
             state = pa[3] < pr.reg_thr;
         } else {
-            const PlaneOut p2 = plane_thread(S, lm.nbb + slot * kMaxK, m, lm.nbb_last[slot], nx, ny, nz, pr);
+            const PlaneOut p2 = m == -3 ? plane_lookup(pk, K, np) : plane_thread(S, lm.nbb + slot * kMaxK, m, lm.nbb_last[slot], nx, ny, nz, pr);
             gates_ok = p2.gates_ok; n3[0] = p2.n.x; n3[1] = p2.n.y; n3[2] = p2.n.z;
             state = p2.gates_ok && p2.reg < pr.reg_thr;
         }

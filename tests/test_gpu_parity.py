@@ -265,3 +265,27 @@ def test_config5_shape_128_beam_scans(oracle_mod, pkg, synth):
         nb_o, _ = orc.associate(X[0])
         assert np.array_equal(c.associate(X[0]), nb_o) and nb_o[3] > 0
         assert np.allclose(c.linearize(X)[:, 0], orc.linearize(X)[:, 0], rtol=1e-6)
+
+
+def test_plane_index_option_gives_identical_results(oracle_mod, pkg, small_pack, small_candidates):
+    """params.plane_index: the local plane of every scan point is fitted once at upload (it does not
+    depend on the candidate) and only looked up afterwards — every number must stay the same."""
+    capi = importlib.import_module(PKG + ".capi")
+    p = pkg.default_params(); p.plane_index = 1
+    pack = small_pack[0].shard(0, 3)
+    orc = oracle_mod.Oracle(pack, kind="best")
+    want, _, _ = orc.ba_error_sums(small_candidates, mode=0)
+    with capi.Context(params=p) as c:
+        c.upload(pack)
+        got = c.eval_sums(small_candidates)
+        _check_sums(got, want)
+        with capi.Context() as plain:      # and bit-identical to the on-the-fly path
+            plain.upload(pack)
+            assert np.array_equal(plain.eval_sums(small_candidates), got)
+            nb0 = plain.associate(small_candidates[1]); L0 = plain.linearize(small_candidates[:2])
+        d = orc.frame_debug(small_candidates[2], 1)
+        a = c.debug_align(2, 1)
+        assert np.array_equal(a["nn"], d["align_nn"]) and np.array_equal(a["m"], d["align_m"])
+        assert np.array_equal(a["is_plane"], d["align_is_plane"]) and np.allclose(a["dist"], d["align_dist"], rtol=1e-10, atol=1e-12)
+        nb1 = c.associate(small_candidates[1]); L1 = c.linearize(small_candidates[:2])
+        assert np.array_equal(nb0, nb1) and np.array_equal(L0, L1)
