@@ -26,7 +26,7 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kSurvCap = 4096;
-constexpr int kMatchCache = 8;  // matches a thread remembers between the two exact passes
+constexpr int kMatchCap = 8192;  // (keypoint, point) matches a unit may record between the two exact passes
 constexpr unsigned long long kInf64 = 0x7ff0000000000000ull;  // +inf bits
 constexpr unsigned long long kNoKey = 0xffffffffffffffffull;
 
@@ -36,7 +36,8 @@ struct Smem {  // fixed part; dynamic arrays follow
     float u_hi, v_hi;
     float4 plane[5];   // conservative half-spaces of "may pass the pre-cull": a.xyz . p + a.w >= thr
     float thr[5];
-    int n_surv, overflow, n_groups, recheck;
+    int n_surv, overflow, n_groups, n_match, next_group;
+    double he_val;
     int warp_cnt[16], warp_q[16];
     int base_corr, base_q;
     double red[3][16];
@@ -103,12 +104,11 @@ struct Tables {
 };
 
 // Exact fp64 evaluation of one surviving scan point against the keypoints around its projection.
-// PASS 1: atomicMin of the squared distance per keypoint, remembering the matches in `cache`;
-// PASS 2 (only when some thread's cache overflowed): ties -> atomicMin of (original index, position).
+// PASS 1: atomicMin of the squared distance per keypoint, appending every match to the unit's list;
+// PASS 2 (only when that list overflowed): ties -> atomicMin of (original index, position).
 template <int PASS>
 __device__ __forceinline__ void exact_point(const DevPack &pk, const DevKf &K, const DevCand &c, const DevParams &pr, const Tables &T,
-                                            uint32_t si, int &n_cache, unsigned short *ckp, uint32_t *csi, unsigned long long *cbits,
-                                            int *recheck) {
+                                            uint32_t si, ulonglong2 *__restrict__ matches, int *n_match) {
     const long long g = K.pt_off + si;
     const float xf = pk.px[g], yf = pk.py[g], zf = pk.pz[g];
     double u, v;
@@ -128,8 +128,8 @@ __device__ __forceinline__ void exact_point(const DevPack &pk, const DevKf &K, c
                 const unsigned long long bits = (unsigned long long)__double_as_longlong(d2);
                 if (PASS == 1) {
                     atomicMin(&T.best_d2[k], bits);
-                    if (n_cache < kMatchCache) { ckp[n_cache] = (unsigned short)k; csi[n_cache] = si; cbits[n_cache] = bits; ++n_cache; }
-                    else *recheck = 1;
+                    const int slot = atomicAdd(n_match, 1);  // remembered for the tie pass (coalesced list in HBM/L2)
+                    if (slot < kMatchCap) matches[slot] = make_ulonglong2(bits, ((unsigned long long)k << 32) | si);
                 } else if (bits == T.best_d2[k]) {
                     atomicMin(&T.best_key[k], ((unsigned long long)pk.orig[g] << 32) | si);
                 }
@@ -139,7 +139,7 @@ __device__ __forceinline__ void exact_point(const DevPack &pk, const DevKf &K, c
 }
 
 __global__ void __launch_bounds__(kThreads, 2)
-k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
+k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, const int with_terms) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.x / B, b = blockIdx.x - f * B;
     const DevKf K = pk.kf[f];
@@ -206,7 +206,7 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
             S.thr[1] = -mslab_u; S.thr[2] = -mslab_u;
             S.thr[3] = -mslab_v; S.thr[4] = -mslab_v;
         }
-        S.n_surv = 0; S.overflow = 0; S.n_groups = 0; S.recheck = 0;
+        S.n_surv = 0; S.overflow = 0; S.n_groups = 0; S.n_match = 0; S.next_group = 0; S.he_val = 0.0;
         S.base_corr = 0; S.base_q = 0;
     }
     {
@@ -257,8 +257,14 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
         const float4 *Y = reinterpret_cast<const float4 *>(pk.py + K.pt_off);
         const float4 *Z = reinterpret_cast<const float4 *>(pk.pz + K.pt_off);
         const int ng = S.n_groups;
-#pragma unroll 2
-        for (int w = warp; w < ng; w += kThreads / 32) {
+        // the hand-eye term only needs the candidate: one lane of the last warp evaluates it while the
+        // other warps stream (groups are handed out dynamically, so nobody waits for that warp)
+        if (with_terms && K.he_valid && tid == kThreads - 32) S.he_val = hand_eye_term(pk, c, f);
+        for (;;) {
+            int w = 0;
+            if (lane == 0) w = atomicAdd(&S.next_group, 1);
+            w = __shfl_sync(0xffffffffu, w, 0);
+            if (w >= ng) break;
             const int i = (int)T.groups[w] * 32 + lane;  // float4 index
             const float4 x4 = ld_stream_f4(X + i), y4 = ld_stream_f4(Y + i), z4 = ld_stream_f4(Z + i);
             const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w};
@@ -295,22 +301,21 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
     const bool ovf = S.overflow != 0;
     const int ns = ovf ? K.n_pts : min(S.n_surv, kSurvCap);
     {
-        unsigned short ckp[kMatchCache];
-        uint32_t csi[kMatchCache];
-        unsigned long long cbits[kMatchCache];
-        int n_cache = 0;
-        for (int s = tid; s < ns; s += kThreads)
-            exact_point<1>(pk, K, c, pr, T, ovf ? (uint32_t)s : T.surv[s], n_cache, ckp, csi, cbits, &S.recheck);
+        ulonglong2 *matches = wk.k1_match + (long long)blockIdx.x * kMatchCap;
+        for (int s = tid; s < ns; s += kThreads) exact_point<1>(pk, K, c, pr, T, ovf ? (uint32_t)s : T.surv[s], matches, &S.n_match);
         __syncthreads();
         if (timing) clk[3] = clock64();
-        if (!S.recheck) {  // the usual case: every match is still in its thread's cache
-            for (int i = 0; i < n_cache; ++i)
-                if (cbits[i] == T.best_d2[ckp[i]])
-                    atomicMin(&T.best_key[ckp[i]], ((unsigned long long)pk.orig[K.pt_off + csi[i]] << 32) | csi[i]);
+        const int nm = S.n_match;
+        if (nm <= kMatchCap) {  // the usual case: among the recorded matches, the ones at the minimum compete on the index
+            for (int i = tid; i < nm; i += kThreads) {
+                const ulonglong2 m = matches[i];
+                const uint32_t k = (uint32_t)(m.y >> 32), si = (uint32_t)(m.y & 0xffffffffu);
+                if (m.x == T.best_d2[k]) atomicMin(&T.best_key[k], ((unsigned long long)pk.orig[K.pt_off + si] << 32) | si);
+            }
         } else {
-            for (int s = tid; s < ns; s += kThreads)
-                exact_point<2>(pk, K, c, pr, T, ovf ? (uint32_t)s : T.surv[s], n_cache, ckp, csi, cbits, &S.recheck);
+            for (int s = tid; s < ns; s += kThreads) exact_point<2>(pk, K, c, pr, T, ovf ? (uint32_t)s : T.surv[s], matches, &S.n_match);
         }
+        if (timing) clk[7] = clock64();
     }
     __syncthreads();
     if (ovf && tid == 0 && wk.overflow) atomicAdd(wk.overflow, 1);
@@ -353,7 +358,7 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
 
     // ---- 3-D/2-D term over (correspondence x covisible keyframe), iba_global.cpp:291-328
     double s2d = 0, v2d = 0, c2d = 0;
-    if (kept) {
+    if (kept && with_terms) {
         const int C = pk.n_covis;
         const double fx = K.fx, fy = K.fy, cx = K.cx, cy = K.cy, W = K.W, H = K.H;
         for (int k = tid; k < K.n_kp; k += kThreads) {
@@ -394,7 +399,7 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
         r.s2d = r.v2d = r.c2d = 0;
         for (int w = 0; w < kThreads / 32; ++w) { r.s2d += S.red[0][w]; r.v2d += S.red[1][w]; r.c2d += S.red[2][w]; }
         r.she = 0; r.che = 0;
-        if (kept && K.he_valid) { r.she = hand_eye_term(pk, c, f); r.che = 1; }
+        if (kept && K.he_valid && with_terms) { r.she = S.he_val; r.che = 1; }
         r.kept = kept ? 1.0 : 0.0;
         r.ncorr = kept ? (double)ncorr : 0.0;
         r.nq = kept ? (double)nq : 0.0;
@@ -402,10 +407,10 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
         wk.n_corr[(long long)b * pk.n_kf + f] = ncorr;
         wk.n_q[(long long)b * pk.n_kf + f] = kept ? nq : 0;
         if (timing) {
-            clk[7] = clock64();
             long long *o = wk.k1_clk + (long long)blockIdx.x * 8;
-            for (int i = 0; i < 7; ++i) o[i] = clk[i + 1] - clk[i];
-            o[7] = S.n_surv;
+            for (int i = 0; i < 6; ++i) o[i] = clk[i + 1] - clk[i];
+            o[6] = clock64() - clk[6];
+            o[7] = clk[7] - clk[3];  // thread 0's own tie pass (the rest of exact-2 is barrier wait)
         }
     }
 }
@@ -431,9 +436,9 @@ cudaError_t assoc2d_configure(size_t smem) {
     return e;
 }
 
-cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, cudaStream_t st) {
+cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, cudaStream_t st, int with_terms) {
     if (B <= 0 || pk.n_kf <= 0) return cudaSuccess;
-    k_assoc2d<<<(unsigned)(pk.n_kf * B), kThreads, smem, st>>>(pk, wk, pr, B);
+    k_assoc2d<<<(unsigned)(pk.n_kf * B), kThreads, smem, st>>>(pk, wk, pr, B, with_terms);
     return cudaGetLastError();
 }
 

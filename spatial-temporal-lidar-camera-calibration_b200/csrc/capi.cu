@@ -109,6 +109,7 @@ void free_pack(stl_ctx *c) {
 void free_work(stl_ctx *c) {
     DevWork &w = c->wk;
     dfree(w.cand); dfree(w.corr_kp); dfree(w.corr_pt); dfree(w.corr_sp); dfree(w.q_corr); dfree(w.n_corr); dfree(w.n_q);
+    dfree(w.k1_match);
     dfree(w.frame); dfree(w.align); dfree(w.nn_pos); dfree(w.nb); dfree(w.nb_m); dfree(w.nb_last); dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn); dfree(w.dbg_stats);
     dfree(w.overflow); dfree(w.k1_clk);
     w = DevWork();
@@ -169,7 +170,7 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
     if (ctx->wk_cap == 0) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        const size_t per_cand = (size_t)pk.n_kp_total * 16 + (size_t)pk.n_mp_total * (4 * kMaxK + 16) + (size_t)pk.n_kf * (sizeof(FrameRec) + 4 * sizeof(AlignRec) + 8) + sizeof(DevCand);
+        const size_t per_cand = (size_t)pk.n_kp_total * 16 + (size_t)pk.n_mp_total * (4 * kMaxK + 16) + (size_t)pk.n_kf * (sizeof(FrameRec) + 4 * sizeof(AlignRec) + 8 + sizeof(ulonglong2) * 8192) + sizeof(DevCand);
         size_t budget = std::min<size_t>((size_t)4 << 30, free_b / 4);
         int cap = (int)std::max<size_t>(1, std::min<size_t>(budget / std::max<size_t>(per_cand, 1), 256));
         DevWork &w = ctx->wk;
@@ -179,6 +180,7 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
         CK(cudaMalloc(&w.cand, sizeof(DevCand) * cap));
         CK(cudaMalloc(&w.corr_kp, 4 * nk)); CK(cudaMalloc(&w.corr_pt, 4 * nk)); CK(cudaMalloc(&w.corr_sp, 4 * nk)); CK(cudaMalloc(&w.q_corr, 4 * nk));
         CK(cudaMalloc(&w.n_corr, 4 * nf)); CK(cudaMalloc(&w.n_q, 4 * nf));
+        CK(cudaMalloc(&w.k1_match, sizeof(ulonglong2) * 8192 * nf));
         CK(cudaMalloc(&w.frame, sizeof(FrameRec) * nf)); CK(cudaMalloc(&w.align, sizeof(AlignRec) * nf * w.sub));
         {
             const size_t nm = (size_t)std::max<long long>(pk.n_mp_total, 1) * cap;
@@ -605,7 +607,7 @@ stl_status_t stl_debug_frame(stl_ctx_t *ctx, int32_t b, int32_t kf, double out[1
         cudaMemcpy(h.data(), ctx->wk.k1_clk, 64 * (size_t)ctx->pk.n_kf, cudaMemcpyDeviceToHost);
         double a[8] = {0};
         for (int f = 0; f < ctx->pk.n_kf; ++f) for (int i = 0; i < 8; ++i) a[i] += (double)h[(size_t)f * 8 + i] / ctx->pk.n_kf;
-        fprintf(stderr, "[stl] K1 mean clocks/unit: prologue %.0f | stream %.0f | exact-1 %.0f | exact-2 %.0f | compact %.0f | covis %.0f | epilogue %.0f | survivors %.0f\n", a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+        fprintf(stderr, "[stl] K1 mean clocks/unit: prologue %.0f | stream %.0f | exact-1 %.0f | exact-2 %.0f | compact %.0f | covis %.0f | epilogue %.0f | tie-pass(thread 0) %.0f\n", a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
     }
     if (getenv("STL_DEBUG_STATS")) {
         unsigned long long st[8];
@@ -656,7 +658,7 @@ stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[4]
     CK(cudaMemcpyAsync(ctx->wk.cand, hc, sizeof(DevCand), cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->h2d_done, st));
     // 2-D association at x0 (FindProjectCorrespondences, iba_local.cpp:191) reuses K1
-    { StageTimer t(ctx, STL_STAGE_ASSOC2D, st); CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, st)); }
+    { StageTimer t(ctx, STL_STAGE_ASSOC2D, st); CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, st, 0)); }
     cudaError_t e;
     { StageTimer t(ctx, 5, st); e = lm_associate(ctx->pk, ctx->wk, ctx->dpr, ctx->lm, st); }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "associate: %s", cudaGetErrorString(e));

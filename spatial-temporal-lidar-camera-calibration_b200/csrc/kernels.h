@@ -56,6 +56,7 @@ struct DevWork {
     double *dbg_dist = nullptr;
     uint32_t *dbg_knn = nullptr;  // [n_kp_total][32]
     unsigned long long *dbg_stats = nullptr;  // [8] traversal statistics (debug runs)
+    ulonglong2 *k1_match = nullptr;  // [Bc][n_kf][8192] (d2 bits, keypoint<<32 | position) recorded by K1's exact pass
     long long *k1_clk = nullptr;  // optional [units][8] phase clocks of K1 (diagnostic, STL_K1_CLK=1)
     int *overflow = nullptr;      // K1 survivor-list overflow counter (diagnostic)
 };
@@ -71,7 +72,9 @@ cudaError_t build_plane_index(const DevPack &pk, const DevKf *h_kf, int kf_begin
 // ---- K1 (assoc2d.cu) ------------------------------------------------------------
 size_t assoc2d_smem_bytes(int max_kp, int max_bm_words, int max_cells, int max_groups);
 cudaError_t assoc2d_configure(size_t smem);
-cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, cudaStream_t st);
+// with_terms = 0: correspondences only (the association pass of the LM path needs neither the covisible
+// re-projection term nor the hand-eye term)
+cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, cudaStream_t st, int with_terms = 1);
 
 // ---- K2 (knn3d.cu) ---------------------------------------------------------------
 // K2a (traversal: 1-NN + k-NN, warp per query) then K2b (plane fit + distance, thread per query)
