@@ -86,7 +86,14 @@ typedef struct stl_params {
      * can live in the index like the reference's KD-trees do; evaluations then only look it up.
      * Costs ~36 B per point and a longer upload; results are identical. */
     int32_t plane_index;          /* 0                                               */
-    int32_t reserved_;
+    /* Which BAError the evaluation follows.  0 = src/examples/iba_global.cpp (default).
+     * 1 = src/examples/iba_global_stable.cpp: the 2-D queries are the re-projected map points of the
+     * keypoints that observe one (:67-80, computed at upload from kp_mappoint and Tcw), a projected
+     * scan point is kept when its ROUNDED pixel is inside the image (:92-94), and ComputeAlignmentDist
+     * gates on k < 3 before the fit and on the neighbourhood extent after it (:154,:163-171).
+     * stl_associate / stl_linearize_* (iba_local.cpp has no such variant) and plane_index are refused
+     * with variant 1. */
+    int32_t variant;              /* 0                                               */
 } stl_params_t;
 
 /*

@@ -125,7 +125,14 @@ class Oracle {
             if (z > 0) {
                 const double u = (fx * x + cx * z) / z;
                 const double v = (fx * y + cy * z) / z;  // fx, not fy (iba_global.cpp:73)
-                if (0 <= u && u < W && 0 <= v && v < H) { proj.push_back(u); proj.push_back(v); pidx.push_back((uint32_t)i); }
+                bool in;
+                if (pr_.variant == 1) {  // iba_global_stable.cpp:92-94: the ROUNDED pixel must be inside the image
+                    const double ru = std::round(u), rv = std::round(v);
+                    in = 0 <= ru && ru < W && 0 <= rv && rv < H;
+                } else {
+                    in = 0 <= u && u < W && 0 <= v && v < H;
+                }
+                if (in) { proj.push_back(u); proj.push_back(v); pidx.push_back((uint32_t)i); }
             }
         }
         if (pidx.empty()) return;
@@ -133,7 +140,8 @@ class Oracle {
         const double maxd2 = pr_.max_pixel_dist * pr_.max_pixel_dist;
         const int64_t k0 = pk_.kp_offset[f], k1 = pk_.kp_offset[f + 1];
         for (int64_t k = k0; k < k1; ++k) {
-            const double q[2] = {(double)pk_.kp_xy[k * 2], (double)pk_.kp_xy[k * 2 + 1]};
+            double q[2] = {(double)pk_.kp_xy[k * 2], (double)pk_.kp_xy[k * 2 + 1]};
+            if (pr_.variant == 1 && !stable_keypoint(f, k, q)) continue;  // only keypoints that observe a map point are queried
             uint32_t idx[2]; double d2[2]; bool tie = false;
             const size_t got = knn(tree, q, 1, idx, d2, strict, &tie);
             if (got > 0 && d2[0] <= maxd2) {
@@ -143,8 +151,26 @@ class Oracle {
         }
     }
 
+    // iba_global_stable.cpp:67-80: the query pixel of a keypoint is the re-projection of its map point
+    // with the SLAM pose (float32 widened; fx, fy, cx, cy as stored), in keypoint-index order here
+    // (the reference walks an unordered_map; only the summation order depends on it).  The 3x3 * 3x1
+    // product is summed (R0 X + R1 Y) + R2 Z, then + t (Eigen's order for this expression is unverified).
+    bool stable_keypoint(int f, int64_t k, double q[2]) const {
+        const float *mp = pk_.kp_mappoint + (size_t)k * 3;
+        if (std::isnan(mp[0])) return false;
+        const float *Tcw = pk_.Tcw + (size_t)f * 12;
+        const double X = mp[0], Y = mp[1], Z = mp[2];
+        double P[3];
+        for (int i = 0; i < 3; ++i)
+            P[i] = (((double)Tcw[i * 4] * X + (double)Tcw[i * 4 + 1] * Y) + (double)Tcw[i * 4 + 2] * Z) + (double)Tcw[i * 4 + 3];
+        const double fx = pk_.intrinsics[f * 4], fy = pk_.intrinsics[f * 4 + 1], cx = pk_.intrinsics[f * 4 + 2], cy = pk_.intrinsics[f * 4 + 3];
+        q[0] = fx * P[0] / P[2] + cx;
+        q[1] = fy * P[1] / P[2] + cy;
+        return true;
+    }
+
     // ------------------------------------------------------------------ ComputeAlignmentDist
-    // iba_global.cpp:111-156
+    // iba_global.cpp:111-156; variant 1 = iba_global_stable.cpp:130-176
     void align_dist(int f, const double q[3], AlignResult &r, bool strict, TieStats *ties) const {
         const std::vector<double> &P = scans_[f];
         const Tree3 &tree = *trees_[f];
@@ -172,8 +198,12 @@ class Oracle {
         r.m = (int32_t)m;
         for (size_t i = 0; i < m; ++i) r.knn[i] = idx[i];
         if (m == 0) return;  // unreachable in the reference (nn_pt is a data point); guards sq_dist[k-1]
-        if (d2[m - 1] < pr_.min_diff_dist * pr_.min_diff_dist) return;
-        if ((int)m < pr_.norm_min_pts) return;
+        if (pr_.variant == 1) {
+            if (m < 3) return;  // iba_global_stable.cpp:154
+        } else {
+            if (d2[m - 1] < pr_.min_diff_dist * pr_.min_diff_dist) return;
+            if ((int)m < pr_.norm_min_pts) return;
+        }
         Cumulants cu;
         for (size_t i = 0; i < m; ++i) cu.add(P[(size_t)idx[i] * 3], P[(size_t)idx[i] * 3 + 1], P[(size_t)idx[i] * 3 + 2]);
         double cov[6], nrm[3];
@@ -188,6 +218,15 @@ class Oracle {
             reg_err += std::fabs(dot3(d, nrm));
         }
         if (reg_err / (double)(m - 1) > pr_.norm_reg_threshold) return;
+        if (pr_.variant == 1) {  // iba_global_stable.cpp:167-171: extent gate after the fit, on the norm
+            double max_dist = 0;
+            for (size_t i = 0; i < m; ++i) {
+                const double *p = &P[(size_t)idx[i] * 3];
+                const double d[3] = {p[0] - nn_pt[0], p[1] - nn_pt[1], p[2] - nn_pt[2]};
+                max_dist = std::max(std::sqrt(dot3(d, d)), max_dist);
+            }
+            if (max_dist < pr_.min_diff_dist) return;
+        }
         r.is_plane = 1;
         r.dist = std::fabs(dot3(dq, nrm));
     }
@@ -209,7 +248,11 @@ class Oracle {
         for (size_t i = 0; i < n; ++i) apply(Tcl, &PL[i * 3], &PC[i * 3]);  // TransformPointCloud (pointcloud.h:82-86)
         std::vector<Corr> corrset;
         find_corr(f, PC, corrset, strict, ties);
-        acc.q2d += pk_.kp_offset[f + 1] - pk_.kp_offset[f];
+        if (pr_.variant == 1) {
+            for (int64_t k = pk_.kp_offset[f]; k < pk_.kp_offset[f + 1]; ++k) acc.q2d += !std::isnan(pk_.kp_mappoint[(size_t)k * 3]);
+        } else {
+            acc.q2d += pk_.kp_offset[f + 1] - pk_.kp_offset[f];
+        }
         if (dbg) dbg->corr = corrset;
         if ((int)corrset.size() < pr_.num_min_corr) return;  // iba_global.cpp:203
         acc.kept++;

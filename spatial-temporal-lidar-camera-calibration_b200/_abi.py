@@ -51,7 +51,7 @@ class Params(C.Structure):
         ("gpr_l", C.c_double),
         ("gpr_sigma_noise", C.c_double),
         ("plane_index", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("variant", C.c_int32),
     ]
 
 

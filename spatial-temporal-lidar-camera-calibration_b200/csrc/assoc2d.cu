@@ -43,6 +43,7 @@ struct Smem {  // fixed part; dynamic arrays follow
     double red[3][16];
 };
 
+template <bool STABLE>
 __device__ __forceinline__ bool exact_project(const DevCand &c, double fx, double cx, double cy, double W, double H, float xf,
                                               float yf, float zf, double &u, double &v) {
     double xc, yc, zc;
@@ -50,6 +51,10 @@ __device__ __forceinline__ bool exact_project(const DevCand &c, double fx, doubl
     if (!(zc > 0.0)) return false;
     u = ddiv(dadd(dmul(fx, xc), dmul(cx, zc)), zc);
     v = ddiv(dadd(dmul(fx, yc), dmul(cy, zc)), zc);  // fx, not fy (iba_global.cpp:73)
+    if (STABLE) {  // iba_global_stable.cpp:92-94: the rounded pixel (half away from zero) must be inside
+        const double ru = round(u), rv = round(v);
+        return (0.0 <= ru && ru < W && 0.0 <= rv && rv < H);
+    }
     return (0.0 <= u && u < W && 0.0 <= v && v < H);
 }
 
@@ -112,8 +117,10 @@ __device__ __forceinline__ void exact_point(const DevPack &pk, const DevKf &K, c
     const long long g = K.pt_off + si;
     const float xf = pk.px[g], yf = pk.py[g], zf = pk.pz[g];
     double u, v;
-    if (!exact_project(c, (double)K.fx, (double)K.cx, (double)K.cy, (double)K.W, (double)K.H, xf, yf, zf, u, v)) return;
-    const double rp = sqrt(pr.max_pixel_dist2) + 1e-6;
+    const bool stable = pk.kp_xyd != nullptr;
+    if (stable ? !exact_project<true>(c, (double)K.fx, (double)K.cx, (double)K.cy, (double)K.W, (double)K.H, xf, yf, zf, u, v)
+               : !exact_project<false>(c, (double)K.fx, (double)K.cx, (double)K.cy, (double)K.W, (double)K.H, xf, yf, zf, u, v)) return;
+    const double rp = sqrt(pr.max_pixel_dist2) + (stable ? 1e-3 : 1e-6);  // stable: cells are keyed by the float32 copy
     int gx0 = (int)floor((u - rp) * (1.0 / kGridCell)), gx1 = (int)floor((u + rp) * (1.0 / kGridCell));
     int gy0 = (int)floor((v - rp) * (1.0 / kGridCell)), gy1 = (int)floor((v + rp) * (1.0 / kGridCell));
     gx0 = max(gx0, 0); gy0 = max(gy0, 0); gx1 = min(gx1, K.gw - 1); gy1 = min(gy1, K.gh - 1);
@@ -121,8 +128,10 @@ __device__ __forceinline__ void exact_point(const DevPack &pk, const DevKf &K, c
         const int a = T.gstart[gy * K.gw + gx0], b = T.gstart[gy * K.gw + gx1 + 1];  // cells of one row are contiguous
         for (int j = a; j < b; ++j) {
             const int k = T.gkp[j];
-            const float2 q = T.kp[k];
-            const double dx = dsub((double)q.x, u), dy = dsub((double)q.y, v);
+            double qx, qy;
+            if (stable) { const double2 q = pk.kp_xyd[K.kp_off + k]; qx = q.x; qy = q.y; }
+            else { const float2 q = T.kp[k]; qx = (double)q.x; qy = (double)q.y; }
+            const double dx = dsub(qx, u), dy = dsub(qy, v);
             const double d2 = dadd(dmul(dx, dx), dmul(dy, dy));  // nanoflann.hpp:524-535, query - data
             if (d2 <= pr.max_pixel_dist2) {
                 const unsigned long long bits = (unsigned long long)__double_as_longlong(d2);

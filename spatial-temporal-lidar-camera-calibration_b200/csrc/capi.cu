@@ -101,7 +101,7 @@ void free_pack(stl_ctx *c) {
     DevPack &p = c->pk;
     dfree(p.kf); dfree(p.px); dfree(p.py); dfree(p.pz); dfree(p.orig); dfree(p.node_lo); dfree(p.node_hi);
     dfree(p.pl_rec); dfree(p.pl_m);
-    dfree(p.bitmap); dfree(p.grid_start); dfree(p.grid_kp); dfree(p.kp_xy); dfree(p.kp_mp); dfree(p.Tcw);
+    dfree(p.bitmap); dfree(p.grid_start); dfree(p.grid_kp); dfree(p.kp_xy); dfree(p.kp_xyd); dfree(p.kp_mp); dfree(p.Tcw);
     dfree(p.relpose); dfree(p.covis_valid); dfree(p.covis_uv); dfree(p.he_Tc); dfree(p.he_Tl);
     p = DevPack();
     c->has_pack = false;
@@ -136,6 +136,7 @@ void set_dev_params(stl_ctx *c) {
     d.min_pts = p.norm_min_pts;
     d.use_plane = p.use_plane;
     d.use_gpr = p.use_gpr; d.plane_index = p.plane_index;
+    d.variant = p.variant; d.min_diff = p.min_diff_dist;
     d.gpr_sigma = p.gpr_sigma; d.gpr_l = p.gpr_l; d.gpr_noise = p.gpr_sigma_noise;
 }
 
@@ -173,6 +174,7 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
         const size_t per_cand = (size_t)pk.n_kp_total * 16 + (size_t)pk.n_mp_total * (4 * kMaxK + 16) + (size_t)pk.n_kf * (sizeof(FrameRec) + 4 * sizeof(AlignRec) + 8 + sizeof(ulonglong2) * 8192) + sizeof(DevCand);
         size_t budget = std::min<size_t>((size_t)4 << 30, free_b / 4);
         int cap = (int)std::max<size_t>(1, std::min<size_t>(budget / std::max<size_t>(per_cand, 1), 256));
+        if (const char *e = getenv("STL_MAX_CHUNK")) cap = std::max(1, std::min(cap, atoi(e)));  // tests: force the multi-chunk path
         DevWork &w = ctx->wk;
         w.Bc = cap;
         w.sub = 4;
@@ -273,7 +275,7 @@ void stl_default_params(stl_params_t *p) {
     p->max_3d_dist = 1.0; p->robust_kernel_delta = 2.98; p->robust_kernel_3ddelta = 1.0;
     p->num_min_corr = 30; p->norm_max_pts = 30; p->norm_min_pts = 5; p->use_plane = 1;
     p->use_gpr = 0; p->gpr_sigma = 10.0; p->gpr_l = 10.0; p->gpr_sigma_noise = 1e-10;
-    p->plane_index = 0; p->reserved_ = 0;
+    p->plane_index = 0; p->variant = 0;
 }
 
 stl_status_t stl_create(const stl_params_t *params, int32_t device, stl_ctx_t **out) {
@@ -285,6 +287,7 @@ stl_status_t stl_create(const stl_params_t *params, int32_t device, stl_ctx_t **
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return STL_ERR_NO_DEVICE;
     if (prop.major != 10) return STL_ERR_NO_DEVICE;  // kernels are built for sm_100a only
     if (params->norm_max_pts < 1 || params->norm_max_pts > kMaxK) return STL_ERR_CAPACITY;
+    if (params->variant != 0 && params->variant != 1) return STL_ERR_INVALID;
     if (cudaSetDevice(device) != cudaSuccess) return STL_ERR_CUDA;
     stl_ctx *c = new stl_ctx();
     c->device = device;
@@ -390,16 +393,46 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
         return fail(ctx, STL_ERR_CAPACITY, "K1 needs %zu B of shared memory (%d keypoints); device limit %d", ctx->k1_smem, max_kp, smem_optin);
     CK(assoc2d_configure(ctx->k1_smem));
 
+    // ---- variant 1 (iba_global_stable.cpp:67-80): the query pixel of a keypoint is its map point re-projected
+    // with the SLAM pose, in fp64; keypoints without a map point are not queried (NaN).  A float32 copy
+    // drives the coarse structures (grid, bitmap: their margins cover the rounding), the fp64 one the exact pass.
+    std::vector<double> kpd;
+    std::vector<float> kpf;
+    const float *kp_host = p->kp_xy;
+    if (ctx->params.variant == 1) {
+        kpd.assign((size_t)std::max<long long>(NK, 1) * 2, std::nan(""));
+        kpf.assign((size_t)std::max<long long>(NK, 1) * 2, std::nanf(""));
+#pragma omp parallel for schedule(static)
+        for (int f = 0; f < F; ++f) {
+            const float *T = p->Tcw + (size_t)f * 12;
+            const double fx = p->intrinsics[f * 4], fy = p->intrinsics[f * 4 + 1], cx = p->intrinsics[f * 4 + 2], cy = p->intrinsics[f * 4 + 3];
+            for (long long k = p->kp_offset[f]; k < p->kp_offset[f + 1]; ++k) {
+                const float *mp = p->kp_mappoint + k * 3;
+                if (mp[0] != mp[0]) continue;
+                const double X = mp[0], Y = mp[1], Z = mp[2];
+                double P[3];
+                for (int i = 0; i < 3; ++i)
+                    P[i] = (((double)T[i * 4] * X + (double)T[i * 4 + 1] * Y) + (double)T[i * 4 + 2] * Z) + (double)T[i * 4 + 3];
+                kpd[k * 2] = fx * P[0] / P[2] + cx;
+                kpd[k * 2 + 1] = fy * P[1] / P[2] + cy;
+                kpf[k * 2] = (float)kpd[k * 2];
+                kpf[k * 2 + 1] = (float)kpd[k * 2 + 1];
+            }
+        }
+        kp_host = kpf.data();
+    }
+
     // ---- keypoint bitmap + cell grid (host, candidate-independent)
     std::vector<uint32_t> bitmap((size_t)bmw, 0u), gstart((size_t)gcells, 0u), gkp((size_t)std::max<long long>(NK, 1), 0u);
-    const double Rdil = ctx->params.max_pixel_dist + (double)kFastErrPx;
+    // variant 1: + the float32 rounding of the coarse keypoint copy (< 1e-3 px for any image size)
+    const double Rdil = ctx->params.max_pixel_dist + (double)kFastErrPx + (ctx->params.variant == 1 ? 1e-3 : 0.0);
 #pragma omp parallel for schedule(dynamic, 8)
     for (int f = 0; f < F; ++f) {
         const DevKf &K = hk[f];
         uint32_t *bm = bitmap.data() + K.bm_off;
         uint32_t *gs = gstart.data() + K.grid_off;
         uint32_t *gk = gkp.data() + K.kp_off;
-        const float *kp = p->kp_xy + K.kp_off * 2;
+        const float *kp = kp_host + K.kp_off * 2;
         const int bw_total = (K.W + kBmCell - 1) / kBmCell + 2, bh_total = (K.H + kBmCell - 1) / kBmCell + 2;
         const int ncell = K.gw * K.gh;
         std::vector<uint32_t> cell(K.n_kp);
@@ -440,7 +473,11 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     CK(cudaMemcpyAsync(pk.grid_start, gstart.data(), 4 * (size_t)gcells, cudaMemcpyHostToDevice, st));
     if (NK > 0) {
         CK(cudaMemcpyAsync(pk.grid_kp, gkp.data(), 4 * (size_t)NK, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(pk.kp_xy, p->kp_xy, 8 * (size_t)NK, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(pk.kp_xy, kp_host, 8 * (size_t)NK, cudaMemcpyHostToDevice, st));
+        if (ctx->params.variant == 1) {
+            CK(cudaMalloc(&pk.kp_xyd, sizeof(double2) * nkk));
+            CK(cudaMemcpyAsync(pk.kp_xyd, kpd.data(), 16 * (size_t)NK, cudaMemcpyHostToDevice, st));
+        }
         CK(cudaMemcpyAsync(pk.kp_mp, p->kp_mappoint, 12 * (size_t)NK, cudaMemcpyHostToDevice, st));
         if (C > 0) CK(cudaMemcpyAsync(pk.covis_uv, p->covis_uv, 8 * (size_t)NK * C, cudaMemcpyHostToDevice, st));
     }
@@ -647,6 +684,8 @@ stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[4]
     if (!ctx || !x0) return STL_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!ctx->has_pack) return fail(ctx, STL_ERR_STATE, "stl_upload_pack has not been called");
+    if (ctx->params.variant != 0)
+        return fail(ctx, STL_ERR_STATE, "stl_associate follows iba_local.cpp, which has no iba_global_stable variant: create the context with variant = 0");
     CK(cudaSetDevice(ctx->device));
     stl_status_t s = ensure_work(ctx, 1, false);
     if (s != STL_OK) return s;

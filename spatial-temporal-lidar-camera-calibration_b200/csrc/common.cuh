@@ -73,7 +73,8 @@ struct DevParams {
     double max_3d_dist2, delta2d, delta3d;
     double w0, w1;
     int num_min_corr, k, min_pts, use_plane;
-    int use_gpr, plane_index;
+    int use_gpr, plane_index, variant;
+    double min_diff;  // un-squared (variant 1 compares norms)
     double gpr_sigma, gpr_l, gpr_noise;
 };
 

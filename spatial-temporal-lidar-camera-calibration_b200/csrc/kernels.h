@@ -22,6 +22,7 @@ struct DevPack {
     uint32_t *grid_start = nullptr;  // per keyframe gw*gh+1 entries
     uint32_t *grid_kp = nullptr;     // [n_kp_total] keypoint ids sorted by cell (local ids)
     float2 *kp_xy = nullptr;         // [n_kp_total]
+    double2 *kp_xyd = nullptr;       // [n_kp_total] fp64 query pixels (variant 1 only; NaN = not queried)
     float *kp_mp = nullptr;          // [n_kp_total][3]
     float *Tcw = nullptr;            // [n_kf][12]
     float *relpose = nullptr;        // [n_kf][C][12]

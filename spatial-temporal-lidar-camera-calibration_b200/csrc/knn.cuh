@@ -253,13 +253,17 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
 struct PlaneOut { V3 n; double reg; int m; bool gates_ok; };
 
 __device__ __forceinline__ PlaneOut plane_thread(const ScanView &S, const uint32_t *__restrict__ nb, int m, double last, double cx,
-                                                 double cy, double cz, const DevParams &pr) {
+                                                 double cy, double cz, const DevParams &pr, const bool stable = false) {
     PlaneOut out;
     out.m = m;
     out.n = {0.0, 0.0, 0.0};
     out.reg = 0;
     out.gates_ok = false;
-    if (m == 0 || (last < pr.min_diff2) || (m < pr.min_pts)) return out;
+    if (stable) {  // iba_global_stable.cpp:154
+        if (m < 3) return out;
+    } else if (m == 0 || (last < pr.min_diff2) || (m < pr.min_pts)) {
+        return out;
+    }
     out.gates_ok = true;
     double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0;
     for (int j = 0; j < m; ++j) {
@@ -281,6 +285,9 @@ __device__ __forceinline__ PlaneOut plane_thread(const ScanView &S, const uint32
     }
     out.n = n;
     out.reg = reg / (double)(m - 1);
+    // iba_global_stable.cpp:167-171: after the regression gate, a neighbourhood whose farthest point
+    // (norm = sqrt of the k-NN distance) is closer than min_diff_dist is no plane either
+    if (stable && sqrt(last) < pr.min_diff) out.reg = __longlong_as_double(0x7ff0000000000000ll);
     return out;
 }
 

@@ -95,7 +95,7 @@ k_plane_dist(const DevPack pk, const DevWork wk, const DevParams pr, const int B
             int is_plane = 0, m = 0;
             if (pr.use_plane) {
                 const PlaneOut po = pr.plane_index ? plane_lookup(pk, K, np)
-                                                   : plane_thread(S, wk.nb + (qbase + qi) * kMaxK, wk.nb_m[qbase + qi], wk.nb_last[qbase + qi], nx, ny, nz, pr);
+                                                   : plane_thread(S, wk.nb + (qbase + qi) * kMaxK, wk.nb_m[qbase + qi], wk.nb_last[qbase + qi], nx, ny, nz, pr, pr.variant == 1);
                 m = po.m;
                 if (po.gates_ok && !(po.reg > pr.reg_thr)) {  // iba_global.cpp:147
                     is_plane = 1;
@@ -184,7 +184,7 @@ k_index_plane(const DevPack pk, const int kf_begin, const DevParams pr, const lo
         int mm = -1;
         if (p < K.n_pts) {
             const long long o = K.pt_off - first_pt + p;
-            const PlaneOut po = plane_thread(S, nb + o * kMaxK, nb_m[o], nb_last[o], (double)S.px[p], (double)S.py[p], (double)S.pz[p], pr);
+            const PlaneOut po = plane_thread(S, nb + o * kMaxK, nb_m[o], nb_last[o], (double)S.px[p], (double)S.py[p], (double)S.pz[p], pr, pr.variant == 1);
             r.nx = po.n.x; r.ny = po.n.y; r.nz = po.n.z; r.reg = po.reg;
             mm = po.gates_ok ? po.m : -(po.m + 1);
         }

@@ -289,3 +289,64 @@ def test_plane_index_option_gives_identical_results(oracle_mod, pkg, small_pack,
         assert np.array_equal(a["is_plane"], d["align_is_plane"]) and np.allclose(a["dist"], d["align_dist"], rtol=1e-10, atol=1e-12)
         nb1 = c.associate(small_candidates[1]); L1 = c.linearize(small_candidates[:2])
         assert np.array_equal(nb0, nb1) and np.array_equal(L0, L1)
+
+
+@pytest.mark.parametrize("plane_index", [0, 1])
+def test_stable_variant(oracle_mod, pkg, small_pack, small_candidates, plane_index):
+    """params.variant = 1 follows src/examples/iba_global_stable.cpp: queries are the re-projected map
+    points (fp64), the rounded pixel decides the image bound, gates are k < 3 and the extent after the fit."""
+    capi = importlib.import_module(PKG + ".capi")
+    p = pkg.default_params(); p.variant = 1; p.plane_index = plane_index
+    p.min_diff_dist = 0.45   # makes the extent gate (iba_global_stable.cpp:167-171) bite on some neighbourhoods
+    pack = small_pack[0].shard(0, 3)
+    orc = oracle_mod.Oracle(pack, params=p, kind="best")
+    want, ties, cnt = orc.ba_error_sums(small_candidates[:4], mode=0)
+    assert ties.sum() == 0 and want[:, 6].min() > 50
+    p0 = pkg.default_params(); p0.min_diff_dist = 0.45
+    base, _, _ = oracle_mod.Oracle(pack, params=p0, kind="best").ba_error_sums(small_candidates[:4], mode=0)
+    assert not np.array_equal(base[:, COUNTERS], want[:, COUNTERS])   # the variant is not a no-op on this data
+    with capi.Context(params=p) as c:
+        c.upload(pack)
+        got = c.eval_sums(small_candidates[:4])
+        _check_sums(got, want)
+        for b, f in ((0, 0), (3, 2)):
+            d = orc.frame_debug(small_candidates[b], f)
+            kp, pt = c.debug_corrset(b, f)
+            assert np.array_equal(kp, d["corr_kp"]) and np.array_equal(pt, d["corr_pt"])
+            a = c.debug_align(b, f)
+            assert np.array_equal(a["nn"], d["align_nn"]) and np.array_equal(a["m"], d["align_m"])
+            assert np.array_equal(a["is_plane"], d["align_is_plane"]) and np.allclose(a["dist"], d["align_dist"], rtol=1e-10, atol=1e-12)
+            assert 0 < a["is_plane"].sum() < len(a["is_plane"])
+        with pytest.raises(pkg._abi.StlError):   # iba_local.cpp has no such variant
+            c.associate(small_candidates[0])
+
+
+def test_batch_larger_than_a_chunk(pkg, small_pack, small_candidates, synth, monkeypatch):
+    """A poll batch larger than the work-buffer chunk is evaluated in several passes with identical results."""
+    capi = importlib.import_module(PKG + ".capi")
+    pack = small_pack[0].shard(2, 5)
+    X = synth.candidates(small_pack[1], 7, 0.4, seed=11)
+    with capi.Context() as c:
+        c.upload(pack)
+        want = c.eval_sums(X)
+    monkeypatch.setenv("STL_MAX_CHUNK", "3")
+    with capi.Context() as c:
+        c.upload(pack)
+        assert np.array_equal(c.eval_sums(X), want)
+        c.associate(X[1])
+        L = c.linearize(X)
+        assert np.array_equal(L[1], c.linearize(X[1:2])[0])
+
+
+def test_concurrent_callers_are_serialised(gpu_ctx, small_candidates):
+    """BALoss::eval_x is const and NOMAD may call it from several evaluation threads
+    (iba_global.cpp:377): concurrent calls on one context must give the single-threaded answers."""
+    import threading
+    want = gpu_ctx.eval_sums(small_candidates)
+    got = [None] * 8
+    def work(i):
+        got[i] = gpu_ctx.eval_sums(small_candidates[i % 4: i % 4 + 1])[0]
+    th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in th]; [t.join() for t in th]
+    for i in range(8):
+        assert np.array_equal(got[i], want[i % 4])

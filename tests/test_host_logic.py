@@ -85,3 +85,32 @@ def test_pack_npz_roundtrip(pkg, small_pack):
     assert back.n_kf == 2 and np.array_equal(back.scan_xyz, sub.scan_xyz) and np.array_equal(back.he_Tl, sub.he_Tl)
     c = sub.as_c()
     assert c.n_kf == 2 and c.scan_offset[2] == sub.n_points
+
+
+def test_stand_in_optimisers_on_analytic_problems(pkg):
+    """optim.py (the NOMAD / Ceres stand-ins used by the final-extrinsic parity tests) on closed forms."""
+    optim = importlib.import_module(PKG + ".optim")
+    target = np.array([0.02, -0.03, 0.01, 0.1, -0.2, 0.05, 0.3])
+
+    class Quad:
+        def eval_block(self, X):
+            X = np.atleast_2d(X)
+            # objective + one active constraint x[6] <= 0.25 + two slack ones
+            return [[float(((x - target) ** 2).sum()), x[6] - 0.25, -1.0, -1.0] for x in X]
+
+    x, bbo, n_eval, hist = optim.poll_search(Quad(), np.zeros(7), -np.ones(7), np.ones(7), max_bb_eval=1500, init_frame=0.5 * np.ones(7))
+    want = target.copy(); want[6] = 0.25
+    assert np.abs(x - want).max() < 1e-3 and bbo[1] <= 0 and n_eval <= 1500
+    assert all(b[1] <= a[1] or b[2] < a[2] for a, b in zip(hist, hist[1:]))
+
+    class Rosen:
+        def build(self, x):
+            return None
+
+        def evaluate(self, x):  # residuals r = (10 (x1 - x0^2), 1 - x0) padded to 7 parameters
+            r = np.concatenate([[10 * (x[1] - x[0] ** 2), 1 - x[0]], x[2:]])
+            J = np.zeros((7, 7)); J[0, 0] = -20 * x[0]; J[0, 1] = 10; J[1, 0] = -1; J[2:, 2:] = np.eye(5)
+            return 0.5 * float(r @ r), J.T @ r, J.T @ J
+
+    x, costs = optim.lm_refine(Rosen(), np.array([-1.2, 1.0, 0.3, 0, 0, 0, 0.1]), max_iba_iter=3, max_num_iterations=60)
+    assert np.abs(x[:2] - 1).max() < 1e-6 and np.abs(x[2:]).max() < 1e-8 and costs[-1] < 1e-12

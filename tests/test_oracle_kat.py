@@ -91,6 +91,32 @@ def test_lattice_correspondences_are_known_by_construction(pkg, oracle_mod):
     assert d["ties"].sum() == 0
 
 
+def test_stable_variant_rules_on_the_lattice(pkg, oracle_mod):
+    """iba_global_stable.cpp: (a) only keypoints that observe a map point are queried, at the map
+    point's re-projection (:67-80); (b) a scan point whose ROUNDED pixel is inside stays (:92-94)."""
+    pack, K = _lattice_pack(pkg)
+    # two extra scan points at u = -0.25 (rounds to 0: kept by the variant only) and u = -0.75 (rounds to -1)
+    z = np.float32(4.0)
+    extra = np.array([[(-0.25 - 320.0) / 512.0 * 4.0, (100.0 - 240.0) / 512.0 * 4.0, z],
+                      [(-0.75 - 320.0) / 512.0 * 4.0, (200.0 - 240.0) / 512.0 * 4.0, z]], np.float32)
+    n0 = int(pack.scan_offset[1])
+    pack.scan_xyz = np.concatenate([pack.scan_xyz, extra]); pack.scan_offset = np.array([0, n0 + 2])
+    # map points: keypoint k (k % 4 == 0) observes the world point that IS lattice point k (Tcw = identity),
+    # so its query pixel is the lattice pixel itself whatever kp_xy says; keypoints K-2, K-1 look at the extras
+    mp = np.full((K, 3), np.nan, np.float32)
+    mp[::4] = pack.scan_xyz[:K][::4]
+    mp[K - 2], mp[K - 1] = extra[0], extra[1]
+    pack.kp_mappoint = mp
+    p = pkg.default_params(); p.variant = 1
+    d = oracle_mod.Oracle(pack, params=p).frame_debug(np.array([0, 0, 0, 0, 0, 0, 1.0]), 0)
+    want_kp = sorted(set(range(0, K, 4)) | {K - 2})
+    assert list(d["corr_kp"]) == want_kp
+    assert list(d["corr_pt"]) == [k if k != K - 2 else n0 for k in want_kp]
+    # the same pack under iba_global.cpp: kp_xy is used as is and the extras are outside the image
+    d0 = oracle_mod.Oracle(pack).frame_debug(np.array([0, 0, 0, 0, 0, 0, 1.0]), 0)
+    assert list(d0["corr_kp"]) == [k for k in range(K) if k % 3 != 1]
+
+
 @pytest.fixture(scope="module")
 def assoc(oracle_mod, small_pack, small_candidates):
     pack, _ = small_pack
