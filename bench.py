@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--shard", default="candidates", choices=["candidates", "keyframes"])
     ap.add_argument("--cpu-sample-kf", type=int, default=192, help="keyframes of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-poll-batch", action="store_true", help="skip the 256-candidate poll-batch measurement")
+    ap.add_argument("--poll-batch", type=int, default=256)
     ap.add_argument("--no-plane-index", action="store_true", help="skip the extra measurement with params.plane_index=1")
     ap.add_argument("--seed", type=int, default=1000)
     return ap.parse_args()
@@ -282,6 +284,35 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
 
+    # ---- BASELINE configs[3] shape: a NOMAD poll batch of 256 candidates (cost) + the same batch linearised on the
+    # frozen association (cost + JtJ), candidates dealt out across the ranks; device-timed, reported beside `value`
+    pb_ms, pb_B = float("nan"), 0
+    if not args.no_poll_batch:
+        pb_total = args.poll_batch
+        if by_kf:
+            Xp = synth.candidates(x_gt, pb_total + 1, 0.2, seed=43)[1:]
+        else:
+            Xp = synth.candidates(x_gt, pb_total + 1, 0.2, seed=43)[1:][rank::world]
+        pb_B = len(Xp)
+        d_ps = torch.zeros((pb_B, _abi.STL_EVAL_NSUMS), dtype=torch.float64, device=dev)
+        d_pl = torch.zeros((pb_B, _abi.STL_LIN_NSUMS), dtype=torch.float64, device=dev)
+
+        def poll_step():
+            ctx.eval_sums_device(Xp, d_ps.data_ptr(), stream.cuda_stream)
+            ctx.linearize_device(Xp, d_pl.data_ptr(), stream.cuda_stream)
+            if by_kf:
+                dist.all_reduce(d_ps)
+                dist.all_reduce(d_pl)
+        ctx.associate(Xp[0])
+        ctx.eval_sums_device(Xp[:8], d_ps.data_ptr(), stream.cuda_stream)   # warm the batch-sized buffers
+        barrier()
+        qe0, qe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        qe0.record(stream)
+        poll_step()
+        qe1.record(stream)
+        barrier()
+        pb_ms = qe0.elapsed_time(qe1)
+
     # ---- the same step with the optional plane index (local planes fitted once at upload, looked up after)
     pi_ms, pi_upload = float("nan"), float("nan")
     if not args.no_plane_index:
@@ -307,10 +338,10 @@ def main():
         pi_ms = pe0.elapsed_time(pe1)
         pi_check = float(d_sums.cpu().numpy()[0][0])
 
-    tmax = torch.tensor([ms, e2e_s * 1e3, pi_ms], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([ms, e2e_s * 1e3, pi_ms, pb_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max, pi_ms_max = float(tmax[0]), float(tmax[1]), float(tmax[2])
+    ms_max, e2e_ms_max, pi_ms_max, pb_ms_max = float(tmax[0]), float(tmax[1]), float(tmax[2]), float(tmax[3])
     units_per_step = 1 if by_kf else world
     value = units_per_step * args.steps / (ms_max * 1e-3)
     e2e_value = units_per_step * args.steps / (e2e_ms_max * 1e-3)
@@ -351,6 +382,11 @@ def main():
             "stage_ms_per_launch": {k: round(v[0] / v[1], 4) for k, v in stats.items() if v[1] and k != "build"},
             "knn": {"queries_per_eval": knn_q_eval, "queries_per_s_whole_step": knn_q_eval * value,
                     "k2_pairs_per_s": (q3 / (k2_ms / max(k2_n, 1) * 1e-3)) if k2_ms > 0 else None},
+            "poll_batch": None if args.no_poll_batch else {
+                "candidates": args.poll_batch, "per_rank": pb_B, "ms": pb_ms_max,
+                "evals_per_s": args.poll_batch / (pb_ms_max * 1e-3), "unit": UNIT,
+                "note": "BASELINE configs[3]: one stl_eval_batch (BAError sums) + one stl_linearize_batch (cost, J^T r, J^T J on the "
+                        "frozen association) over the whole poll batch; device-timed, max over ranks"},
             "plane_index_option": None if args.no_plane_index else {
                 "value": units_per_step * args.steps / (pi_ms_max * 1e-3), "unit": UNIT, "ms_per_step": pi_ms_max / args.steps,
                 "upload_s": round(pi_upload, 3), "extra_hbm_bytes": 36 * int(n_pts),

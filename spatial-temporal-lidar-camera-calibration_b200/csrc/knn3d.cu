@@ -22,6 +22,9 @@ namespace stl {
 namespace {
 
 constexpr int kWarps = 8;
+#ifndef STL_KNN_MINB
+#define STL_KNN_MINB 6  // resident CTAs per SM the traversal kernels are compiled for (40 registers; measured best of 4/5/6)
+#endif
 constexpr int kPlaneThreads = 128;
 
 // the map point of correspondence `kp` in the LiDAR frame of candidate c (iba_global.cpp:231-234)
@@ -39,7 +42,7 @@ __device__ __forceinline__ void map_point_lidar(const DevPack &pk, const DevKf &
 }
 
 // K2a — grid: (candidate, keyframe, sub-block), one warp per query
-__global__ void __launch_bounds__(kWarps * 32, 4)
+__global__ void __launch_bounds__(kWarps * 32, STL_KNN_MINB)
 k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
     const int sub = wk.sub;
     const int j = blockIdx.x % sub;
@@ -158,7 +161,7 @@ k_knn3d(const DevPack pk, const int kf, const double *__restrict__ q, const int 
 
 // ---- plane index: local plane of every scan point, computed once per pack ---------------------
 // grid (blocks, nkf): one warp per point of the keyframe range; lists go to a scratch buffer
-__global__ void __launch_bounds__(kWarps * 32, 4)
+__global__ void __launch_bounds__(kWarps * 32, STL_KNN_MINB)
 k_index_knn(const DevPack pk, const int kf_begin, const DevParams pr, const long long first_pt, uint32_t *__restrict__ nb,
             int *__restrict__ nb_m, double *__restrict__ nb_last) {
     const DevKf K = pk.kf[kf_begin + blockIdx.y];

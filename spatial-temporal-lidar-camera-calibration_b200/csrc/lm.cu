@@ -26,6 +26,9 @@ namespace stl {
 namespace {
 
 constexpr int kWarps = 8;
+#ifndef STL_KNN_MINB
+#define STL_KNN_MINB 6  // resident CTAs per SM the traversal kernels are compiled for (40 registers; measured best of 4/5/6)
+#endif
 constexpr int kAssocSub = 8;
 constexpr int kLinVals = 41;  // cost, g[7], H upper 28, n2d, npt, npl, nres, ngpr
 constexpr int kGprWarps = 3;
@@ -54,7 +57,7 @@ __device__ __forceinline__ void lm_map_point(const DevPack &pk, const DevKf &K, 
 // The reference searches for every correspondence and only afterwards drops those without a map
 // point (:213) or without a covisible observation (:259); neither test depends on the search, so
 // they come first here.
-__global__ void __launch_bounds__(kWarps * 32, 4)
+__global__ void __launch_bounds__(kWarps * 32, STL_KNN_MINB)
 k_lm_knn_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
     const int j = blockIdx.x % kAssocSub, f = blockIdx.x / kAssocSub;
     int nq;
@@ -128,7 +131,7 @@ k_lm_plane_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
 
 // L3: map point -> LiDAR frame with the association extrinsic, 1-NN gate, neighbourhood of that point
 // (iba_local.cpp:283-295)
-__global__ void __launch_bounds__(kWarps * 32, 4)
+__global__ void __launch_bounds__(kWarps * 32, STL_KNN_MINB)
 k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
     const int j = blockIdx.x % kAssocSub, f = blockIdx.x / kAssocSub;
     int nq;
