@@ -110,7 +110,7 @@ void free_work(stl_ctx *c) {
     DevWork &w = c->wk;
     dfree(w.cand); dfree(w.corr_kp); dfree(w.corr_pt); dfree(w.corr_sp); dfree(w.q_corr); dfree(w.n_corr); dfree(w.n_q);
     dfree(w.k1_match);
-    dfree(w.frame); dfree(w.align); dfree(w.nn_pos); dfree(w.nb); dfree(w.nb_m); dfree(w.nb_last); dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn); dfree(w.dbg_stats);
+    dfree(w.frame); dfree(w.align); dfree(w.nn_pos); dfree(w.nb); dfree(w.nbx); dfree(w.nb_m); dfree(w.nb_last); dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn); dfree(w.dbg_stats);
     dfree(w.overflow); dfree(w.k1_clk);
     w = DevWork();
     c->wk_cap = 0;
@@ -171,8 +171,8 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
     if (ctx->wk_cap == 0) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        const size_t per_cand = (size_t)pk.n_kp_total * 16 + (size_t)pk.n_mp_total * (4 * kMaxK + 16) + (size_t)pk.n_kf * (sizeof(FrameRec) + 4 * sizeof(AlignRec) + 8 + sizeof(ulonglong2) * 8192) + sizeof(DevCand);
-        size_t budget = std::min<size_t>((size_t)4 << 30, free_b / 4);
+        const size_t per_cand = (size_t)pk.n_kp_total * 16 + (size_t)pk.n_mp_total * (20 * kMaxK + 16) + (size_t)pk.n_kf * (sizeof(FrameRec) + 4 * sizeof(AlignRec) + 8 + sizeof(ulonglong2) * 8192) + sizeof(DevCand);
+        size_t budget = std::min<size_t>((size_t)12 << 30, free_b / 4);
         int cap = (int)std::max<size_t>(1, std::min<size_t>(budget / std::max<size_t>(per_cand, 1), 256));
         if (const char *e = getenv("STL_MAX_CHUNK")) cap = std::max(1, std::min(cap, atoi(e)));  // tests: force the multi-chunk path
         DevWork &w = ctx->wk;
@@ -186,7 +186,7 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
         CK(cudaMalloc(&w.frame, sizeof(FrameRec) * nf)); CK(cudaMalloc(&w.align, sizeof(AlignRec) * nf * w.sub));
         {
             const size_t nm = (size_t)std::max<long long>(pk.n_mp_total, 1) * cap;
-            CK(cudaMalloc(&w.nn_pos, 4 * nm)); CK(cudaMalloc(&w.nb, 4 * nm * kMaxK)); CK(cudaMalloc(&w.nb_m, 4 * nm)); CK(cudaMalloc(&w.nb_last, 8 * nm));
+            CK(cudaMalloc(&w.nn_pos, 4 * nm)); CK(cudaMalloc(&w.nb, 4 * nm * kMaxK)); CK(cudaMalloc(&w.nbx, sizeof(float4) * nm * kMaxK)); w.nbx_stride = (long long)nm; CK(cudaMalloc(&w.nb_m, 4 * nm)); CK(cudaMalloc(&w.nb_last, 8 * nm));
         }
         if (getenv("STL_K1_CLK")) { CK(cudaMalloc(&w.k1_clk, 64 * nf)); CK(cudaMemset(w.k1_clk, 0, 64 * nf)); }
         CK(cudaMalloc(&w.overflow, 4));

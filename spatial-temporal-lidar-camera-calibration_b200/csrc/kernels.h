@@ -48,6 +48,8 @@ struct DevWork {
     // neighbour lists of the 3-D queries, slot = b * n_mp_total + mp_off[f] + qi
     uint32_t *nn_pos = nullptr;   // [Bc][n_mp_total] sorted position of the 1-NN
     uint32_t *nb = nullptr;       // [Bc][n_mp_total][32] sorted positions of the k-NN, distance order
+    float4 *nbx = nullptr;        // [32][Bc * n_mp_total] their coordinates, transposed (plane kernels read them coalesced)
+    long long nbx_stride = 0;
     int *nb_m = nullptr;          // [Bc][n_mp_total] neighbours kept (d2 < radius^2)
     double *nb_last = nullptr;    // [Bc][n_mp_total] d2 of the last kept neighbour
     // optional per-query debug (allocated on demand, Bc_dbg = 1)

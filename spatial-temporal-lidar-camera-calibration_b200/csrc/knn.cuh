@@ -252,8 +252,36 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
 // pointcloud.h:126-158), closed-form smallest eigenvector, regression error.
 struct PlaneOut { V3 n; double reg; int m; bool gates_ok; };
 
-__device__ __forceinline__ PlaneOut plane_thread(const ScanView &S, const uint32_t *__restrict__ nb, int m, double last, double cx,
-                                                 double cy, double cz, const DevParams &pr, const bool stable = false) {
+// where the coordinates of neighbour j come from: gathered through the position list, or read from
+// the transposed float4 rows the traversal kernels write (element (j, slot) at base[j * stride]:
+// consecutive threads read consecutive slots, i.e. coalesced 16 B loads instead of three gathers)
+struct NbGather {
+    const ScanView &S;
+    const uint32_t *__restrict__ nb;
+    __device__ __forceinline__ void get(int j, double &x, double &y, double &z) const {
+        const uint32_t p = nb[j];
+        x = (double)S.px[p]; y = (double)S.py[p]; z = (double)S.pz[p];
+    }
+};
+struct NbCoords {
+    const float4 *__restrict__ base;
+    long long stride;
+    __device__ __forceinline__ void get(int j, double &x, double &y, double &z) const {
+        const float4 v = base[(long long)j * stride];
+        x = (double)v.x; y = (double)v.y; z = (double)v.z;
+    }
+};
+// what a traversal warp stores for lane j of slot `slot`
+__device__ __forceinline__ void store_nb_coords(float4 *__restrict__ nbx, long long stride, long long slot, const ScanView &S, int lane,
+                                                int count, uint32_t kpos) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < count) v = make_float4(S.px[kpos], S.py[kpos], S.pz[kpos], __uint_as_float(kpos));
+    nbx[(long long)lane * stride + slot] = v;
+}
+
+template <class Src>
+__device__ __forceinline__ PlaneOut plane_fit(const Src &src, int m, double last, double cx, double cy, double cz, const DevParams &pr,
+                                              const bool stable = false) {
     PlaneOut out;
     out.m = m;
     out.n = {0.0, 0.0, 0.0};
@@ -267,8 +295,8 @@ __device__ __forceinline__ PlaneOut plane_thread(const ScanView &S, const uint32
     out.gates_ok = true;
     double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0;
     for (int j = 0; j < m; ++j) {
-        const uint32_t p = nb[j];
-        const double x = (double)S.px[p], y = (double)S.py[p], z = (double)S.pz[p];
+        double x, y, z;
+        src.get(j, x, y, z);
         c0 += x; c1 += y; c2 += z;
         c3 += x * x; c4 += x * y; c5 += x * z;
         c6 += y * y; c7 += y * z; c8 += z * z;
@@ -279,8 +307,9 @@ __device__ __forceinline__ PlaneOut plane_thread(const ScanView &S, const uint32
     const V3 n = normalized(smallest_eigvec(cov));
     double reg = 0;
     for (int j = 0; j < m; ++j) {
-        const uint32_t p = nb[j];
-        const V3 d = {(double)S.px[p] - cx, (double)S.py[p] - cy, (double)S.pz[p] - cz};
+        double x, y, z;
+        src.get(j, x, y, z);
+        const V3 d = {x - cx, y - cy, z - cz};
         reg += fabs(dot(d, n));
     }
     out.n = n;
@@ -291,6 +320,11 @@ __device__ __forceinline__ PlaneOut plane_thread(const ScanView &S, const uint32
     return out;
 }
 
+
+__device__ __forceinline__ PlaneOut plane_thread(const ScanView &S, const uint32_t *__restrict__ nb, int m, double last, double cx,
+                                                 double cy, double cz, const DevParams &pr, const bool stable = false) {
+    return plane_fit(NbGather{S, nb}, m, last, cx, cy, cz, pr, stable);
+}
 
 // plane of scan point `pos` from the precomputed index (same PlaneOut as plane_thread)
 __device__ __forceinline__ PlaneOut plane_lookup(const DevPack &pk, const DevKf &K, uint32_t pos) {

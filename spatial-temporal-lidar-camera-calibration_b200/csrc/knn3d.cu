@@ -26,6 +26,9 @@ constexpr int kWarps = 8;
 #define STL_KNN_MINB 6  // resident CTAs per SM the traversal kernels are compiled for (40 registers; measured best of 4/5/6)
 #endif
 constexpr int kPlaneThreads = 128;
+#ifndef STL_PLANE_MINB
+#define STL_PLANE_MINB 4
+#endif
 
 // the map point of correspondence `kp` in the LiDAR frame of candidate c (iba_global.cpp:231-234)
 __device__ __forceinline__ void map_point_lidar(const DevPack &pk, const DevKf &K, const DevCand &c, int f, uint32_t kp, double &qx,
@@ -68,16 +71,20 @@ k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
             SinkK kn(pr.k, pr.radius2);
             traverse(S, nx, ny, nz, kn, lane, (int)(nn.pos >> 5));
             wk.nb[(qbase + qi) * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
+            store_nb_coords(wk.nbx, wk.nbx_stride, qbase + qi, S, lane, kn.count, kn.kpos);
             const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
             if (lane == 0) { wk.nb_m[qbase + qi] = kn.count; wk.nb_last[qbase + qi] = last; }
         }
     }
 }
 
-// K2b — grid: (candidate, keyframe), one thread per query
-__global__ void __launch_bounds__(kPlaneThreads)
+// K2b — grid: (candidate, keyframe, sub-block), one thread per query
+__global__ void __launch_bounds__(kPlaneThreads, STL_PLANE_MINB)
 k_plane_dist(const DevPack pk, const DevWork wk, const DevParams pr, const int B, const int debug) {
-    const int f = blockIdx.x / B, b = blockIdx.x - f * B;
+    const int sub = wk.sub;
+    const int j = blockIdx.x % sub;
+    const int bf = blockIdx.x / sub;
+    const int f = bf / B, b = bf - f * B;
     const long long rec = (long long)b * pk.n_kf + f;
     const int nq = wk.n_q[rec];
     double s3d = 0, v3d = 0, c3d = 0, vpl = 0, vpt = 0;
@@ -87,7 +94,7 @@ k_plane_dist(const DevPack pk, const DevWork wk, const DevParams pr, const int B
         const ScanView S = make_view(pk, K);
         const long long cbase = (long long)b * pk.n_kp_total + K.kp_off;
         const long long qbase = (long long)b * pk.n_mp_total + K.mp_off;
-        for (int qi = threadIdx.x; qi < nq; qi += kPlaneThreads) {
+        for (int qi = j * kPlaneThreads + threadIdx.x; qi < nq; qi += sub * kPlaneThreads) {
             const uint32_t kp = wk.corr_kp[cbase + wk.q_corr[cbase + qi]];
             double qx, qy, qz;
             map_point_lidar(pk, K, c, f, kp, qx, qy, qz);
@@ -98,7 +105,7 @@ k_plane_dist(const DevPack pk, const DevWork wk, const DevParams pr, const int B
             int is_plane = 0, m = 0;
             if (pr.use_plane) {
                 const PlaneOut po = pr.plane_index ? plane_lookup(pk, K, np)
-                                                   : plane_thread(S, wk.nb + (qbase + qi) * kMaxK, wk.nb_m[qbase + qi], wk.nb_last[qbase + qi], nx, ny, nz, pr, pr.variant == 1);
+                                                   : plane_fit(NbCoords{wk.nbx + qbase + qi, wk.nbx_stride}, wk.nb_m[qbase + qi], wk.nb_last[qbase + qi], nx, ny, nz, pr, pr.variant == 1);
                 m = po.m;
                 if (po.gates_ok && !(po.reg > pr.reg_thr)) {  // iba_global.cpp:147
                     is_plane = 1;
@@ -136,8 +143,7 @@ k_plane_dist(const DevPack pk, const DevWork wk, const DevParams pr, const int B
     if (threadIdx.x == 0) {
         AlignRec r = {0, 0, 0, 0, 0};
         for (int w = 0; w < kPlaneThreads / 32; ++w) { r.s3d += red[0][w]; r.v3d += red[1][w]; r.c3d += red[2][w]; r.vpl += red[3][w]; r.vpt += red[4][w]; }
-        wk.align[rec * wk.sub] = r;
-        for (int s = 1; s < wk.sub; ++s) wk.align[rec * wk.sub + s] = AlignRec{0, 0, 0, 0, 0};
+        wk.align[rec * sub + j] = r;
     }
 }
 
@@ -224,7 +230,7 @@ cudaError_t launch_align3d(const DevPack &pk, const DevWork &wk, const DevParams
     k_nn_knn<<<(unsigned)(pk.n_kf * B * wk.sub), kWarps * 32, 0, st>>>(pk, wk, pr, B);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    k_plane_dist<<<(unsigned)(pk.n_kf * B), kPlaneThreads, 0, st>>>(pk, wk, pr, B, debug);
+    k_plane_dist<<<(unsigned)(pk.n_kf * B * wk.sub), kPlaneThreads, 0, st>>>(pk, wk, pr, B, debug);
     return cudaGetLastError();
 }
 

@@ -30,6 +30,7 @@ constexpr int kWarps = 8;
 #define STL_KNN_MINB 6  // resident CTAs per SM the traversal kernels are compiled for (40 registers; measured best of 4/5/6)
 #endif
 constexpr int kAssocSub = 8;
+constexpr int kPlaneSub = 4;  // CTAs of 128 threads per keyframe in the thread-per-query plane kernels
 constexpr int kLinVals = 41;  // cost, g[7], H upper 28, n2d, npt, npl, nres, ngpr
 constexpr int kGprWarps = 3;
 constexpr int kLinThreads = 128;
@@ -84,6 +85,7 @@ k_lm_knn_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
         SinkK kn(pr.k, pr.radius2);
         traverse(S, (double)S.px[sp], (double)S.py[sp], (double)S.pz[sp], kn, lane, (int)(sp >> 5));
         wk.nb[slot * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
+        store_nb_coords(wk.nbx, wk.nbx_stride, slot, S, lane, kn.count, kn.kpos);
         const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
         if (lane == 0) { wk.nb_m[slot] = kn.count; wk.nb_last[slot] = last; }
     }
@@ -92,12 +94,12 @@ k_lm_knn_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
 // L2: plane at the scan point (iba_local.cpp:218-231) -> 3-D/2-D block; decides whether the 3-D search runs
 __global__ void __launch_bounds__(128)
 k_lm_plane_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
-    const int f = blockIdx.x;
+    const int j = blockIdx.x % kPlaneSub, f = blockIdx.x / kPlaneSub;
     int nq;
     if (!lm_frame_active(wk, pr, f, nq)) return;
     const DevKf K = pk.kf[f];
     const ScanView S = make_view(pk, K);
-    for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) {
+    for (int qi = j * blockDim.x + threadIdx.x; qi < nq; qi += kPlaneSub * blockDim.x) {
         const long long slot = K.mp_off + qi;
         const int m = wk.nb_m[slot];
         lm.stage[slot] = 0;
@@ -106,7 +108,7 @@ k_lm_plane_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
         const uint32_t kp = wk.corr_kp[K.kp_off + ci], sp = wk.corr_sp[K.kp_off + ci];
         const double cx = (double)S.px[sp], cy = (double)S.py[sp], cz = (double)S.pz[sp];
         const PlaneOut po = (pr.plane_index && !pr.use_gpr) ? plane_lookup(pk, K, sp)
-                                                             : plane_thread(S, wk.nb + slot * kMaxK, m, wk.nb_last[slot], cx, cy, cz, pr);
+                                                             : plane_fit(NbCoords{wk.nbx + slot, wk.nbx_stride}, m, wk.nb_last[slot], cx, cy, cz, pr);
         if (!po.gates_ok) continue;  // m < min_pts || d2[m-1] < min_diff^2 (pointcloud.h:754)
         const long long cs = K.kp_off + ci;  // block slot = correspondence slot
         lm.slot_kf[cs] = f;
@@ -166,6 +168,7 @@ k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
         SinkK kn(pr.k, pr.radius2);
         traverse(S, (double)S.px[nn.pos], (double)S.py[nn.pos], (double)S.pz[nn.pos], kn, lane, (int)(nn.pos >> 5));
         lm.nbb[slot * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
+        store_nb_coords(lm.nbbx, lm.nbbx_stride, slot, S, lane, kn.count, kn.kpos);
         const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
         if (lane == 0) { lm.nbb_m[slot] = kn.count; lm.nbb_last[slot] = last; }
     }
@@ -174,12 +177,12 @@ k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
 // L4: ComputeLocalNormalSingleThre at the map point's neighbour (pointcloud.h:699-717,651-666) -> 3-D/3-D block
 __global__ void __launch_bounds__(128)
 k_lm_plane_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
-    const int f = blockIdx.x;
+    const int j = blockIdx.x % kPlaneSub, f = blockIdx.x / kPlaneSub;
     int nq;
     if (!lm_frame_active(wk, pr, f, nq)) return;
     const DevKf K = pk.kf[f];
     const ScanView S = make_view(pk, K);
-    for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) {
+    for (int qi = j * blockDim.x + threadIdx.x; qi < nq; qi += kPlaneSub * blockDim.x) {
         const long long slot = K.mp_off + qi;
         if (lm.stage[slot] != 1) continue;
         const uint32_t np = lm.nnb_pos[slot];
@@ -196,7 +199,7 @@ k_lm_plane_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
             gates_ok = true; n3[0] = pa[0]; n3[1] = pa[1]; n3[2] = pa[2];
             state = pa[3] < pr.reg_thr;
         } else {
-            const PlaneOut p2 = m == -3 ? plane_lookup(pk, K, np) : plane_thread(S, lm.nbb + slot * kMaxK, m, lm.nbb_last[slot], nx, ny, nz, pr);
+            const PlaneOut p2 = m == -3 ? plane_lookup(pk, K, np) : plane_fit(NbCoords{lm.nbbx + slot, lm.nbbx_stride}, m, lm.nbb_last[slot], nx, ny, nz, pr);
             gates_ok = p2.gates_ok; n3[0] = p2.n.x; n3[1] = p2.n.y; n3[2] = p2.n.z;
             state = p2.gates_ok && p2.reg < pr.reg_thr;
         }
@@ -580,7 +583,7 @@ template <class T> void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
 void lm_free(LmState &lm) {
     dfree(lm.slot_kf); dfree(lm.slot_kp); dfree(lm.flag2d); dfree(lm.type3d); dfree(lm.flag3d); dfree(lm.geo2d); dfree(lm.geo3d);
     dfree(lm.flagG); dfree(lm.idxG); dfree(lm.slot_mp); dfree(lm.gpr_nb); dfree(lm.gpr_m);
-    dfree(lm.stage); dfree(lm.plane_a); dfree(lm.nnb_pos); dfree(lm.nbb); dfree(lm.nbb_m); dfree(lm.nbb_last);
+    dfree(lm.stage); dfree(lm.plane_a); dfree(lm.nnb_pos); dfree(lm.nbb); dfree(lm.nbbx); dfree(lm.nbb_m); dfree(lm.nbb_last);
     dfree(lm.idx2d); dfree(lm.idx3d); dfree(lm.d_counts); dfree(lm.d_tmp); dfree(lm.partial); dfree(lm.d_cand);
     if (lm.h_cand) cudaFreeHost(lm.h_cand);
     if (lm.h2d_done) cudaEventDestroy(lm.h2d_done);
@@ -601,7 +604,7 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
         TRY(cudaMalloc(&lm.d_counts, 16));
         const long long nm = pk.n_mp_total > 0 ? pk.n_mp_total : 1;
         TRY(cudaMalloc(&lm.stage, nm)); TRY(cudaMalloc(&lm.plane_a, 32 * nm)); TRY(cudaMalloc(&lm.nnb_pos, 4 * nm));
-        TRY(cudaMalloc(&lm.nbb, 4 * nm * kMaxK)); TRY(cudaMalloc(&lm.nbb_m, 4 * nm)); TRY(cudaMalloc(&lm.nbb_last, 8 * nm));
+        TRY(cudaMalloc(&lm.nbb, 4 * nm * kMaxK)); TRY(cudaMalloc(&lm.nbbx, sizeof(float4) * nm * kMaxK)); lm.nbbx_stride = (long long)nm; TRY(cudaMalloc(&lm.nbb_m, 4 * nm)); TRY(cudaMalloc(&lm.nbb_last, 8 * nm));
         TRY(cudaMalloc(&lm.flagG, ns)); TRY(cudaMalloc(&lm.idxG, 4 * ns)); TRY(cudaMalloc(&lm.slot_mp, 4 * ns));
         if (pr.use_gpr) { TRY(cudaMalloc(&lm.gpr_nb, 4 * nm * kMaxK)); TRY(cudaMalloc(&lm.gpr_m, 4 * nm)); }
         size_t tb = 0;
@@ -617,9 +620,9 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
     TRY(cudaMemsetAsync(lm.flagG, 0, ns, st));
     TRY(cudaMemsetAsync(lm.d_counts, 0, 16, st));
     k_lm_knn_a<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
-    k_lm_plane_a<<<(unsigned)pk.n_kf, 128, 0, st>>>(pk, wk, pr, lm);
+    k_lm_plane_a<<<(unsigned)(pk.n_kf * kPlaneSub), 128, 0, st>>>(pk, wk, pr, lm);
     k_lm_knn_b<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
-    k_lm_plane_b<<<(unsigned)pk.n_kf, 128, 0, st>>>(pk, wk, pr, lm);
+    k_lm_plane_b<<<(unsigned)(pk.n_kf * kPlaneSub), 128, 0, st>>>(pk, wk, pr, lm);
     TRY(cudaGetLastError());
     cub::CountingInputIterator<int> it(0);
     size_t tb = lm.tmp_bytes;

@@ -24,6 +24,8 @@ struct LmState {
     double *plane_a = nullptr;    // [n_mp][4] normal + regression error at the scan point
     uint32_t *nnb_pos = nullptr;  // [n_mp] 1-NN of the map point (0xffffffff = beyond max_3d_dist)
     uint32_t *nbb = nullptr;      // [n_mp][32] neighbour list of that point
+    float4 *nbbx = nullptr;       // [32][n_mp] coordinates of those neighbours, transposed
+    long long nbbx_stride = 0;
     int *nbb_m = nullptr;         // [n_mp] (-2 = same point as the associated one)
     double *nbb_last = nullptr;
     int *idx2d = nullptr, *idx3d = nullptr;  // [n_slots] dense slot lists
