@@ -261,10 +261,94 @@ __global__ void k_inner_aabb(const DevKf *__restrict__ kf, int kf_begin, int lev
     if (lane == 0) { node_lo[out_base + node] = lo; node_hi[out_base + node] = hi; }
 }
 
+// ---- leaf adjacency ---------------------------------------------------------------------------
+// For every leaf box A: the (at most 32) nearest leaves whose box lies within r of A (conservative
+// float32 lower bound of the box-to-box distance), nearest first — one per lane of the warp that later
+// scans them — plus the COVERAGE of the row: the squared box distance of the nearest leaf that did not
+// fit (+inf when every leaf within r is listed).  A search around a point of A whose answer lies closer
+// than the coverage only has to look at the listed leaves, so the 3-level descent is replaced by one box
+// test per lane.  Rows of empty leaves (or with > 256 leaves in range) stay empty: coverage -1.
+constexpr int kAdjCand = 256;
+
+__device__ __forceinline__ float boxbox_lb(float4 alo, float4 ahi, float4 blo, float4 bhi) {
+    const float dx = fmaxf(fmaxf(__fsub_rd(blo.x, ahi.x), __fsub_rd(alo.x, bhi.x)), 0.f);
+    const float dy = fmaxf(fmaxf(__fsub_rd(blo.y, ahi.y), __fsub_rd(alo.y, bhi.y)), 0.f);
+    const float dz = fmaxf(fmaxf(__fsub_rd(blo.z, ahi.z), __fsub_rd(alo.z, bhi.z)), 0.f);
+    const float s = __fadd_rd(__fadd_rd(__fmul_rd(dx, dx), __fmul_rd(dy, dy)), __fmul_rd(dz, dz));
+    return __fmul_rd(s, 0.99999976f);
+}
+
+__device__ __forceinline__ unsigned long long warp_min64(unsigned long long v) {
+    for (int o = 16; o; o >>= 1) {
+        const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w < v ? w : v;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+k_leaf_adj(const DevKf *__restrict__ kf, int kf_begin, const float4 *__restrict__ node_lo, const float4 *__restrict__ node_hi,
+           uint16_t *__restrict__ adj, float *__restrict__ adj_cov, const float r2, const float min_cov) {
+    __shared__ unsigned long long cand[8][kAdjCand];
+    constexpr unsigned long long kNone = 0xffffffffffffffffull;
+    const DevKf K = kf[kf_begin + blockIdx.y];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int leaf = blockIdx.x * 8 + warp;
+    if (leaf >= K.n0) return;
+    const float4 *lo0 = node_lo + K.node_off, *hi0 = node_hi + K.node_off;
+    const float4 *lo1 = lo0 + K.n0, *hi1 = hi0 + K.n0, *lo2 = lo1 + K.n1, *hi2 = hi1 + K.n1;
+    const float4 alo = lo0[leaf], ahi = hi0[leaf];
+    int cnt = 0;
+    bool over = !(alo.x <= ahi.x) || K.n0 > 65535;
+    if (!over) {
+        unsigned m2 = __ballot_sync(0xffffffffu, boxbox_lb(alo, ahi, lo2[lane], hi2[lane]) <= r2);
+        while (m2 && !over) {
+            const int s2 = __ffs(m2) - 1;
+            m2 &= m2 - 1;
+            unsigned m1 = __ballot_sync(0xffffffffu, boxbox_lb(alo, ahi, lo1[s2 * 32 + lane], hi1[s2 * 32 + lane]) <= r2);
+            while (m1 && !over) {
+                const int s1 = __ffs(m1) - 1;
+                m1 &= m1 - 1;
+                const int n0i = (s2 * 32 + s1) * 32 + lane;
+                const float lb = boxbox_lb(alo, ahi, lo0[n0i], hi0[n0i]);
+                const unsigned m0 = __ballot_sync(0xffffffffu, lb <= r2);
+                const int c = __popc(m0);
+                if (cnt + c > kAdjCand) { over = true; break; }
+                if ((m0 >> lane) & 1u) cand[warp][cnt + __popc(m0 & ((1u << lane) - 1))] = ((unsigned long long)__float_as_uint(lb) << 32) | (unsigned)n0i;
+                cnt += c;
+            }
+        }
+    }
+    __syncwarp();
+    // the 32 smallest (distance, leaf) keys by repeated extraction; lane t keeps the t-th
+    unsigned long long mine = kNone;
+    float cov = -1.f;
+    if (!over) {
+        for (int t = 0; t <= 32; ++t) {
+            unsigned long long best = kNone;
+            for (int i = lane; i < cnt; i += 32) best = cand[warp][i] < best ? cand[warp][i] : best;
+            best = warp_min64(best);
+            if (t == 32) {  // the nearest leaf left out bounds what the row covers
+                cov = best == kNone ? __int_as_float(0x7f800000) : __uint_as_float((unsigned)(best >> 32));
+                break;
+            }
+            if (best == kNone) { cov = __int_as_float(0x7f800000); break; }
+            if (lane == t) mine = best;
+            for (int i = lane; i < cnt; i += 32)
+                if (cand[warp][i] == best) cand[warp][i] = kNone;
+            __syncwarp();
+        }
+    }
+    // a truncated row that covers less than a third of the radius would mostly be scanned in vain
+    if (cov >= 0.f && cov < min_cov) { cov = -1.f; mine = kNone; }
+    adj[(K.node_off + leaf) * 32 + lane] = mine == kNone ? (uint16_t)0xffffu : (uint16_t)(mine & 0xffffu);
+    if (lane == 0) adj_cov[K.node_off + leaf] = cov;
+}
+
 }  // namespace
 
 cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int nkf, int kf_begin, const DevKf *h_kf, DevPack &pack,
-                             cudaStream_t st) {
+                             float adj_r2, cudaStream_t st) {
     const long long n = h_raw_off[nkf] - h_raw_off[0];
     cudaError_t err = cudaSuccess;
     long long *d_off = nullptr;
@@ -318,6 +402,9 @@ cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int
         k_leaf_aabb<<<dim3((max_n0 + 7) / 8, nkf), 256, 0, st>>>(pack.kf, kf_begin, pack.px, pack.py, pack.pz, pack.node_lo, pack.node_hi);
         k_inner_aabb<<<dim3((max_n1 + 7) / 8, nkf), 256, 0, st>>>(pack.kf, kf_begin, 1, pack.node_lo, pack.node_hi);
         k_inner_aabb<<<dim3(4, nkf), 256, 0, st>>>(pack.kf, kf_begin, 2, pack.node_lo, pack.node_hi);
+        if (pack.adj && adj_r2 > 0.f)
+            k_leaf_adj<<<dim3((max_n0 + 7) / 8, nkf), 256, 0, st>>>(pack.kf, kf_begin, pack.node_lo, pack.node_hi, pack.adj, pack.adj_cov, adj_r2,
+                                                                    adj_r2 * (getenv("STL_ADJ_TRUNC") ? (float)atof(getenv("STL_ADJ_TRUNC")) : 1.f / 9.f));
     }
     STL_TRY(cudaGetLastError());
     STL_TRY(cudaStreamSynchronize(st));

@@ -31,6 +31,7 @@ struct stl_ctx {
     std::mutex mu;
     std::string err;
     bool has_pack = false;
+    float adj_r2 = 0.f;  // squared radius of the leaf adjacency lists, rounded up (0: none)
     DevPack pk;
     std::vector<DevKf> h_kf;
     int max_kp = 0, max_bm_words = 0;
@@ -99,7 +100,7 @@ template <class T> void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
 
 void free_pack(stl_ctx *c) {
     DevPack &p = c->pk;
-    dfree(p.kf); dfree(p.px); dfree(p.py); dfree(p.pz); dfree(p.orig); dfree(p.node_lo); dfree(p.node_hi);
+    dfree(p.kf); dfree(p.px); dfree(p.py); dfree(p.pz); dfree(p.orig); dfree(p.node_lo); dfree(p.node_hi); dfree(p.adj); dfree(p.adj_cov);
     dfree(p.pl_rec); dfree(p.pl_m);
     dfree(p.bitmap); dfree(p.grid_start); dfree(p.grid_kp); dfree(p.kp_xy); dfree(p.kp_xyd); dfree(p.kp_mp); dfree(p.Tcw);
     dfree(p.relpose); dfree(p.covis_valid); dfree(p.covis_uv); dfree(p.he_Tc); dfree(p.he_Tl);
@@ -137,6 +138,12 @@ void set_dev_params(stl_ctx *c) {
     d.use_plane = p.use_plane;
     d.use_gpr = p.use_gpr; d.plane_index = p.plane_index;
     d.variant = p.variant; d.min_diff = p.min_diff_dist;
+    // leaf adjacency lists cover norm_radius (the k-NN searches never look farther); STL_NO_ADJ=1 keeps the plain descent
+    c->adj_r2 = 0.f; d.adj_r = 0.f;
+    if (!getenv("STL_NO_ADJ") && p.use_plane && p.norm_radius > 0 && p.norm_radius < 1e3) {
+        c->adj_r2 = nextafterf((float)d.radius2, INFINITY);
+        d.adj_r = nextafterf((float)sqrt(d.radius2), 0.f);
+    }
     d.gpr_sigma = p.gpr_sigma; d.gpr_l = p.gpr_l; d.gpr_noise = p.gpr_sigma_noise;
 }
 
@@ -463,6 +470,7 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     CK(cudaMalloc(&pk.kf, sizeof(DevKf) * F));
     CK(cudaMalloc(&pk.px, 4 * npt)); CK(cudaMalloc(&pk.py, 4 * npt)); CK(cudaMalloc(&pk.pz, 4 * npt)); CK(cudaMalloc(&pk.orig, 4 * npt));
     CK(cudaMalloc(&pk.node_lo, sizeof(float4) * nodes)); CK(cudaMalloc(&pk.node_hi, sizeof(float4) * nodes));
+    if (ctx->adj_r2 > 0.f) { CK(cudaMalloc(&pk.adj, sizeof(uint16_t) * 32 * (size_t)nodes)); CK(cudaMalloc(&pk.adj_cov, sizeof(float) * (size_t)nodes)); }
     CK(cudaMalloc(&pk.bitmap, 4 * (size_t)bmw)); CK(cudaMalloc(&pk.grid_start, 4 * (size_t)gcells)); CK(cudaMalloc(&pk.grid_kp, 4 * nkk));
     CK(cudaMalloc(&pk.kp_xy, sizeof(float2) * nkk)); CK(cudaMalloc(&pk.kp_mp, 12 * nkk));
     CK(cudaMalloc(&pk.Tcw, 48 * (size_t)F)); CK(cudaMalloc(&pk.relpose, 48 * (size_t)std::max(F * C, 1)));
@@ -504,13 +512,35 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
             if (n > 0) CK(cudaMemcpyAsync(d_raw, p->scan_xyz + p->scan_offset[f0] * 3, 12 * (size_t)n, cudaMemcpyHostToDevice, st));
             std::vector<long long> off(f1 - f0 + 1);
             for (int f = f0; f <= f1; ++f) off[f - f0] = p->scan_offset[f];
-            cudaError_t e = build_scan_index(d_raw, off.data(), f1 - f0, f0, hk.data(), pk, st);
+            cudaError_t e = build_scan_index(d_raw, off.data(), f1 - f0, f0, hk.data(), pk, ctx->adj_r2, st);
             if (e != cudaSuccess) { dfree(d_raw); return fail(ctx, STL_ERR_CUDA, "index build: %s", cudaGetErrorString(e)); }
             f0 = f1;
         }
         dfree(d_raw);
     }
     CK(cudaMemcpy(hk.data(), pk.kf, sizeof(DevKf) * F, cudaMemcpyDeviceToHost));  // pmax filled by the build
+    if (pk.adj && getenv("STL_DEBUG_STATS")) {  // how many real leaves got no adjacency row (> 32 neighbours)?
+        long long real = 0, empty = 0, entries = 0, partial = 0;
+        double cov_sum = 0;
+        std::vector<uint16_t> row;
+        std::vector<float> cov;
+        for (int f = 0; f < F; f += std::max(1, F / 16)) {
+            const int nl = (hk[f].n_pts + kLeaf - 1) / kLeaf;
+            row.resize((size_t)nl * 32);
+            CK(cudaMemcpy(row.data(), pk.adj + hk[f].node_off * 32, row.size() * 2, cudaMemcpyDeviceToHost));
+            cov.resize((size_t)nl);
+            CK(cudaMemcpy(cov.data(), pk.adj_cov + hk[f].node_off, cov.size() * 4, cudaMemcpyDeviceToHost));
+            for (int l = 0; l < nl; ++l) if (cov[l] >= 0 && cov[l] < 1e30f) { ++partial; cov_sum += std::sqrt((double)cov[l]); }
+            for (int l = 0; l < nl; ++l) {
+                int c = 0;
+                for (int t = 0; t < 32; ++t) c += row[(size_t)l * 32 + t] != 0xffffu;
+                ++real; empty += c == 0; entries += c;
+            }
+        }
+        fprintf(stderr, "[stl] leaf adjacency (sampled keyframes): %lld leaves, %.2f%% without a row, %.1f neighbours per row, %.1f%% truncated (mean coverage %.3f m)\n", real,
+                100.0 * empty / std::max<long long>(real, 1), (double)entries / std::max<long long>(real - empty, 1),
+                100.0 * partial / std::max<long long>(real, 1), cov_sum / std::max<long long>(partial, 1));
+    }
     if (ctx->params.plane_index) {
         CK(cudaMalloc(&pk.pl_rec, sizeof(PlaneRec) * npt));
         CK(cudaMalloc(&pk.pl_m, 4 * npt));

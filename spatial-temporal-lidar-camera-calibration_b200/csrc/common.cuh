@@ -74,6 +74,7 @@ struct DevParams {
     double w0, w1;
     int num_min_corr, k, min_pts, use_plane;
     int use_gpr, plane_index, variant;
+    float adj_r;      // radius the leaf adjacency lists cover, rounded down (0: no lists)
     double min_diff;  // un-squared (variant 1 compares norms)
     double gpr_sigma, gpr_l, gpr_noise;
 };

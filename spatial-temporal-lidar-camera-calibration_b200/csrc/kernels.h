@@ -16,6 +16,8 @@ struct DevPack {
     float *px = nullptr, *py = nullptr, *pz = nullptr;
     uint32_t *orig = nullptr;
     float4 *node_lo = nullptr, *node_hi = nullptr;
+    uint16_t *adj = nullptr;         // [n_nodes_total][32] leaf adjacency: the nearest leaves within adj_r of each leaf box (0xffff = none)
+    float *adj_cov = nullptr;        // [n_nodes_total] squared distance the row covers (+inf: all of adj_r; -1: no row)
     PlaneRec *pl_rec = nullptr;      // [n_pad_total] plane index (null unless params.plane_index)
     int *pl_m = nullptr;             // [n_pad_total] neighbours kept; negative (-(m+1)) when the gates failed
     uint32_t *bitmap = nullptr;
@@ -66,8 +68,9 @@ struct DevWork {
 
 // ---- index build (build.cu) ---------------------------------------------------
 // raw: [n][3] float32 device points of a chunk of keyframes; raw_off[nkf+1] host offsets.
+// adj_r2: squared radius of the leaf adjacency lists (<= 0: none are built)
 cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int nkf, int kf_begin, const DevKf *h_kf,
-                             DevPack &pack, cudaStream_t st);
+                             DevPack &pack, float adj_r2, cudaStream_t st);
 
 // plane index (knn3d.cu): k-NN + plane of every point of keyframes [kf_begin, kf_begin + nkf)
 cudaError_t build_plane_index(const DevPack &pk, const DevKf *h_kf, int kf_begin, int nkf, const DevParams &pr, cudaStream_t st);

@@ -26,6 +26,8 @@ struct ScanView {
     const float *px, *py, *pz;
     const uint32_t *orig;
     const float4 *lo, *hi;  // [n0 leaves][n1 level-1][32 level-2]
+    const uint16_t *adj;    // [n0][32] leaf adjacency rows (null: none)
+    const float *adj_cov;   // [n0] squared distance each row covers
     int n0, n1;
 };
 
@@ -34,6 +36,8 @@ __device__ __forceinline__ ScanView make_view(const DevPack &pk, const DevKf &K)
     v.px = pk.px + K.pt_off; v.py = pk.py + K.pt_off; v.pz = pk.pz + K.pt_off;
     v.orig = pk.orig + K.pt_off;
     v.lo = pk.node_lo + K.node_off; v.hi = pk.node_hi + K.node_off;
+    v.adj = pk.adj ? pk.adj + K.node_off * 32 : nullptr;
+    v.adj_cov = pk.adj ? pk.adj_cov + K.node_off : nullptr;
     v.n0 = K.n0; v.n1 = K.n1;
     return v;
 }
@@ -242,6 +246,66 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
             }
         }
     }
+}
+
+// ---- adjacency scan -----------------------------------------------------------------------
+// The nearest leaves around leaf `home` are listed in pk.adj (build.cu, nearest first, one per lane)
+// together with the squared distance `cov` the row covers: every point closer than sqrt(cov) to ANY
+// point of the home box lives in a listed leaf (cov = +inf: everything within adj_r does).  A search
+// whose answer provably lies inside the covered range replaces the 3-level descent by one box test
+// per lane.  Returns cov, or -1 when there is no row (the caller then runs the descent).
+template <class Sink>
+__device__ __forceinline__ float scan_adjacent(const ScanView &S, int home, double qx, double qy, double qz, Sink &sink, int lane) {
+    if (S.adj == nullptr) return -1.f;
+    const float cov = S.adj_cov[home];
+    if (cov < 0.f) return -1.f;
+    const unsigned id = S.adj[(long long)home * 32 + lane];
+    const QueryF qf = make_queryf(qx, qy, qz);
+    const float lb = id != 0xffffu ? box_lbf(qf, S.lo[id], S.hi[id]) : __int_as_float(0x7f800000);
+    const unsigned key = __float_as_uint(lb);
+    unsigned done = 0;
+    for (;;) {  // nearest box first: the bound tightens fastest
+        const bool c = !((done >> lane) & 1u) && sink.may_contain(lb);
+        const unsigned m = __reduce_min_sync(kFull, c ? key : 0xffffffffu);
+        if (m == 0xffffffffu) break;
+        const int s = __ffs(__ballot_sync(kFull, c && key == m)) - 1;
+        done |= 1u << s;
+        sink.visit(S, (int)__shfl_sync(kFull, id, s), qx, qy, qz, lane);
+    }
+    return cov;
+}
+
+// k-NN (radius-limited) around the scan point at sorted position `pos`.  The adjacency result is final
+// when the row covers the whole radius, or when the list is full and its worst distance lies strictly
+// inside the covered range (an unlisted point cannot even tie with it); otherwise start over with the descent.
+__device__ __forceinline__ void knn_around_point(const ScanView &S, uint32_t pos, SinkK &kn, int lane) {
+    const double x = (double)S.px[pos], y = (double)S.py[pos], z = (double)S.pz[pos];
+    const float cov = scan_adjacent(S, (int)(pos >> 5), x, y, z, kn, lane);
+    if (cov > 3.0e38f || (cov >= 0.f && kn.count == kn.k && kn.wdf < cov)) return;
+    if (cov >= 0.f) kn = SinkK(kn.k, kn.r2);
+    traverse(S, x, y, z, kn, lane, (int)(pos >> 5));
+}
+
+// 1-NN of an arbitrary query that is expected to lie near leaf `home` (the leaf of the scan point its
+// keypoint was associated with).  The adjacency scan is exact when nearest distance + distance from the
+// query to the home box stays inside the covered range (all bounds rounded to the safe side); otherwise
+// the descent finishes the search with the bound already found (re-visiting a leaf cannot change a
+// (d2, index) minimum).
+__device__ __forceinline__ void nn_near_leaf(const ScanView &S, float adj_r, int home, double qx, double qy, double qz, Sink1 &nn,
+                                             int lane) {
+    const float cov = scan_adjacent(S, home, qx, qy, qz, nn, lane);
+    if (cov >= 0.f && nn.pos != 0xffffffffu) {
+        const float4 lo = S.lo[home], hi = S.hi[home];
+        const float xl = __double2float_rd(qx), xh = __double2float_ru(qx), yl = __double2float_rd(qy), yh = __double2float_ru(qy);
+        const float zl = __double2float_rd(qz), zh = __double2float_ru(qz);
+        const float gx = fmaxf(fmaxf(__fsub_ru(lo.x, xl), __fsub_ru(xh, hi.x)), 0.f);
+        const float gy = fmaxf(fmaxf(__fsub_ru(lo.y, yl), __fsub_ru(yh, hi.y)), 0.f);
+        const float gz = fmaxf(fmaxf(__fsub_ru(lo.z, zl), __fsub_ru(zh, hi.z)), 0.f);
+        const float delta = __fsqrt_ru(__fadd_ru(__fadd_ru(__fmul_ru(gx, gx), __fmul_ru(gy, gy)), __fmul_ru(gz, gz)));
+        const float reach = __fadd_ru(__fsqrt_ru(nn.df), delta);
+        if (cov > 3.0e38f ? reach <= adj_r : reach < __fsqrt_rd(cov)) return;
+    }
+    traverse(S, qx, qy, qz, nn, lane);
 }
 
 // ---- local plane around a scan point (one THREAD per neighbourhood) ---------------------

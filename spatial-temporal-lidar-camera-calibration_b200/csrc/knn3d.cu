@@ -60,16 +60,16 @@ k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
     const long long cbase = (long long)b * pk.n_kp_total + K.kp_off;
     const long long qbase = (long long)b * pk.n_mp_total + K.mp_off;
     for (int qi = j * kWarps + warp; qi < nq; qi += sub * kWarps) {
-        const uint32_t kp = wk.corr_kp[cbase + wk.q_corr[cbase + qi]];
+        const uint32_t ci = wk.q_corr[cbase + qi];
+        const uint32_t kp = wk.corr_kp[cbase + ci];
         double qx, qy, qz;
         map_point_lidar(pk, K, c, f, kp, qx, qy, qz);
         Sink1 nn;
-        traverse(S, qx, qy, qz, nn, lane);
+        nn_near_leaf(S, pr.adj_r, (int)(wk.corr_sp[cbase + ci] >> 5), qx, qy, qz, nn, lane);
         if (lane == 0) wk.nn_pos[qbase + qi] = nn.pos;
         if (pr.use_plane && !pr.plane_index) {  // with the plane index the neighbourhood of nn is already fitted
-            const double nx = (double)S.px[nn.pos], ny = (double)S.py[nn.pos], nz = (double)S.pz[nn.pos];
             SinkK kn(pr.k, pr.radius2);
-            traverse(S, nx, ny, nz, kn, lane, (int)(nn.pos >> 5));
+            knn_around_point(S, nn.pos, kn, lane);
             wk.nb[(qbase + qi) * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
             store_nb_coords(wk.nbx, wk.nbx_stride, qbase + qi, S, lane, kn.count, kn.kpos);
             const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
@@ -175,7 +175,7 @@ k_index_knn(const DevPack pk, const int kf_begin, const DevParams pr, const long
     const ScanView S = make_view(pk, K);
     for (int p = blockIdx.x * kWarps + warp; p < K.n_pts; p += gridDim.x * kWarps) {
         SinkK kn(pr.k, pr.radius2);
-        traverse(S, (double)S.px[p], (double)S.py[p], (double)S.pz[p], kn, lane, p >> 5);
+        knn_around_point(S, (uint32_t)p, kn, lane);
         const long long o = K.pt_off - first_pt + p;
         nb[o * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
         const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);

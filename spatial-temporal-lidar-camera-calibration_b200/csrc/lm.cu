@@ -83,7 +83,7 @@ k_lm_knn_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
             continue;
         }
         SinkK kn(pr.k, pr.radius2);
-        traverse(S, (double)S.px[sp], (double)S.py[sp], (double)S.pz[sp], kn, lane, (int)(sp >> 5));
+        knn_around_point(S, sp, kn, lane);
         wk.nb[slot * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
         store_nb_coords(wk.nbx, wk.nbx_stride, slot, S, lane, kn.count, kn.kpos);
         const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
@@ -151,7 +151,7 @@ k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
         lm_map_point(pk, K, f, kp, Mx, My, Mz);
         xform(c0.Ri, c0.ti, dmul(Mx, c0.s), dmul(My, c0.s), dmul(Mz, c0.s), qx, qy, qz);  // initSE3.inverse() * (MapPoint * init_scale)
         Sink1 nn;
-        traverse(S, qx, qy, qz, nn, lane);
+        nn_near_leaf(S, pr.adj_r, (int)(sp >> 5), qx, qy, qz, nn, lane);
         if (nn.d > pr.max_3d_dist2) {  // iba_local.cpp:289
             if (lane == 0) lm.nnb_pos[slot] = 0xffffffffu;
             continue;
@@ -166,7 +166,7 @@ k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
             continue;
         }
         SinkK kn(pr.k, pr.radius2);
-        traverse(S, (double)S.px[nn.pos], (double)S.py[nn.pos], (double)S.pz[nn.pos], kn, lane, (int)(nn.pos >> 5));
+        knn_around_point(S, nn.pos, kn, lane);
         lm.nbb[slot * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
         store_nb_coords(lm.nbbx, lm.nbbx_stride, slot, S, lane, kn.count, kn.kpos);
         const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
