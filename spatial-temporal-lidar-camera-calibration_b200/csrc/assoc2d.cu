@@ -350,7 +350,10 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
             wk.corr_kp[out_base + pc] = (uint32_t)k;
             wk.corr_pt[out_base + pc] = (uint32_t)(key >> 32);
             wk.corr_sp[out_base + pc] = (uint32_t)(key & 0xffffffffu);
-            if (hasq) wk.q_corr[out_base + pq] = (uint32_t)pc;
+            if (hasq) {
+                wk.q_corr[out_base + pq] = (uint32_t)pc;
+                wk.q_kpsp[out_base + pq] = make_uint2((uint32_t)k, (uint32_t)(key & 0xffffffffu));
+            }
         }
         __syncthreads();
         if (tid == 0) {

@@ -109,7 +109,7 @@ void free_pack(stl_ctx *c) {
 }
 void free_work(stl_ctx *c) {
     DevWork &w = c->wk;
-    dfree(w.cand); dfree(w.corr_kp); dfree(w.corr_pt); dfree(w.corr_sp); dfree(w.q_corr); dfree(w.n_corr); dfree(w.n_q);
+    dfree(w.cand); dfree(w.corr_kp); dfree(w.corr_pt); dfree(w.corr_sp); dfree(w.q_corr); dfree(w.q_kpsp); dfree(w.n_corr); dfree(w.n_q);
     dfree(w.k1_match);
     dfree(w.frame); dfree(w.align); dfree(w.nn_pos); dfree(w.nb); dfree(w.nbx); dfree(w.nb_m); dfree(w.nb_last); dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn); dfree(w.dbg_stats);
     dfree(w.overflow); dfree(w.k1_clk);
@@ -178,7 +178,7 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
     if (ctx->wk_cap == 0) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        const size_t per_cand = (size_t)pk.n_kp_total * 16 + (size_t)pk.n_mp_total * (20 * kMaxK + 16) + (size_t)pk.n_kf * (sizeof(FrameRec) + 4 * sizeof(AlignRec) + 8 + sizeof(ulonglong2) * 8192) + sizeof(DevCand);
+        const size_t per_cand = (size_t)pk.n_kp_total * 24 + (size_t)pk.n_mp_total * (20 * kMaxK + 16) + (size_t)pk.n_kf * (sizeof(FrameRec) + 4 * sizeof(AlignRec) + 8 + sizeof(ulonglong2) * 8192) + sizeof(DevCand);
         size_t budget = std::min<size_t>((size_t)12 << 30, free_b / 4);
         int cap = (int)std::max<size_t>(1, std::min<size_t>(budget / std::max<size_t>(per_cand, 1), 256));
         if (const char *e = getenv("STL_MAX_CHUNK")) cap = std::max(1, std::min(cap, atoi(e)));  // tests: force the multi-chunk path
@@ -187,7 +187,7 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
         w.sub = 4;
         const size_t nk = (size_t)std::max<long long>(pk.n_kp_total, 1) * cap, nf = (size_t)pk.n_kf * cap;
         CK(cudaMalloc(&w.cand, sizeof(DevCand) * cap));
-        CK(cudaMalloc(&w.corr_kp, 4 * nk)); CK(cudaMalloc(&w.corr_pt, 4 * nk)); CK(cudaMalloc(&w.corr_sp, 4 * nk)); CK(cudaMalloc(&w.q_corr, 4 * nk));
+        CK(cudaMalloc(&w.corr_kp, 4 * nk)); CK(cudaMalloc(&w.corr_pt, 4 * nk)); CK(cudaMalloc(&w.corr_sp, 4 * nk)); CK(cudaMalloc(&w.q_corr, 4 * nk)); CK(cudaMalloc(&w.q_kpsp, 8 * nk));
         CK(cudaMalloc(&w.n_corr, 4 * nf)); CK(cudaMalloc(&w.n_q, 4 * nf));
         CK(cudaMalloc(&w.k1_match, sizeof(ulonglong2) * 8192 * nf));
         CK(cudaMalloc(&w.frame, sizeof(FrameRec) * nf)); CK(cudaMalloc(&w.align, sizeof(AlignRec) * nf * w.sub));

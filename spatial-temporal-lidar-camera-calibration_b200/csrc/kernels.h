@@ -43,6 +43,7 @@ struct DevWork {
     uint32_t *corr_pt = nullptr;  // [Bc][n_kp_total]  original scan index
     uint32_t *corr_sp = nullptr;  // [Bc][n_kp_total]  sorted scan position
     uint32_t *q_corr = nullptr;   // [Bc][n_kp_total]  correspondence indices that carry a map point
+    uint2 *q_kpsp = nullptr;      // [Bc][n_kp_total]  (keypoint, sorted scan position) of those, so that K2 needs no second hop
     int *n_corr = nullptr;        // [Bc][n_kf]
     int *n_q = nullptr;           // [Bc][n_kf]
     FrameRec *frame = nullptr;    // [Bc][n_kf]

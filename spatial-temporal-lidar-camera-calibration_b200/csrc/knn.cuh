@@ -152,9 +152,9 @@ struct SinkK {
         //     order is monotone in d2) with the five low bits replaced by the lane — one SHFL and one
         //     MIN/MAX per compare-exchange instead of moving the (d2, index, position) triple.
         unsigned key = cd < (double)INFINITY ? ((__float_as_uint(__double2float_rd(cd)) & ~31u) | (unsigned)lane) : (0xffffffe0u | (unsigned)lane);
-#pragma unroll 1
+#pragma unroll
         for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll 1
+#pragma unroll
             for (int j = kk >> 1; j > 0; j >>= 1) {
                 const unsigned o = __shfl_xor_sync(kFull, key, j);
                 const bool keep_min = ((lane & kk) == 0) == ((lane & j) == 0);
@@ -195,7 +195,7 @@ struct SinkK {
             const double rd = __shfl_sync(kFull, cd, 31 - lane);
             const uint32_t ri = __shfl_sync(kFull, ci, 31 - lane), rp = __shfl_sync(kFull, cp, 31 - lane);
             if (rd < kd || (rd == kd && ri < ki)) { kd = rd; ki = ri; kpos = rp; }
-#pragma unroll 1
+#pragma unroll
             for (int j = 16; j > 0; j >>= 1) cx(kd, ki, kpos, j, (lane & j) == 0);
         }
         const int nvalid = __popc(__ballot_sync(kFull, kd < (double)INFINITY));

@@ -60,12 +60,11 @@ k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
     const long long cbase = (long long)b * pk.n_kp_total + K.kp_off;
     const long long qbase = (long long)b * pk.n_mp_total + K.mp_off;
     for (int qi = j * kWarps + warp; qi < nq; qi += sub * kWarps) {
-        const uint32_t ci = wk.q_corr[cbase + qi];
-        const uint32_t kp = wk.corr_kp[cbase + ci];
+        const uint2 ks = wk.q_kpsp[cbase + qi];  // (keypoint, associated scan position)
         double qx, qy, qz;
-        map_point_lidar(pk, K, c, f, kp, qx, qy, qz);
+        map_point_lidar(pk, K, c, f, ks.x, qx, qy, qz);
         Sink1 nn;
-        nn_near_leaf(S, pr.adj_r, (int)(wk.corr_sp[cbase + ci] >> 5), qx, qy, qz, nn, lane);
+        nn_near_leaf(S, pr.adj_r, (int)(ks.y >> 5), qx, qy, qz, nn, lane);
         if (lane == 0) wk.nn_pos[qbase + qi] = nn.pos;
         if (pr.use_plane && !pr.plane_index) {  // with the plane index the neighbourhood of nn is already fitted
             SinkK kn(pr.k, pr.radius2);

@@ -68,8 +68,8 @@ k_lm_knn_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
     const ScanView S = make_view(pk, K);
     const int C = pk.n_covis;
     for (int qi = j * kWarps + warp; qi < nq; qi += kAssocSub * kWarps) {
-        const uint32_t ci = wk.q_corr[K.kp_off + qi];
-        const uint32_t kp = wk.corr_kp[K.kp_off + ci], sp = wk.corr_sp[K.kp_off + ci];
+        const uint2 ks = wk.q_kpsp[K.kp_off + qi];
+        const uint32_t kp = ks.x, sp = ks.y;
         const long long slot = K.mp_off + qi;
         int ncov = 0;
         for (int s = 0; s < C; ++s)
@@ -145,8 +145,8 @@ k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
     for (int qi = j * kWarps + warp; qi < nq; qi += kAssocSub * kWarps) {
         const long long slot = K.mp_off + qi;
         if (lm.stage[slot] != 1) continue;
-        const uint32_t ci = wk.q_corr[K.kp_off + qi];
-        const uint32_t kp = wk.corr_kp[K.kp_off + ci], sp = wk.corr_sp[K.kp_off + ci];
+        const uint2 ks = wk.q_kpsp[K.kp_off + qi];
+        const uint32_t kp = ks.x, sp = ks.y;
         double Mx, My, Mz, qx, qy, qz;
         lm_map_point(pk, K, f, kp, Mx, My, Mz);
         xform(c0.Ri, c0.ti, dmul(Mx, c0.s), dmul(My, c0.s), dmul(Mz, c0.s), qx, qy, qz);  // initSE3.inverse() * (MapPoint * init_scale)
