@@ -248,6 +248,14 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
     }
 }
 
+// Queries of a CTA are handed out through a shared-memory ticket: a warp that drew short traversals
+// takes the next query instead of idling until the slowest warp of the CTA is done.
+__device__ __forceinline__ int next_ticket(int *ticket, int lane) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 1);
+    return __shfl_sync(kFull, t, 0);
+}
+
 // ---- adjacency scan -----------------------------------------------------------------------
 // The nearest leaves around leaf `home` are listed in pk.adj (build.cu, nearest first, one per lane)
 // together with the squared distance `cov` the row covers: every point closer than sqrt(cov) to ANY

@@ -59,7 +59,12 @@ k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
     const ScanView S = make_view(pk, K);
     const long long cbase = (long long)b * pk.n_kp_total + K.kp_off;
     const long long qbase = (long long)b * pk.n_mp_total + K.mp_off;
-    for (int qi = j * kWarps + warp; qi < nq; qi += sub * kWarps) {
+    __shared__ int ticket;
+    if (threadIdx.x == 0) ticket = 0;
+    __syncthreads();
+    for (;;) {
+        const int qi = next_ticket(&ticket, lane) * sub + j;
+        if (qi >= nq) break;
         const uint2 ks = wk.q_kpsp[cbase + qi];  // (keypoint, associated scan position)
         double qx, qy, qz;
         map_point_lidar(pk, K, c, f, ks.x, qx, qy, qz);

@@ -67,7 +67,12 @@ k_lm_knn_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
     const DevKf K = pk.kf[f];
     const ScanView S = make_view(pk, K);
     const int C = pk.n_covis;
-    for (int qi = j * kWarps + warp; qi < nq; qi += kAssocSub * kWarps) {
+    __shared__ int ticket;
+    if (threadIdx.x == 0) ticket = 0;
+    __syncthreads();
+    for (;;) {
+        const int qi = next_ticket(&ticket, lane) * kAssocSub + j;
+        if (qi >= nq) break;
         const uint2 ks = wk.q_kpsp[K.kp_off + qi];
         const uint32_t kp = ks.x, sp = ks.y;
         const long long slot = K.mp_off + qi;
@@ -142,7 +147,12 @@ k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
     const DevKf K = pk.kf[f];
     const DevCand &c0 = wk.cand[0];
     const ScanView S = make_view(pk, K);
-    for (int qi = j * kWarps + warp; qi < nq; qi += kAssocSub * kWarps) {
+    __shared__ int ticket;
+    if (threadIdx.x == 0) ticket = 0;
+    __syncthreads();
+    for (;;) {
+        const int qi = next_ticket(&ticket, lane) * kAssocSub + j;
+        if (qi >= nq) break;
         const long long slot = K.mp_off + qi;
         if (lm.stage[slot] != 1) continue;
         const uint2 ks = wk.q_kpsp[K.kp_off + qi];
