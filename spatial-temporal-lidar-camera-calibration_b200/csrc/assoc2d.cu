@@ -269,13 +269,26 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
         // the hand-eye term only needs the candidate: one lane of the last warp evaluates it while the
         // other warps stream (groups are handed out dynamically, so nobody waits for that warp)
         if (with_terms && K.he_valid && tid == kThreads - 32) S.he_val = hand_eye_term(pk, c, f);
-        for (;;) {
-            int w = 0;
-            if (lane == 0) w = atomicAdd(&S.next_group, 1);
-            w = __shfl_sync(0xffffffffu, w, 0);
-            if (w >= ng) break;
-            const int i = (int)T.groups[w] * 32 + lane;  // float4 index
-            const float4 x4 = ld_stream_f4(X + i), y4 = ld_stream_f4(Y + i), z4 = ld_stream_f4(Z + i);
+        // software-pipelined: the loads of the next group are in flight while the current one is culled
+        int w = 0;
+        if (lane == 0) w = atomicAdd(&S.next_group, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f), y4 = x4, z4 = x4;
+        int i = 0;
+        if (w < ng) {
+            i = (int)T.groups[w] * 32 + lane;  // float4 index
+            x4 = ld_stream_f4(X + i); y4 = ld_stream_f4(Y + i); z4 = ld_stream_f4(Z + i);
+        }
+        while (w < ng) {
+            int wn = 0;
+            if (lane == 0) wn = atomicAdd(&S.next_group, 1);
+            wn = __shfl_sync(0xffffffffu, wn, 0);
+            float4 xn = x4, yn = y4, zn = z4;
+            int in = 0;
+            if (wn < ng) {
+                in = (int)T.groups[wn] * 32 + lane;
+                xn = ld_stream_f4(X + in); yn = ld_stream_f4(Y + in); zn = ld_stream_f4(Z + in);
+            }
             const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -301,6 +314,7 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
                     else S.overflow = 1;
                 }
             }
+            w = wn; i = in; x4 = xn; y4 = yn; z4 = zn;
         }
     }
     __syncthreads();
@@ -330,39 +344,47 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
     if (ovf && tid == 0 && wk.overflow) atomicAdd(wk.overflow, 1);
     if (timing) clk[4] = clock64();
 
-    // ---- phase D: corrset in keypoint order (block scan), query list = correspondences with a map point
+    // ---- phase D: corrset in keypoint order, query list = correspondences with a map point.
+    // One block scan: thread t owns the consecutive keypoints [t*per, (t+1)*per).
     unsigned long long *best_key = T.best_key;
     const long long out_base = (long long)b * pk.n_kp_total + K.kp_off;
     const float *mp = pk.kp_mp + K.kp_off * 3;
-    for (int k0 = 0; k0 < K.n_kp; k0 += kThreads) {
-        const int k = k0 + tid;
-        const bool has = k < K.n_kp && best_key[k] != kNoKey;
-        const bool hasq = has && !isnan(mp[k * 3]);
-        const unsigned m1 = __ballot_sync(0xffffffffu, has), m2 = __ballot_sync(0xffffffffu, hasq);
-        if (lane == 0) { S.warp_cnt[warp] = __popc(m1); S.warp_q[warp] = __popc(m2); }
+    {
+        const int per = (K.n_kp + kThreads - 1) / kThreads;
+        const int k_lo = min(tid * per, K.n_kp), k_hi = min(k_lo + per, K.n_kp);
+        int c = 0, cq = 0;
+        for (int k = k_lo; k < k_hi; ++k) {
+            const bool has = best_key[k] != kNoKey;
+            c += has;
+            cq += has && !isnan(mp[k * 3]);
+        }
+        int ic = c, iq = cq;  // inclusive warp scans
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, ic, o), a2 = __shfl_up_sync(0xffffffffu, iq, o);
+            if (lane >= o) { ic += a; iq += a2; }
+        }
+        if (lane == 31) { S.warp_cnt[warp] = ic; S.warp_q[warp] = iq; }
         __syncthreads();
-        int pc = S.base_corr, pq = S.base_q;
-        for (int w = 0; w < warp; ++w) { pc += S.warp_cnt[w]; pq += S.warp_q[w]; }
-        pc += __popc(m1 & ((1u << lane) - 1));
-        pq += __popc(m2 & ((1u << lane) - 1));
-        if (has) {
+        int pc = ic - c, pq = iq - cq, tc = 0, tq = 0;
+        for (int w = 0; w < kThreads / 32; ++w) {
+            if (w < warp) { pc += S.warp_cnt[w]; pq += S.warp_q[w]; }
+            tc += S.warp_cnt[w]; tq += S.warp_q[w];
+        }
+        for (int k = k_lo; k < k_hi; ++k) {
             const unsigned long long key = best_key[k];
+            if (key == kNoKey) continue;
             wk.corr_kp[out_base + pc] = (uint32_t)k;
             wk.corr_pt[out_base + pc] = (uint32_t)(key >> 32);
             wk.corr_sp[out_base + pc] = (uint32_t)(key & 0xffffffffu);
-            if (hasq) {
+            if (!isnan(mp[k * 3])) {
                 wk.q_corr[out_base + pq] = (uint32_t)pc;
                 wk.q_kpsp[out_base + pq] = make_uint2((uint32_t)k, (uint32_t)(key & 0xffffffffu));
+                ++pq;
             }
+            ++pc;
         }
-        __syncthreads();
-        if (tid == 0) {
-            int tc = 0, tq = 0;
-            for (int w = 0; w < kThreads / 32; ++w) { tc += S.warp_cnt[w]; tq += S.warp_q[w]; }
-            S.base_corr += tc;
-            S.base_q += tq;
-        }
-        __syncthreads();
+        if (tid == 0) { S.base_corr = tc; S.base_q = tq; }
+        __syncthreads();  // also publishes the lists to the covisible phase below
     }
     if (timing) clk[5] = clock64();
     const int ncorr = S.base_corr, nq = S.base_q;
@@ -373,10 +395,11 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
     if (kept && with_terms) {
         const int C = pk.n_covis;
         const double fx = K.fx, fy = K.fy, cx = K.cx, cy = K.cy, W = K.W, H = K.H;
-        for (int k = tid; k < K.n_kp; k += kThreads) {
-            const unsigned long long key = best_key[k];
-            if (key == kNoKey) continue;
-            const long long g = K.pt_off + (uint32_t)(key & 0xffffffffu);
+        // over the compacted correspondences (written above by this CTA; the barrier that ends phase D makes
+        // them visible), not over all keypoints: a poor candidate keeps a third of them
+        for (int i = tid; i < ncorr; i += kThreads) {
+            const int k = (int)wk.corr_kp[out_base + i];
+            const long long g = K.pt_off + wk.corr_sp[out_base + i];
             double p0x, p0y, p0z;
             xform(c.R, c.t, (double)pk.px[g], (double)pk.py[g], (double)pk.pz[g], p0x, p0y, p0z);
             for (int j = 0; j < C; ++j) {

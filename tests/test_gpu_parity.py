@@ -350,3 +350,34 @@ def test_concurrent_callers_are_serialised(gpu_ctx, small_candidates):
     [t.start() for t in th]; [t.join() for t in th]
     for i in range(8):
         assert np.array_equal(got[i], want[i % 4])
+
+
+@pytest.mark.parametrize("radius", [0.6, 1.5])
+def test_leaf_adjacency_scan_equals_tree_descent(oracle_mod, pkg, small_pack, small_candidates, radius, monkeypatch):
+    """The adjacency lists (K0) only change HOW neighbourhoods are searched.  radius = 1.5 m makes most rows
+    truncated or empty, so the coverage test, the restart and the descent fallback all run; a far-off
+    candidate makes the 1-NN of the map points leave the covered range."""
+    capi = importlib.import_module(PKG + ".capi")
+    p = pkg.default_params(); p.norm_radius = radius
+    pack = small_pack[0].shard(1, 4)
+    X = np.concatenate([small_candidates[:3], small_candidates[3:4] + np.array([0.03, -0.02, 0.02, 0.4, -0.3, 0.2, 0.0])])
+    with capi.Context(params=p) as c:
+        c.upload(pack)
+        got = c.eval_sums(X)
+        a = [c.debug_align(b, 1) for b in (0, 3)]
+        nb = c.associate(X[1]); L = c.linearize(X[:2])
+    monkeypatch.setenv("STL_NO_ADJ", "1")
+    with capi.Context(params=p) as c:
+        c.upload(pack)
+        assert np.array_equal(c.eval_sums(X), got)
+        for b, ab in zip((0, 3), a):
+            d = c.debug_align(b, 1)
+            assert all(np.array_equal(d[k], ab[k]) for k in ("nn", "m", "is_plane", "knn", "dist"))
+        assert np.array_equal(c.associate(X[1]), nb) and np.array_equal(c.linearize(X[:2]), L)
+    monkeypatch.delenv("STL_NO_ADJ")
+    orc = oracle_mod.Oracle(pack, params=p, kind="best")
+    want, ties, _ = orc.ba_error_sums(X, mode=0)
+    assert ties.sum() == 0
+    _check_sums(got, want)
+    d = orc.frame_debug(X[3], 1)
+    assert np.array_equal(a[1]["nn"], d["align_nn"]) and np.array_equal(a[1]["m"], d["align_m"])
