@@ -731,7 +731,7 @@ stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[4]
     cudaError_t e;
     { StageTimer t(ctx, 5, st); e = lm_associate(ctx->pk, ctx->wk, ctx->dpr, ctx->lm, st); }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "associate: %s", cudaGetErrorString(e));
-    ctx->launches += 5 + (ctx->lm.n3d > 0 ? 1 : 0);  // K1, four association kernels, k_count_types (cub select kernels not counted)
+    ctx->launches += 6;  // K1, four association kernels, k_count_types (cub select kernels not counted)
     if (n_blocks) for (int i = 0; i < 4; ++i) n_blocks[i] = ctx->lm.n_blocks[i];
     ctx->dbg_b = -1;
     ctx->last_x.clear();

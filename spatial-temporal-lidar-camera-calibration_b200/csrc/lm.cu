@@ -223,7 +223,8 @@ k_lm_plane_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
     }
 }
 
-__global__ void k_count_types(const uint8_t *__restrict__ type3d, const int *__restrict__ idx3d, int n3d, int *out) {
+__global__ void k_count_types(const uint8_t *__restrict__ type3d, const int *__restrict__ idx3d, const int *__restrict__ n3d_dev, int *out) {
+    const int n3d = *n3d_dev;  // written by the select just before, on the same stream
     int pt = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n3d; i += gridDim.x * blockDim.x) pt += type3d[idx3d[i]] == 1;
     for (int o = 16; o; o >>= 1) pt += __shfl_down_sync(0xffffffffu, pt, o);
@@ -566,13 +567,17 @@ k_linearize_gpr(const DevPack pk, const DevParams pr, const LmState lm, const Lm
 }
 
 // one CTA per candidate: sums the per-CTA partials in order and expands H to the full symmetric 7x7
-__global__ void k_lin_finish(const double *__restrict__ partial, int nchunks, double *__restrict__ out) {
+// one CTA of 1024 threads per candidate: warp w sums values w, w+32 over the chunks (lane-strided partial
+// sums, then a shuffle tree: a fixed order, so the result is reproducible)
+__global__ void __launch_bounds__(1024)
+k_lin_finish(const double *__restrict__ partial, int nchunks, double *__restrict__ out) {
     __shared__ double tot[kLinVals];
-    const int b = blockIdx.x;
-    if (threadIdx.x < kLinVals) {
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int v = warp; v < kLinVals; v += 32) {
         double x = 0.0;
-        for (int i = 0; i < nchunks; ++i) x += partial[((long long)b * nchunks + i) * kLinVals + threadIdx.x];
-        tot[threadIdx.x] = x;
+        for (int i = lane; i < nchunks; i += 32) x += partial[((long long)b * nchunks + i) * kLinVals + v];
+        for (int o = 16; o; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) tot[v] = x;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -643,17 +648,13 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
         tb = lm.tmp_bytes;
         TRY(cub::DeviceSelect::Flagged(lm.d_tmp, tb, it, lm.flagG, lm.idxG, lm.d_counts + 3, (int)ns, st));
     }
+    k_count_types<<<64, 256, 0, st>>>(lm.type3d, lm.idx3d, lm.d_counts + 1, lm.d_counts + 2);
+    TRY(cudaGetLastError());
     int h[4] = {0, 0, 0, 0};
     TRY(cudaMemcpyAsync(h, lm.d_counts, 16, cudaMemcpyDeviceToHost, st));
-    TRY(cudaStreamSynchronize(st));
+    TRY(cudaStreamSynchronize(st));  // the one host round trip of the association: BuildProblem returns the block counts
     lm.n2d = h[0]; lm.n3d = h[1]; lm.nG = pr.use_gpr ? h[3] : 0;
-    int npt = 0;
-    if (lm.n3d > 0) {
-        k_count_types<<<64, 256, 0, st>>>(lm.type3d, lm.idx3d, lm.n3d, lm.d_counts + 2);
-        TRY(cudaGetLastError());
-        TRY(cudaMemcpyAsync(&npt, lm.d_counts + 2, 4, cudaMemcpyDeviceToHost, st));
-        TRY(cudaStreamSynchronize(st));
-    }
+    const int npt = h[2];
     lm.n_blocks[0] = lm.n2d; lm.n_blocks[1] = npt; lm.n_blocks[2] = lm.n3d - npt; lm.n_blocks[3] = lm.nG;
     lm.ready = true;
     return cudaSuccess;
@@ -694,7 +695,7 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
         k_linearize_gpr<<<dim3(gchunks, B), kGprWarps * 32, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, chunks);
         TRY(cudaGetLastError());
     }
-    k_lin_finish<<<B, 64, 0, st>>>(lm.partial, stride, d_out);
+    k_lin_finish<<<B, 1024, 0, st>>>(lm.partial, stride, d_out);
     TRY(cudaGetLastError());
 #undef TRY
     return cudaSuccess;
