@@ -29,7 +29,7 @@ constexpr int kWarps = 8;
 #ifndef STL_KNN_MINB
 #define STL_KNN_MINB 6  // resident CTAs per SM the traversal kernels are compiled for (40 registers; measured best of 4/5/6)
 #endif
-constexpr int kAssocSub = 8;
+constexpr int kAssocSub = 4;
 constexpr int kPlaneSub = 4;  // CTAs of 128 threads per keyframe in the thread-per-query plane kernels
 constexpr int kLinVals = 41;  // cost, g[7], H upper 28, n2d, npt, npl, nres, ngpr
 constexpr int kGprWarps = 3;
@@ -76,9 +76,9 @@ k_lm_knn_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
         const uint2 ks = wk.q_kpsp[K.kp_off + qi];
         const uint32_t kp = ks.x, sp = ks.y;
         const long long slot = K.mp_off + qi;
-        int ncov = 0;
-        for (int s = 0; s < C; ++s)
-            if (pk.covis_valid[f * C + s] && !isnan(pk.covis_uv[(K.kp_off + kp) * C + s].x)) ++ncov;
+        // lane s looks at covisible keyframe s (C <= STL_MAX_COVIS <= 32)
+        const bool obs = lane < C && pk.covis_valid[f * C + lane] && !isnan(pk.covis_uv[(K.kp_off + kp) * C + lane].x);
+        const int ncov = __popc(__ballot_sync(kFull, obs));
         if (ncov == 0) {  // iba_local.cpp:259
             if (lane == 0) wk.nb_m[slot] = -1;
             continue;
