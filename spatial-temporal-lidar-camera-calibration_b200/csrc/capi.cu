@@ -679,8 +679,9 @@ stl_status_t stl_debug_frame(stl_ctx_t *ctx, int32_t b, int32_t kf, double out[1
     if (getenv("STL_DEBUG_STATS")) {
         unsigned long long st[8];
         cudaMemcpy(st, ctx->wk.dbg_stats, 64, cudaMemcpyDeviceToHost);
-        if (st[0]) fprintf(stderr, "[stl] traversal stats (cumulative): queries %llu | 1-NN iters %.1f visits %.1f | k-NN iters %.1f visits %.1f inserts %.1f m %.1f\n",
-                st[0], (double)st[1] / st[0], (double)st[2] / st[0], (double)st[3] / st[0], (double)st[4] / st[0], (double)st[5] / st[0], (double)st[6] / st[0]);
+        if (st[0] + st[4]) fprintf(stderr, "[stl] K2a search paths (cumulative): k-NN %llu = adjacency %.1f%% + restart %.1f%% + no row %.1f%% | 1-NN %llu = adjacency %.1f%% + descent after scan %.1f%% + no row %.1f%%\n",
+                st[0], 100.0 * st[1] / std::max(st[0], 1ull), 100.0 * st[2] / std::max(st[0], 1ull), 100.0 * st[3] / std::max(st[0], 1ull),
+                st[4], 100.0 * st[5] / std::max(st[4], 1ull), 100.0 * st[6] / std::max(st[4], 1ull), 100.0 * st[7] / std::max(st[4], 1ull));
     }
     for (auto &x : a) { out[8] += x.s3d; out[9] += x.v3d; out[10] += x.c3d; out[11] += x.vpl; out[12] += x.vpt; }
     return STL_OK;

@@ -28,6 +28,7 @@ struct ScanView {
     const float4 *lo, *hi;  // [n0 leaves][n1 level-1][32 level-2]
     const uint16_t *adj;    // [n0][32] leaf adjacency rows (null: none)
     const float *adj_cov;   // [n0] squared distance each row covers
+    unsigned long long *stats;  // optional [8] path counters (debug contexts only; null otherwise)
     int n0, n1;
 };
 
@@ -38,6 +39,7 @@ __device__ __forceinline__ ScanView make_view(const DevPack &pk, const DevKf &K)
     v.lo = pk.node_lo + K.node_off; v.hi = pk.node_hi + K.node_off;
     v.adj = pk.adj ? pk.adj + K.node_off * 32 : nullptr;
     v.adj_cov = pk.adj ? pk.adj_cov + K.node_off : nullptr;
+    v.stats = nullptr;
     v.n0 = K.n0; v.n1 = K.n1;
     return v;
 }
@@ -289,7 +291,9 @@ __device__ __forceinline__ float scan_adjacent(const ScanView &S, int home, doub
 __device__ __forceinline__ void knn_around_point(const ScanView &S, uint32_t pos, SinkK &kn, int lane) {
     const double x = (double)S.px[pos], y = (double)S.py[pos], z = (double)S.pz[pos];
     const float cov = scan_adjacent(S, (int)(pos >> 5), x, y, z, kn, lane);
-    if (cov > 3.0e38f || (cov >= 0.f && kn.count == kn.k && kn.wdf < cov)) return;
+    const bool done = cov > 3.0e38f || (cov >= 0.f && kn.count == kn.k && kn.wdf < cov);
+    if (S.stats && lane == 0) { atomicAdd(S.stats + 0, 1ull); atomicAdd(S.stats + (done ? 1 : (cov >= 0.f ? 2 : 3)), 1ull); }
+    if (done) return;
     if (cov >= 0.f) kn = SinkK(kn.k, kn.r2);
     traverse(S, x, y, z, kn, lane, (int)(pos >> 5));
 }
@@ -302,6 +306,7 @@ __device__ __forceinline__ void knn_around_point(const ScanView &S, uint32_t pos
 __device__ __forceinline__ void nn_near_leaf(const ScanView &S, float adj_r, int home, double qx, double qy, double qz, Sink1 &nn,
                                              int lane) {
     const float cov = scan_adjacent(S, home, qx, qy, qz, nn, lane);
+    if (S.stats && lane == 0) atomicAdd(S.stats + 4, 1ull);
     if (cov >= 0.f && nn.pos != 0xffffffffu) {
         const float4 lo = S.lo[home], hi = S.hi[home];
         const float xl = __double2float_rd(qx), xh = __double2float_ru(qx), yl = __double2float_rd(qy), yh = __double2float_ru(qy);
@@ -311,8 +316,12 @@ __device__ __forceinline__ void nn_near_leaf(const ScanView &S, float adj_r, int
         const float gz = fmaxf(fmaxf(__fsub_ru(lo.z, zl), __fsub_ru(zh, hi.z)), 0.f);
         const float delta = __fsqrt_ru(__fadd_ru(__fadd_ru(__fmul_ru(gx, gx), __fmul_ru(gy, gy)), __fmul_ru(gz, gz)));
         const float reach = __fadd_ru(__fsqrt_ru(nn.df), delta);
-        if (cov > 3.0e38f ? reach <= adj_r : reach < __fsqrt_rd(cov)) return;
+        if (cov > 3.0e38f ? reach <= adj_r : reach < __fsqrt_rd(cov)) {
+            if (S.stats && lane == 0) atomicAdd(S.stats + 5, 1ull);
+            return;
+        }
     }
+    if (S.stats && lane == 0) atomicAdd(S.stats + (cov >= 0.f ? 6 : 7), 1ull);
     traverse(S, qx, qy, qz, nn, lane);
 }
 

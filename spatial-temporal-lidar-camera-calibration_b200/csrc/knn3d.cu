@@ -56,7 +56,8 @@ k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const DevKf K = pk.kf[f];
     const DevCand &c = wk.cand[b];
-    const ScanView S = make_view(pk, K);
+    ScanView S = make_view(pk, K);
+    S.stats = wk.dbg_stats;
     const long long cbase = (long long)b * pk.n_kp_total + K.kp_off;
     const long long qbase = (long long)b * pk.n_mp_total + K.mp_off;
     __shared__ int ticket;
