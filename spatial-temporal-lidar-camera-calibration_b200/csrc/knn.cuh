@@ -320,6 +320,19 @@ __device__ __forceinline__ void nn_near_leaf(const ScanView &S, float adj_r, int
             if (S.stats && lane == 0) atomicAdd(S.stats + 5, 1ull);
             return;
         }
+        // second chance through the leaf of the point just found (p1, at distance rho): every point as
+        // close to the query as p1 lies within 2 rho of p1, hence of p1's leaf box — if that row covers
+        // 2 rho, scanning it is exhaustive
+        const int l1 = (int)(nn.pos >> 5);
+        if (l1 != home) {
+            const float cov1 = S.adj_cov[l1];
+            const float two_rho = __fmul_ru(2.f, __fsqrt_ru(nn.df));
+            if (cov1 >= 0.f && (cov1 > 3.0e38f ? two_rho <= adj_r : two_rho < __fsqrt_rd(cov1))) {
+                scan_adjacent(S, l1, qx, qy, qz, nn, lane);
+                if (S.stats && lane == 0) atomicAdd(S.stats + 5, 1ull);
+                return;
+            }
+        }
     }
     if (S.stats && lane == 0) atomicAdd(S.stats + (cov >= 0.f ? 6 : 7), 1ull);
     traverse(S, qx, qy, qz, nn, lane);
