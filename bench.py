@@ -447,6 +447,20 @@ def main():
                           f"OpenMP over keyframes, extrapolated linearly; KNN = {'reference nanoflann v1.5.0' if kind == 'ref' else 'nanoflann port'}; "
                           f"KD-tree build {build_s:.2f}s excluded",
             }
+            # SURVEY §8d asks for both CPU modes of the BAError cost alone: M1 = OpenMP over keyframes, one candidate
+            # at a time (iba_func.cpp:203,463); M2 = candidates in parallel, each serial over keyframes (NOMAD threads)
+            try:
+                from oracle import oracle as O
+                n2 = min(96, F)
+                o2 = O.Oracle(pack.shard(0, n2), kind="ref" if O.have_ref() else "port", nthreads=cores)
+                Xc = X[args.warmup: args.warmup + cores] if len(X) - args.warmup >= cores else np.resize(X[args.warmup:], (cores, 7))
+                t0 = time.perf_counter(); o2.ba_error_sums(Xc, mode=1, strict=True, nthreads=cores); t_m1 = time.perf_counter() - t0
+                t0 = time.perf_counter(); o2.ba_error_sums(Xc, mode=2, strict=True, nthreads=cores); t_m2 = time.perf_counter() - t0
+                line["cpu_baseline"]["bae_only"] = {
+                    "m1_keyframe_parallel_evals_per_s": len(Xc) * (n2 / F) / t_m1, "m2_candidate_parallel_evals_per_s": len(Xc) * (n2 / F) / t_m2,
+                    "sample": f"BAError only, {len(Xc)} candidates x {n2} of {F} keyframes, {cores} threads, extrapolated linearly"}
+            except Exception as e:  # the headline baseline above stands on its own
+                line["cpu_baseline"]["bae_only"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

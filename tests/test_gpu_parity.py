@@ -381,3 +381,39 @@ def test_leaf_adjacency_scan_equals_tree_descent(oracle_mod, pkg, small_pack, sm
     _check_sums(got, want)
     d = orc.frame_debug(X[3], 1)
     assert np.array_equal(a[1]["nn"], d["align_nn"]) and np.array_equal(a[1]["m"], d["align_m"])
+
+
+def test_exact_ties_are_broken_by_original_index(oracle_mod, pkg, small_pack, small_candidates):
+    """Duplicated scan points create exact distance ties in every search.  nanoflann resolves them by visit
+    order; the contract here is (distance, original index) order — the oracle's non-strict mode —
+    for the 2-D association, the 1-NN, the k-NN lists and everything derived from them."""
+    capi = importlib.import_module(PKG + ".capi")
+    one = small_pack[0].shard(2, 3)
+    rng = np.random.default_rng(5)
+    n = one.n_points
+    dup = rng.choice(n, 6000, replace=False)
+    one.scan_xyz = np.concatenate([one.scan_xyz, one.scan_xyz[dup]])      # copies get the HIGHER indices
+    one.scan_offset = np.array([0, n + len(dup)], np.int64)
+    orc = oracle_mod.Oracle(one, kind="best")
+    x = small_candidates[0]
+    want, ties, _ = orc.ba_error_sums(x, mode=0)
+    assert ties[0] > 0 and ties[2] > 0                                     # the ties are really there
+    d = orc.frame_debug(x, 0)
+    with capi.Context() as c:
+        c.upload(one)
+        got = c.eval_sums(x)
+        _check_sums(got, want)
+        kp, pt = c.debug_corrset(0, 0)
+        assert np.array_equal(kp, d["corr_kp"]) and np.array_equal(pt, d["corr_pt"])
+        assert (pt < n).all()                                              # never the copy
+        a = c.debug_align(0, 0)
+        assert np.array_equal(a["nn"], d["align_nn"]) and np.array_equal(a["m"], d["align_m"])
+        assert all(np.array_equal(a["knn"][i][: a["m"][i]], d["align_knn"][i][: d["align_m"][i]]) for i in range(len(a["m"])))
+        P = one.scan_xyz.astype(np.float64)
+        q = np.concatenate([P[dup[:200]], P[rng.choice(n, 200)] + rng.normal(0, 0.02, (200, 3))])
+        io, do, co, t3 = orc.knn3d(0, q, 30, 0.36)
+        assert t3 > 0
+        ig, dg, cg = c.knn3d(0, q, 30, 0.36)
+        assert np.array_equal(cg, co) and np.array_equal(ig, io) and np.array_equal(dg, do)
+        nb_o, _ = orc.associate(x)
+        assert np.array_equal(c.associate(x), nb_o)
