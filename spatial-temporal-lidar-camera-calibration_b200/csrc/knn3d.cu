@@ -23,7 +23,7 @@ namespace {
 
 constexpr int kWarps = 8;
 #ifndef STL_KNN_MINB
-#define STL_KNN_MINB 6  // resident CTAs per SM the traversal kernels are compiled for (40 registers; measured best of 4/5/6)
+#define STL_KNN_MINB 8  // resident CTAs per SM the traversal kernels are compiled for (32 registers, full occupancy; measured best of 4..8)
 #endif
 constexpr int kPlaneThreads = 128;
 #ifndef STL_PLANE_MINB

@@ -27,7 +27,7 @@ namespace {
 
 constexpr int kWarps = 8;
 #ifndef STL_KNN_MINB
-#define STL_KNN_MINB 6  // resident CTAs per SM the traversal kernels are compiled for (40 registers; measured best of 4/5/6)
+#define STL_KNN_MINB 8  // resident CTAs per SM the traversal kernels are compiled for (32 registers, full occupancy; measured best of 4..8)
 #endif
 constexpr int kAssocSub = 4;
 constexpr int kPlaneSub = 4;  // CTAs of 128 threads per keyframe in the thread-per-query plane kernels
