@@ -233,6 +233,18 @@ stl_status_t stl_linearize_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl
 stl_status_t stl_linearize_batch_device(stl_ctx_t *ctx, const double *x, int32_t B, double *d_out,
                                         void *stream);
 
+/* Per-block view of one evaluation, for solvers that want residual blocks rather than normal equations
+ * (ceres::CostFunction::Evaluate of IBA_PlaneFactor / Point2Point_Factor / Point2Plane_Factor /
+ * IBA_GPRFactor, IBACalib2.hpp:152-184,472-507,570-625; g2o IBAPlaneEdge computeError + linearizeOplus,
+ * IBACalib.hpp:103-155): for every frozen block its type (0 plane 3-D/2-D, 1 point-to-point,
+ * 2 point-to-plane, 3 GPR), keyframe, keypoint, residual count, the RAW residuals (no robust kernel:
+ * the solver applies its own HuberLoss) and their Jacobian rows with respect to the 7 parameters,
+ * row-major [block][rmax][7] with a fixed stride of `rmax` rows (>= max(3, 2 * n_covis); g2o's edge is
+ * the same layout with rmax = 20).  Blocks are ordered plane, then 3-D/3-D, then GPR, each in keyframe
+ * order.  All buffers are host memory sized for `cap_blocks`; *n_blocks_out receives the count. */
+stl_status_t stl_eval_blocks(stl_ctx_t *ctx, const double *x, int32_t rmax, int64_t cap_blocks, int32_t *type, int32_t *kf,
+                             int32_t *kp, int32_t *n_res, double *residuals, double *jacobians, int64_t *n_blocks_out);
+
 /* ---- debug getters (parity tests only) --------------------------------- */
 
 /* 2-D correspondences of keyframe `kf` for the candidate at index `b` of the

@@ -50,6 +50,27 @@ class Context {
         check(stl_associate(ctx_, x0, n.data()), "stl_associate");
         return n;
     }
+    // per-block residuals / Jacobians of the frozen problem (stl_eval_blocks); n = blocks from associate()
+    struct Blocks {
+        int rmax = 0;
+        std::vector<int32_t> type, kf, kp, n_res;
+        std::vector<double> residuals, jacobians;  // [n][rmax], [n][rmax][7]
+        size_t size() const { return type.size(); }
+    };
+    Blocks eval_blocks(const double *x, int64_t n, int rmax) {
+        Blocks b;
+        b.rmax = rmax;
+        const size_t cap = (size_t)(n > 0 ? n : 1);
+        b.type.resize(cap); b.kf.resize(cap); b.kp.resize(cap); b.n_res.resize(cap);
+        b.residuals.resize(cap * rmax); b.jacobians.resize(cap * rmax * 7);
+        int64_t got = 0;
+        check(stl_eval_blocks(ctx_, x, rmax, (int64_t)cap, b.type.data(), b.kf.data(), b.kp.data(), b.n_res.data(), b.residuals.data(),
+                              b.jacobians.data(), &got),
+              "stl_eval_blocks");
+        b.type.resize((size_t)got); b.kf.resize((size_t)got); b.kp.resize((size_t)got); b.n_res.resize((size_t)got);
+        b.residuals.resize((size_t)got * rmax); b.jacobians.resize((size_t)got * rmax * 7);
+        return b;
+    }
     std::vector<stl_lin_sums_t> linearize(const double *x, int B) {
         std::vector<stl_lin_sums_t> out((size_t)B);
         check(stl_linearize_batch(ctx_, x, B, out.data()), "stl_linearize_batch");
@@ -115,11 +136,14 @@ class BALoss {
 class LMProblem {
   public:
     explicit LMProblem(Context &ctx) : ctx_(ctx) {}
-    std::array<int64_t, 4> build(const double x0[7]) { return ctx_.associate(x0); }
+    std::array<int64_t, 4> build(const double x0[7]) { return n_ = ctx_.associate(x0); }
     stl_lin_sums_t evaluate(const double x[7]) { return ctx_.linearize(x, 1)[0]; }
+    // block by block (raw residuals + Jacobian rows): what each CostFunction::Evaluate / g2o edge returns
+    Context::Blocks blocks(const double x[7], int rmax) { return ctx_.eval_blocks(x, n_[0] + n_[1] + n_[2] + n_[3], rmax); }
 
   private:
     Context &ctx_;
+    std::array<int64_t, 4> n_{};
 };
 
 }  // namespace stl

@@ -128,6 +128,7 @@ CALIB_SYMBOLS = {
     "stl_associate": (C.c_int, [_vp, _dp, _i64p]),
     "stl_linearize_batch": (C.c_int, [_vp, _dp, C.c_int32, C.POINTER(LinSums)]),
     "stl_linearize_batch_device": (C.c_int, [_vp, _dp, C.c_int32, _vp, _vp]),
+    "stl_eval_blocks": (C.c_int, [_vp, _dp, C.c_int32, C.c_int64, _i32p, _i32p, _i32p, _i32p, _dp, _dp, C.POINTER(C.c_int64)]),
     "stl_debug_corrset": (C.c_int, [_vp, C.c_int32, C.c_int32, _u32p, _u32p, C.c_int32, _i32p]),
     "stl_debug_align": (C.c_int, [_vp, C.c_int32, C.c_int32, _u32p, _u32p, _i32p, _i32p, _dp, _u32p,
                                   C.c_int32, _i32p]),

@@ -91,6 +91,7 @@ class Context:
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         nb = np.zeros(4, np.int64)
         _check(self.lib, self.h, self.lib.stl_associate(self.h, x0.ctypes.data_as(_dp), nb.ctypes.data_as(_abi._i64p)))
+        self.n_blocks = nb.copy()
         return nb
 
     def linearize(self, x) -> np.ndarray:
@@ -105,6 +106,24 @@ class Context:
         x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
         _check(self.lib, self.h, self.lib.stl_linearize_batch_device(self.h, x.ctypes.data_as(_dp), x.shape[0],
                                                                      C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr)))
+
+    def eval_blocks(self, x, rmax: int = 0):
+        """Per-block residuals and Jacobians of the frozen problem at x (what each ceres::CostFunction /
+        g2o edge of iba_local.cpp would return, before the robust kernel).  -> dict(type, kf, kp, n_res,
+        residuals [nb, rmax], jacobians [nb, rmax, 7])."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(7)
+        ncov = int(self.pack.n_covis) if self.pack is not None else _abi.STL_MAX_COVIS
+        rmax = int(rmax) if rmax else max(3, 2 * ncov)
+        nb = int(self.n_blocks.sum()) if getattr(self, "n_blocks", None) is not None else 0
+        cap = max(nb, 1)
+        out = dict(type=np.zeros(cap, np.int32), kf=np.zeros(cap, np.int32), kp=np.zeros(cap, np.int32), n_res=np.zeros(cap, np.int32),
+                   residuals=np.zeros((cap, rmax)), jacobians=np.zeros((cap, rmax, 7)))
+        n = C.c_int64(0)
+        _check(self.lib, self.h, self.lib.stl_eval_blocks(
+            self.h, x.ctypes.data_as(_dp), rmax, cap, out["type"].ctypes.data_as(_abi._i32p), out["kf"].ctypes.data_as(_abi._i32p),
+            out["kp"].ctypes.data_as(_abi._i32p), out["n_res"].ctypes.data_as(_abi._i32p), out["residuals"].ctypes.data_as(_dp),
+            out["jacobians"].ctypes.data_as(_dp), C.byref(n)))
+        return {k: v[: n.value] for k, v in out.items()}
 
     # -- debug getters (parity tests) ------------------------------------------
     def debug_corrset(self, b: int, kf: int):

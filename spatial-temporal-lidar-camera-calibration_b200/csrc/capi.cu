@@ -776,6 +776,46 @@ stl_status_t stl_linearize_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl
     return STL_OK;
 }
 
+stl_status_t stl_eval_blocks(stl_ctx_t *ctx, const double *x, int32_t rmax, int64_t cap_blocks, int32_t *type, int32_t *kf, int32_t *kp,
+                             int32_t *n_res, double *residuals, double *jacobians, int64_t *n_blocks_out) {
+    if (!ctx || !x || !type || !kf || !kp || !n_res || !residuals || !jacobians) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->lm.ready) return fail(ctx, STL_ERR_STATE, "stl_associate has not been called");
+    if (rmax < 3 || rmax < 2 * ctx->pk.n_covis) return fail(ctx, STL_ERR_INVALID, "rmax = %d is smaller than max(3, 2 * n_covis = %d)", rmax, 2 * ctx->pk.n_covis);
+    const long long nb = (long long)ctx->lm.n2d + ctx->lm.n3d + ctx->lm.nG;
+    if (n_blocks_out) *n_blocks_out = nb;
+    if (nb > cap_blocks) return fail(ctx, STL_ERR_CAPACITY, "%lld residual blocks, room for %lld", nb, (long long)cap_blocks);
+    if (nb == 0) return STL_OK;
+    CK(cudaSetDevice(ctx->device));
+    BlockOut bo;
+    bo.rmax = rmax;
+    int32_t *d_i = nullptr;
+    double *d_d = nullptr, *d_sums = nullptr;
+    const size_t nbs = (size_t)nb;
+    cudaError_t e = cudaMalloc(&d_i, 4 * 4 * nbs);
+    if (e == cudaSuccess) e = cudaMalloc(&d_d, 8 * nbs * rmax * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d_sums, sizeof(double) * STL_LIN_NSUMS);
+    if (e == cudaSuccess) e = cudaMemset(d_d, 0, 8 * nbs * rmax * 8);  // rows past n_res stay zero (g2o's zero padding, IBACalib.hpp:133-137)
+    stl_status_t s = STL_OK;
+    if (e == cudaSuccess) {
+        bo.type = d_i; bo.kf = d_i + nbs; bo.kp = d_i + 2 * nbs; bo.nres = d_i + 3 * nbs;
+        bo.res = d_d; bo.jac = d_d + nbs * rmax;
+        cudaStream_t st = acquire_stream(ctx, nullptr);
+        e = lm_linearize(ctx->pk, ctx->dpr, ctx->lm, x, 1, d_sums, st, &bo);
+        ctx->launches += 2 + (ctx->lm.nG > 0 ? 1 : 0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaMemcpy(type, bo.type, 4 * nbs, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(kf, bo.kf, 4 * nbs, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(kp, bo.kp, 4 * nbs, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(n_res, bo.nres, 4 * nbs, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(residuals, bo.res, 8 * nbs * rmax, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(jacobians, bo.jac, 8 * nbs * rmax * 7, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_i); cudaFree(d_d); cudaFree(d_sums);
+    if (e != cudaSuccess) s = fail(ctx, STL_ERR_CUDA, "eval_blocks: %s", cudaGetErrorString(e));
+    return s;
+}
+
 // ---- measurement -----------------------------------------------------------------
 
 stl_status_t stl_set_stream(stl_ctx_t *ctx, void *stream) {

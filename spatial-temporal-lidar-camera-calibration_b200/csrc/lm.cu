@@ -266,10 +266,24 @@ __device__ __forceinline__ void mv3(const D7 *M, const D7 *p, D7 *o) {
     for (int i = 0; i < 3; ++i) o[i] = (M[i * 3] * p[0] + M[i * 3 + 1] * p[1]) + M[i * 3 + 2] * p[2];
 }
 
+// Optional per-block output (stl_eval_blocks): what a Ceres CostFunction::Evaluate / a g2o edge would
+// return for each frozen residual block — raw residuals and their 7-column Jacobian rows, no robust
+// kernel (the solver applies its own loss).  Fixed stride of rmax rows per block.
+__device__ __forceinline__ void put_row(const BlockOut &o, long long blk, int r, const D7 &e) {
+    o.res[blk * o.rmax + r] = e.a;
+    double *j = o.jac + (blk * o.rmax + r) * 7;
+#pragma unroll
+    for (int a = 0; a < 7; ++a) j[a] = e.v[a];
+}
+__device__ __forceinline__ void put_head(const BlockOut &o, long long blk, int type, int kf, uint32_t kp, int nres) {
+    o.type[blk] = type; o.kf[blk] = kf; o.kp[blk] = (int32_t)kp; o.nres[blk] = nres;
+}
+
 // grid (chunks, B)
+template <bool WB>
 __global__ void __launch_bounds__(kLinThreads)
 k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand *__restrict__ cands, double *__restrict__ partial,
-            int partial_stride) {
+            int partial_stride, const BlockOut bo) {
     __shared__ LmCand c;
     {
         const double *src = reinterpret_cast<const double *>(cands + blockIdx.y);
@@ -326,6 +340,7 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
         A.v[36] += 1.0;
         A.v[39] += (double)nres;
         // pass 2: duals
+        int wrow = 0;
         for (int s = 0; s < C; ++s) {
             if (!pk.covis_valid[f * C + s]) continue;
             const float2 uv = pk.covis_uv[(K.kp_off + kp) * C + s];
@@ -339,7 +354,9 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
             const D7 ev = ((P1[1] * fy) / P1[2] + cy) - (double)uv.y;
             accumulate(A, eu, sr);
             accumulate(A, ev, sr);
+            if (WB) { put_row(bo, it, wrow, eu); put_row(bo, it, wrow + 1, ev); wrow += 2; }
         }
+        if (WB) put_head(bo, it, 0, f, kp, nres);
     }
 
     // ---- 3-D/3-D blocks: Point2Point_Factor / Point2Plane_Factor (IBACalib2.hpp:570-584,611-625)
@@ -360,12 +377,22 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
             accumulate(A, d[2], sr);
             A.v[37] += 1.0;
             A.v[39] += 3.0;
+            if (WB) {
+                const long long blk = (long long)lm.n2d + it;
+                put_row(bo, blk, 0, d[0]); put_row(bo, blk, 1, d[1]); put_row(bo, blk, 2, d[2]);
+                put_head(bo, blk, 1, lm.slot_kf[slot], lm.slot_kp[slot], 3);
+            }
         } else {
             const D7 e = (d[0] * g[6] + d[1] * g[7]) + d[2] * g[8];
             huber(e.a * e.a, pr.delta3d, rho0, sr);
             accumulate(A, e, sr);
             A.v[38] += 1.0;
             A.v[39] += 1.0;
+            if (WB) {
+                const long long blk = (long long)lm.n2d + it;
+                put_row(bo, blk, 0, e);
+                put_head(bo, blk, 2, lm.slot_kf[slot], lm.slot_kp[slot], 1);
+            }
         }
         A.v[0] += 0.5 * rho0;
     }
@@ -423,9 +450,10 @@ __device__ __forceinline__ double chol_solve(const GprSmem &S, double rhs, int n
 }
 
 // grid (chunks, B)
+template <bool WB>
 __global__ void __launch_bounds__(kGprWarps * 32)
 k_linearize_gpr(const DevPack pk, const DevParams pr, const LmState lm, const LmCand *__restrict__ cands, double *__restrict__ partial,
-                int partial_stride, int partial_off) {
+                int partial_stride, int partial_off, const BlockOut bo) {
     __shared__ GprSmem SM[kGprWarps];
     __shared__ LmCand c;
     {
@@ -445,6 +473,7 @@ k_linearize_gpr(const DevPack pk, const DevParams pr, const LmState lm, const Lm
         const int cs = lm.idxG[it];
         const int f = lm.slot_kf[cs];
         const uint32_t kp = lm.slot_kp[cs];
+        const long long gblk = (long long)lm.n2d + lm.n3d + it;  // block index in stl_eval_blocks order
         const long long ms = lm.slot_mp[cs];
         const int n = lm.gpr_m[ms];
         const DevKf &K = pk.kf[f];
@@ -541,6 +570,7 @@ k_linearize_gpr(const DevPack pk, const DevParams pr, const LmState lm, const Lm
             A.v[0] += 0.5 * rho0;
             A.v[40] += 1.0;
             A.v[39] += (double)nres;
+            int wrow = 0;
             for (int s = 0; s < C; ++s) {
                 if (!pk.covis_valid[f * C + s]) continue;
                 const float2 uv = pk.covis_uv[(K.kp_off + kp) * C + s];
@@ -549,9 +579,13 @@ k_linearize_gpr(const DevPack pk, const DevParams pr, const LmState lm, const Lm
                 D7 P1[3];
                 for (int i = 0; i < 3; ++i)
                     P1[i] = ((P0[0] * (double)rp[i * 4] + P0[1] * (double)rp[i * 4 + 1]) + P0[2] * (double)rp[i * 4 + 2]) + c.s * (double)rp[i * 4 + 3];
-                accumulate(A, ((P1[0] * fx) / P1[2] + cx) - (double)uv.x, sr);
-                accumulate(A, ((P1[1] * fy) / P1[2] + cy) - (double)uv.y, sr);
+                const D7 eu = ((P1[0] * fx) / P1[2] + cx) - (double)uv.x;
+                const D7 ev = ((P1[1] * fy) / P1[2] + cy) - (double)uv.y;
+                accumulate(A, eu, sr);
+                accumulate(A, ev, sr);
+                if (WB) { put_row(bo, gblk, wrow, eu); put_row(bo, gblk, wrow + 1, ev); wrow += 2; }
             }
+            if (WB) put_head(bo, gblk, 3, f, kp, nres);
         }
     }
     // per-CTA partial: only lane 0 of every warp holds data
@@ -660,7 +694,8 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
     return cudaSuccess;
 }
 
-cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st) {
+cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
+                         const BlockOut *blocks) {
     cudaError_t e;
     if (B > lm.cand_cap) {
         dfree(lm.d_cand);
@@ -689,10 +724,13 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
         TRY(cudaMalloc(&lm.partial, 8 * need));
         lm.partial_cap = need;
     }
-    k_linearize<<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride);
+    const BlockOut bo = blocks ? *blocks : BlockOut();
+    if (blocks) k_linearize<true><<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, bo);
+    else k_linearize<false><<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, bo);
     TRY(cudaGetLastError());
     if (gchunks > 0) {
-        k_linearize_gpr<<<dim3(gchunks, B), kGprWarps * 32, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, chunks);
+        if (blocks) k_linearize_gpr<true><<<dim3(gchunks, B), kGprWarps * 32, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, chunks, bo);
+        else k_linearize_gpr<false><<<dim3(gchunks, B), kGprWarps * 32, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, chunks, bo);
         TRY(cudaGetLastError());
     }
     k_lin_finish<<<B, 1024, 0, st>>>(lm.partial, stride, d_out);

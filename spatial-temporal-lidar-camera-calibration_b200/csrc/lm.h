@@ -51,6 +51,15 @@ void lm_free(LmState &lm);
 // wk must hold the K1 result (correspondences) of the association extrinsic at candidate slot 0.
 cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st);
 // x: HOST [B][7]; d_out: DEVICE [B][STL_LIN_NSUMS]
-cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st);
+// optional per-block output of a linearisation (device pointers; B must be 1)
+struct BlockOut {
+    int32_t *type = nullptr, *kf = nullptr, *kp = nullptr, *nres = nullptr;  // [n_blocks]
+    double *res = nullptr;  // [n_blocks][rmax]
+    double *jac = nullptr;  // [n_blocks][rmax][7]
+    int rmax = 0;
+};
+
+cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
+                         const BlockOut *blocks = nullptr);
 
 }  // namespace stl

@@ -96,6 +96,11 @@ class LMProblem:
             s = self.allreduce(s)
         return float(s[0, 0]), s[0, 1:8].copy(), s[0, 8:57].reshape(7, 7).copy()
 
+    def blocks(self, x):
+        """The residual blocks one by one (raw residuals + Jacobian rows, no robust kernel): what
+        ceres::CostFunction::Evaluate / g2o computeError + linearizeOplus return per block."""
+        return self.ctx.eval_blocks(x)
+
     def lm_step(self, x, lam: float):
         """One damped Gauss-Newton step on the raw 7 parameters (VertexSim3 oplus is '+')."""
         cost, g, H = self.evaluate(x)

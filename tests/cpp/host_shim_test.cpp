@@ -37,6 +37,12 @@ int main(int argc, char **argv) {
         auto nb = prob.build(&X[0]);
         stl_lin_sums_t L = prob.evaluate(&X[7]);
         std::printf("LM %lld %lld %lld %.17g %.17g %.17g\n", (long long)nb[0], (long long)nb[1], (long long)nb[2], L.cost, L.g[0], L.H[0]);
+        // per-block view (what a ceres::CostFunction / g2o edge returns): block count, first block, sum of squares
+        const stl::Context::Blocks B = prob.blocks(&X[7], 6);
+        double ss = 0;
+        for (size_t i = 0; i < B.size(); ++i)
+            for (int r = 0; r < B.n_res[i]; ++r) ss += B.residuals[i * B.rmax + r] * B.residuals[i * B.rmax + r];
+        std::printf("BLK %zu %d %d %d %.17g %.17g\n", B.size(), B.type[0], B.n_res[0], B.kp[0], B.residuals[0], ss);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "host shim: %s\n", e.what());
         stl_synth_destroy(S);

@@ -63,3 +63,7 @@ def test_cpp_shim_matches_ctypes_path(pkg, synth):
         lm = [ln for ln in r.stdout.splitlines() if ln.startswith("LM ")][0].split()
         assert [int(v) for v in lm[1:4]] == nb.tolist()[:3]
         assert (float(lm[4]), float(lm[5]), float(lm[6])) == (L[0], L[1], L[8])
+        Bk = ctx.eval_blocks(X[1], rmax=6)
+        blk = [ln for ln in r.stdout.splitlines() if ln.startswith("BLK ")][0].split()
+        assert int(blk[1]) == len(Bk["type"]) == nb.sum() and [int(v) for v in blk[2:5]] == [Bk["type"][0], Bk["n_res"][0], Bk["kp"][0]]
+        assert float(blk[5]) == Bk["residuals"][0, 0] and np.isclose(float(blk[6]), (Bk["residuals"] ** 2).sum(), rtol=1e-12)

@@ -97,3 +97,49 @@ def test_gpr_factor_blocks(pkg, oracle_mod, small_pack, small_candidates):
     sg = np.abs(want[:, 1:8]).max(axis=1, keepdims=True); sh = np.abs(want[:, 8:57]).max(axis=1, keepdims=True)
     assert np.allclose(got[:, 1:8], want[:, 1:8], rtol=1e-5, atol=1e-6 * sg)
     assert np.allclose(got[:, 8:57], want[:, 8:57], rtol=1e-5, atol=1e-6 * sh)
+
+
+@pytest.mark.parametrize("use_gpr", [0, 1])
+def test_per_block_residuals_and_jacobians(pkg, oracle_mod, small_pack, small_candidates, use_gpr):
+    """stl_eval_blocks: the per-block interface a Ceres CostFunction / g2o edge needs.  Every
+    frozen block is matched to the oracle's by (type, keyframe, keypoint); residuals and Jacobian rows agree,
+    padding rows are zero, and re-assembling the blocks with the Huber rule reproduces stl_linearize_batch."""
+    capi = importlib.import_module(PKG + ".capi")
+    p = pkg.default_params(); p.use_gpr = use_gpr
+    pack = small_pack[0].shard(0, 2)
+    orc = oracle_mod.Oracle(pack, params=p, kind="best")
+    x0, x = small_candidates[0], small_candidates[1]
+    nb_o, _ = orc.associate(x0)
+    keys = orc.block_keys()
+    with capi.Context(params=p) as c:
+        c.upload(pack)
+        assert np.array_equal(c.associate(x0), nb_o)
+        B = c.eval_blocks(x)
+        L = c.linearize(x)[0]
+        with pytest.raises(pkg._abi.StlError):
+            c.eval_blocks(x, rmax=2)
+    assert len(B["type"]) == len(keys) == nb_o.sum()
+    gpu_index = {(int(t), int(f), int(k)): i for i, (t, f, k) in enumerate(zip(B["type"], B["kf"], B["kp"]))}
+    assert len(gpu_index) == len(keys)
+    cost, g, H = 0.0, np.zeros(7), np.zeros((7, 7))
+    rng = np.random.default_rng(0)
+    check = set(rng.choice(len(keys), 400, replace=False).tolist()) | {i for i, k in enumerate(keys) if k[0] == 3}
+    for i, key in enumerate(keys):
+        j = gpu_index[tuple(int(v) for v in key)]
+        nr = int(B["n_res"][j])
+        e, J = B["residuals"][j], B["jacobians"][j]
+        assert not e[nr:].any() and not J[nr:].any()
+        if i in check:
+            eo, Jo = orc.block_eval(i, x)
+            assert len(eo) == nr
+            tol = 1e-5 if key[0] == 3 else 1e-9          # GPR: K is conditioned like 1e12 (DESIGN.md §K4b)
+            assert np.allclose(e[:nr], eo, rtol=tol, atol=1e-12) and np.allclose(J[:nr], Jo, rtol=tol, atol=tol * np.abs(Jo).max())
+        sq = float(e[:nr] @ e[:nr])
+        d = p.robust_kernel_delta if key[0] in (0, 3) else p.robust_kernel_3ddelta
+        if sq > d * d:                                    # ceres::HuberLoss + residual / Jacobian rescaling by sqrt(rho')
+            r = np.sqrt(sq); rho0 = 2 * d * r - d * d; sr = np.sqrt(d / r)
+        else:
+            rho0, sr = sq, 1.0
+        cost += 0.5 * rho0; g += sr * sr * (J[:nr].T @ e[:nr]); H += sr * sr * (J[:nr].T @ J[:nr])
+    assert np.isclose(cost, L[0], rtol=1e-10) and np.allclose(g, L[1:8], rtol=1e-8, atol=1e-8 * np.abs(g).max())
+    assert np.allclose(H, L[8:57].reshape(7, 7), rtol=1e-8, atol=1e-8 * np.abs(H).max())
