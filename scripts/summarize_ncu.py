@@ -37,12 +37,18 @@ def launches():
         k = short(r[ik])
         per.setdefault(k, []).append(v)
     tot = sum(sum(v) for v in per.values())
+    # one-off index build (stl_upload_pack) vs the kernels of the timed step
+    build = ("k_kd_refine", "k_leaf_adj", "k_leaf_aabb", "k_inner_aabb", "k_scatter", "k_morton", "k_bbox", "k_index_", "DeviceRadixSort", "at::")
+    is_build = lambda k: any(k.startswith(b) or b in k for b in build)
+    step_tot = sum(sum(v) for k, v in per.items() if not is_build(k)) or 1.0
     with open(os.path.join(P, f"{tag}_launches.txt"), "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  (python bench.py --steps 2 --warmup 1)\n")
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  (python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-plane-index --no-poll-batch)\n")
         f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
-        f.write(f"{'kernel':34s} {'launches':>8s} {'avg_us':>10s} {'total_us':>11s} {'share':>7s}\n")
+        f.write("# share = of everything the process launched; step% = of the kernels of the timed step (index build excluded)\n")
+        f.write(f"{'kernel':34s} {'launches':>8s} {'avg_us':>10s} {'total_us':>11s} {'share':>7s} {'step%':>7s}\n")
         for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
-            f.write(f"{k:34s} {len(v):8d} {sum(v)/len(v):10.1f} {sum(v):11.1f} {100*sum(v)/tot:6.1f}%\n")
+            sp = "      -" if is_build(k) else f"{100*sum(v)/step_tot:6.1f}%"
+            f.write(f"{k:34s} {len(v):8d} {sum(v)/len(v):10.1f} {sum(v):11.1f} {100*sum(v)/tot:6.1f}% {sp}\n")
     print("wrote", f"{tag}_launches.txt")
 
 
