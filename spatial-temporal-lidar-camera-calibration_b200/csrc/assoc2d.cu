@@ -290,6 +290,7 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
                 xn = ld_stream_f4(X + in); yn = ld_stream_f4(Y + in); zn = ld_stream_f4(Z + in);
             }
             const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, zs[4] = {z4.x, z4.y, z4.z, z4.w};
+            unsigned pm = 0;  // which of this lane's four points survive
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float zc = fmaf(mz0, xs[e], fmaf(mz1, ys[e], fmaf(mz2, zs[e], mz3)));
@@ -308,11 +309,29 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
                     // thin slab in front of the camera plane where the float32 bound does not hold: exact path decides
                     pass = fabsf(uz) <= S.ub_u && fabsf(vz) <= S.ub_v;
                 }
-                if (pass) {
-                    const int pos = atomicAdd(&S.n_surv, 1);
-                    if (pos < kSurvCap) T.surv[pos] = (uint32_t)(i * 4 + e);
-                    else S.overflow = 1;
+                pm |= (pass ? 1u : 0u) << e;
+            }
+            // one warp-aggregated append per group (a single shared-memory atomic instead of up to four
+            // dependent ones per lane)
+            if (__ballot_sync(0xffffffffu, pm != 0)) {
+                const int cnt = __popc(pm);
+                int inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
                 }
+                int base = 0;
+                if (lane == 31) base = atomicAdd(&S.n_surv, inc);
+                base = __shfl_sync(0xffffffffu, base, 31);
+                int pos = base + inc - cnt;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if ((pm >> e) & 1u) {
+                        if (pos < kSurvCap) T.surv[pos] = (uint32_t)(i * 4 + e);
+                        else S.overflow = 1;
+                        ++pos;
+                    }
             }
             w = wn; i = in; x4 = xn; y4 = yn; z4 = zn;
         }
