@@ -184,7 +184,7 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
         if (const char *e = getenv("STL_MAX_CHUNK")) cap = std::max(1, std::min(cap, atoi(e)));  // tests: force the multi-chunk path
         DevWork &w = ctx->wk;
         w.Bc = cap;
-        w.sub = 4;
+        w.sub = getenv("STL_SUB") ? std::max(1, std::min(16, atoi(getenv("STL_SUB")))) : 4;
         const size_t nk = (size_t)std::max<long long>(pk.n_kp_total, 1) * cap, nf = (size_t)pk.n_kf * cap;
         CK(cudaMalloc(&w.cand, sizeof(DevCand) * cap));
         CK(cudaMalloc(&w.corr_kp, 4 * nk)); CK(cudaMalloc(&w.corr_pt, 4 * nk)); CK(cudaMalloc(&w.corr_sp, 4 * nk)); CK(cudaMalloc(&w.q_corr, 4 * nk)); CK(cudaMalloc(&w.q_kpsp, 8 * nk));
