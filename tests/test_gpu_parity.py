@@ -190,24 +190,26 @@ def test_host_mirror_matches_reference_signatures(gpu_ctx, orc, small_candidates
     assert rows.shape == (len(small_candidates), 4) and np.isclose(rows[1, 3], fw[3] / fw[4])
 
 
-def test_large_shape_properties(pkg, synth):
-    """KITTI-00-shaped slice too large for a per-item oracle diff in seconds: size-independent
-    properties — batch == singles, shards add up, determinism, survivors never overflow."""
+@pytest.mark.parametrize("nkf,ncand", [(96, 5), (1500, 3)])
+def test_large_shape_properties(pkg, synth, nkf, ncand):
+    """Shapes too large for a per-item oracle diff in seconds — 1500 keyframes is BASELINE's full KITTI-00
+    shape (configs[1]): size-independent properties — batch == singles, keyframe shards add up, determinism,
+    every keyframe kept, the ground truth scores lowest."""
     capi = importlib.import_module(PKG + ".capi")
     par = importlib.import_module(PKG + ".parallel")
-    pack, x_gt, _ = synth.generate(n_kf=96, seed=77)
-    X = synth.candidates(x_gt, 5, 0.7)
+    pack, x_gt, _ = synth.generate(n_kf=nkf, seed=77)
+    X = synth.candidates(x_gt, ncand, 0.7)
     with capi.Context() as c:
         c.upload(pack)
         full = c.eval_sums(X)
         assert np.array_equal(full, c.eval_sums(X))
-        assert np.array_equal(c.eval_sums(X[3:4])[0], full[3])
-        assert (full[:, 10] == 96).all() and (full[:, 4] > 0).all()
+        assert np.array_equal(c.eval_sums(X[ncand - 2: ncand - 1])[0], full[ncand - 2])
+        assert (full[:, 10] == nkf).all() and (full[:, 4] > 0).all()
         f = [sum(c.finalize(r)[:2]) for r in full]
         assert int(np.argmin(f)) == 0  # the ground truth scores lowest (BALoss special points)
     acc = np.zeros_like(full)
     for r in range(3):
-        b, e = par.shard_bounds(96, 3, r)
+        b, e = par.shard_bounds(nkf, 3, r)
         with capi.Context() as c:
             c.upload(pack.shard(b, e))
             acc += c.eval_sums(X)
