@@ -138,7 +138,11 @@ def test_golden_fixtures(path, pkg):
     capi = importlib.import_module(PKG + ".capi")
     g = np.load(path)
     pack = pkg.KeyFramePack.from_npz_dict(g)
-    with capi.Context() as c:
+    params = pkg.default_params()
+    for key in g.files:                      # overrides stored with the fixture (stable variant, GPR factor)
+        if key.startswith("p_"):
+            setattr(params, key[2:], type(getattr(params, key[2:]))(g[key]))
+    with capi.Context(params=params) as c:
         c.upload(pack)
         got = c.eval_sums(g["X"])
         _check_sums(got, g["sums"])
@@ -155,6 +159,14 @@ def test_golden_fixtures(path, pkg):
                     assert np.allclose(a["dist"], g[f"b{b}_kf{kf}_align_dist"], rtol=1e-10, atol=1e-12)
                 else:
                     assert len(a["nn"]) == 0 and len(want_nn) == 0
+        if params.variant == 0:              # frozen LM problem and its linearisation
+            assert np.array_equal(c.associate(g["X"][0]), g["lm_nblocks"])
+            L = c.linearize(g["X"])
+            tol = 1e-6 if params.use_gpr else 1e-9   # GPR: conditioning of K
+            assert np.allclose(L[:, 0], g["lm_lin"][:, 0], rtol=tol) and np.array_equal(L[:, 57:], g["lm_lin"][:, 57:])
+            B = c.eval_blocks(g["X"][1])
+            keys = {tuple(int(v) for v in k) for k in g["lm_keys"]}
+            assert {(int(t), int(f), int(k)) for t, f, k in zip(B["type"], B["kf"], B["kp"])} == keys
 
 
 def test_api_error_behaviour(pkg, small_pack):
