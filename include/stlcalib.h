@@ -299,7 +299,9 @@ stl_status_t stl_stage_stats(stl_ctx_t *ctx, double ms[STL_NSTAGES], int64_t lau
 /* Work counters of the last stl_eval_batch (host-side, summed over b):
  * [0] points streamed by K1, [1] 2-D 1-NN queries (= keypoints),
  * [2] 3-D 1-NN queries, [3] 3-D k-NN queries, [4] algorithmic bytes of K1,
- * [5] kernels of this library launched by the context since its creation. */
+ * [5] kernels of this library launched by the context since its creation,
+ * [6] (candidate, keyframe) units whose K1 survivor list overflowed and that fell back to the exact
+ *     evaluation of every point (cumulative; 0 at the reference's 1.5 px association radius). */
 stl_status_t stl_work_counters(stl_ctx_t *ctx, double out[8]);
 
 #ifdef __cplusplus

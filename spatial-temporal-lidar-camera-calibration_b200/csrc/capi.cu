@@ -850,6 +850,11 @@ stl_status_t stl_work_counters(stl_ctx_t *ctx, double out[8]) {
     if (!ctx || !out) return STL_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->counters[5] = (double)ctx->launches;
+    if (ctx->wk.overflow) {  // units whose survivor list overflowed and took the exact-over-all-points path (cumulative)
+        int ov = 0;
+        cudaSetDevice(ctx->device);
+        if (cudaMemcpy(&ov, ctx->wk.overflow, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) ctx->counters[6] = (double)ov;
+    }
     memcpy(out, ctx->counters, sizeof(ctx->counters));
     return STL_OK;
 }

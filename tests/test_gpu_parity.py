@@ -431,3 +431,25 @@ def test_exact_ties_are_broken_by_original_index(oracle_mod, pkg, small_pack, sm
         assert np.array_equal(cg, co) and np.array_equal(ig, io) and np.array_equal(dg, do)
         nb_o, _ = orc.associate(x)
         assert np.array_equal(c.associate(x), nb_o)
+
+
+def test_survivor_and_match_list_overflow_fallbacks(oracle_mod, pkg, small_pack, small_candidates):
+    """A 4 px association radius makes the float32 pre-cull pass more points than K1's survivor list holds
+    (4096) and more matches than the tie-pass list (8192): the unit then evaluates EVERY point exactly and
+    resolves ties by recomputation.  Slow paths, same answers."""
+    capi = importlib.import_module(PKG + ".capi")
+    p = pkg.default_params(); p.max_pixel_dist = 4.0
+    pack = small_pack[0].shard(0, 2)
+    orc = oracle_mod.Oracle(pack, params=p, kind="best")
+    X = small_candidates[:2]
+    want, ties, _ = orc.ba_error_sums(X, mode=0)
+    assert ties.sum() == 0
+    with capi.Context(params=p) as c:
+        c.upload(pack)
+        got = c.eval_sums(X)
+        assert c.work_counters()["k1_overflow_units"] > 0       # the fallback really ran
+        _check_sums(got, want)
+        for b, f in ((0, 0), (1, 1)):
+            d = orc.frame_debug(X[b], f)
+            kp, pt = c.debug_corrset(b, f)
+            assert np.array_equal(kp, d["corr_kp"]) and np.array_equal(pt, d["corr_pt"])
