@@ -26,6 +26,10 @@
  *      src/examples/iba_local.cpp:263-309)
  *   g2o IBAPlaneEdge computeError/linearizeOplus       → stl_linearize_batch
  *     (include/IBACalib.hpp:74-155)
+ *   one LM iteration at x (BAError for monitoring +    → stl_step_batch (reassociate = 1)
+ *     BuildProblem + Evaluate, iba_local.cpp:434-446)
+ *   the OpenMP reductions of BAError across keyframes  → stl_comm_init: keyframes sharded over GPUs,
+ *     (iba_global.cpp:239-251,274-275,318-326)           one NCCL fp64 all-reduce per call
  */
 #ifndef STLCALIB_H_
 #define STLCALIB_H_
@@ -36,7 +40,7 @@
 extern "C" {
 #endif
 
-#define STL_ABI_VERSION 1
+#define STL_ABI_VERSION 2
 #define STL_MAX_COVIS 10 /* IBAPlaneEdge is fixed at <=10 covisible KFs (IBACalib.hpp:74) */
 
 typedef enum stl_status {
@@ -84,15 +88,16 @@ typedef struct stl_params {
      * scan point in stl_upload_pack.  The plane fit of ComputeAlignmentDist / BuildProblem is a pure
      * function of (scan, neighbour point, parameters) — it does not depend on the candidate — so it
      * can live in the index like the reference's KD-trees do; evaluations then only look it up.
-     * Costs ~36 B per point and a longer upload; results are identical. */
-    int32_t plane_index;          /* 0                                               */
+     * Costs ~36 B per point and a longer upload; results are identical.  On by default; 0 fits every
+     * plane at evaluation time (the reference's order of work). */
+    int32_t plane_index;          /* 1                                               */
     /* Which BAError the evaluation follows.  0 = src/examples/iba_global.cpp (default).
      * 1 = src/examples/iba_global_stable.cpp: the 2-D queries are the re-projected map points of the
      * keypoints that observe one (:67-80, computed at upload from kp_mappoint and Tcw), a projected
      * scan point is kept when its ROUNDED pixel is inside the image (:92-94), and ComputeAlignmentDist
      * gates on k < 3 before the fit and on the neighbourhood extent after it (:154,:163-171).
-     * stl_associate / stl_linearize_* (iba_local.cpp has no such variant) and plane_index are refused
-     * with variant 1. */
+     * stl_associate / stl_linearize_* are refused with variant 1 (iba_local.cpp has no such variant);
+     * plane_index works with both (the index is then fitted with the stable flavour's gates). */
     int32_t variant;              /* 0                                               */
 } stl_params_t;
 
@@ -176,6 +181,14 @@ typedef struct stl_lin_sums {
 } stl_lin_sums_t;
 #define STL_LIN_NSUMS 62
 
+/* One LM iteration's worth of results for one parameter vector: the BAError accumulators followed by the
+ * linearisation, contiguous so that ONE all-reduce covers both (stl_step_batch). */
+typedef struct stl_step_sums {
+    stl_eval_sums_t eval;
+    stl_lin_sums_t lin;
+} stl_step_sums_t;
+#define STL_STEP_NSUMS (STL_EVAL_NSUMS + STL_LIN_NSUMS) /* 74 */
+
 typedef struct stl_ctx stl_ctx_t;
 
 /* ---- life cycle ------------------------------------------------------- */
@@ -224,7 +237,11 @@ void stl_bbo(const stl_params_t *params, const stl_ba_error_t *e, double bbo[4])
 
 /* BuildProblem (iba_local.cpp:145-323): associates at x0[7] and freezes the
  * residual blocks (plane / point-to-point / point-to-plane) on the device.
- * n_blocks[4] (optional) receives the block counts {plane 2d, pt, pl, gpr 2d} of this pack. */
+ * n_blocks[4] receives the block counts {plane 2d, pt, pl, gpr 2d} of this pack; passing NULL makes the
+ * call asynchronous (nothing waits on the host; stl_block_counts fetches the numbers later).
+ * When x0 is bitwise one of the candidates of the immediately preceding stl_eval_batch, its 2-D
+ * correspondences are reused instead of streaming the scans a second time (the reference evaluates
+ * BAError(x) and BuildProblem(x) back to back at the same x, iba_global.cpp:201 / iba_local.cpp:191). */
 stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[4]);
 
 /* Evaluates the frozen blocks at B parameter vectors: cost, J^T r, J^T J
@@ -244,6 +261,39 @@ stl_status_t stl_linearize_batch_device(stl_ctx_t *ctx, const double *x, int32_t
  * order.  All buffers are host memory sized for `cap_blocks`; *n_blocks_out receives the count. */
 stl_status_t stl_eval_blocks(stl_ctx_t *ctx, const double *x, int32_t rmax, int64_t cap_blocks, int32_t *type, int32_t *kf,
                              int32_t *kp, int32_t *n_res, double *residuals, double *jacobians, int64_t *n_blocks_out);
+
+/* Block counts {plane 2d, pt, pl, gpr 2d} of the last association of this context (waits for it). */
+stl_status_t stl_block_counts(stl_ctx_t *ctx, int64_t n_blocks[4]);
+
+/* BAError + (optionally) BuildProblem + linearisation in one call — what one LM / g2o iteration at x asks
+ * for (iba_local.cpp:434-446 with the BAError value iba_global.cpp:169 logged beside it), or, for a NOMAD
+ * poll batch, the cost record and the normal equations of every candidate on the frozen association:
+ *   1. the BAError sums of x[0..B)                                        (as stl_eval_batch)
+ *   2. reassociate != 0: BuildProblem at x[0], REUSING the 2-D association step 1 just computed for it
+ *      (FindProjectCorrespondences at the same extrinsic, iba_global.cpp:201 == iba_local.cpp:191)
+ *   3. cost, J^T r, J^T J of the frozen blocks at x[0..B)                  (as stl_linearize_batch)
+ * Nothing waits on the host between the stages; with a communicator attached the [B][74] record is
+ * all-reduced ONCE.  out[b] = {eval sums, linearisation} of candidate b. */
+stl_status_t stl_step_batch(stl_ctx_t *ctx, const double *x, int32_t B, int32_t reassociate, stl_step_sums_t *out);
+/* Same; the [B][STL_STEP_NSUMS] record stays in DEVICE memory `d_out` on `stream`, no synchronisation. */
+stl_status_t stl_step_batch_device(stl_ctx_t *ctx, const double *x, int32_t B, int32_t reassociate, double *d_out, void *stream);
+
+/* ---- multi-GPU: keyframes sharded over the GPUs of a node -----------------------------
+ * One process (or thread) per GPU, each with its own context holding a contiguous block of keyframes
+ * (stl_pack_t.n_kf = this rank's shard; covisible data is baked per keyframe, so there is no halo).
+ * The only exchange of the path is the sum the reference forms over keyframes
+ * (iba_global.cpp:239-251,274-275,318-326): once a communicator is attached, stl_eval_batch,
+ * stl_linearize_batch, stl_step_batch and their _device twins finish with ONE ncclAllReduce(sum, fp64) of
+ * the [B][12 | 62 | 74] record on the compute stream, and every rank returns the totals.  Every rank must
+ * make the same calls with the same x and B.  stl_associate / stl_block_counts report this rank's blocks. */
+#define STL_COMM_ID_BYTES 128
+/* ncclGetUniqueId: called by one rank; the bytes are handed to the others by the host program (MPI,
+ * torch.distributed, a file ...) before stl_comm_init. */
+stl_status_t stl_comm_unique_id(uint8_t id[STL_COMM_ID_BYTES]);
+/* ncclCommInitRank on the context's device; the context owns the communicator (stl_destroy releases it). */
+stl_status_t stl_comm_init(stl_ctx_t *ctx, const uint8_t id[STL_COMM_ID_BYTES], int32_t rank, int32_t n_ranks);
+/* rank / size of the attached communicator (0 / 1 when none). */
+stl_status_t stl_comm_info(stl_ctx_t *ctx, int32_t *rank, int32_t *n_ranks);
 
 /* ---- debug getters (parity tests only) --------------------------------- */
 
@@ -282,6 +332,9 @@ stl_status_t stl_knn3d(stl_ctx_t *ctx, int32_t kf, const double *q, int32_t nq, 
 #define STL_STAGE_REDUCE 2   /* K3 per-candidate reduction                    */
 #define STL_STAGE_LINEARIZE 3
 #define STL_STAGE_BUILD 4    /* one-off index build of stl_upload_pack        */
+#define STL_STAGE_ASSOC_LM 5 /* BuildProblem kernels of stl_associate / stl_step_batch */
+#define STL_STAGE_ALLREDUCE 6 /* the NCCL all-reduce of the record (communicator attached) */
+#define STL_STAGE_PLANE_INDEX 7 /* plane index part of the build (params.plane_index)  */
 #define STL_NSTAGES 8
 
 /* Sets the CUDA stream (a cudaStream_t) on which the calls WITHOUT an explicit stream argument
@@ -301,7 +354,8 @@ stl_status_t stl_stage_stats(stl_ctx_t *ctx, double ms[STL_NSTAGES], int64_t lau
  * [2] 3-D 1-NN queries, [3] 3-D k-NN queries, [4] algorithmic bytes of K1,
  * [5] kernels of this library launched by the context since its creation,
  * [6] (candidate, keyframe) units whose K1 survivor list overflowed and that fell back to the exact
- *     evaluation of every point (cumulative; 0 at the reference's 1.5 px association radius). */
+ *     evaluation of every point (cumulative; 0 at the reference's 1.5 px association radius),
+ * [7] associations that reused the 2-D correspondences of a preceding evaluation at the same x (cumulative). */
 stl_status_t stl_work_counters(stl_ctx_t *ctx, double out[8]);
 
 #ifdef __cplusplus

@@ -43,6 +43,7 @@ _SYMS = {
     "orc_knn3d": (None, [_vp, C.c_int, _dp, C.c_int, C.c_int, C.c_double, C.c_int, _u32p, _dp, _i32p, _i64p]),
     "orc_associate": (None, [_vp, _dp, C.c_int, _i64p, _i64p]),
     "orc_linearize": (None, [_vp, _dp, C.c_int, C.POINTER(_abi.LinSums)]),
+    "orc_linearize_mt": (None, [_vp, _dp, C.c_int, C.c_int, C.POINTER(_abi.LinSums)]),
     "orc_num_blocks": (C.c_int64, [_vp]),
     "orc_block_key": (None, [_vp, C.c_int64, _i32p]),
     "orc_block_eval": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp]),
@@ -198,12 +199,17 @@ class Oracle:
         nr = self.lib.orc_block_eval(self.h, i, _d(x), _d(e), _d(J))
         return e[:nr], J[:nr]
 
-    def linearize(self, x):
-        """x: [B,7] -> list of dict(cost, g[7], H[7,7], n_blocks_*, n_residuals)."""
+    def linearize(self, x, nthreads: int = 1):
+        """x: [B,7] -> [B,62] rows (cost, g[7], H[7,7], n_blocks_*, n_residuals).  nthreads = 1: one accumulator in
+        block order (the goldens' order); otherwise the residual blocks of each x are evaluated by `nthreads`
+        threads (0 = all), as Ceres does with options.num_threads (iba_local.cpp:439)."""
         x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
         B = x.shape[0]
         out = (_abi.LinSums * B)()
-        self.lib.orc_linearize(self.h, _d(x), B, out)
+        if nthreads == 1:
+            self.lib.orc_linearize(self.h, _d(x), B, out)
+        else:
+            self.lib.orc_linearize_mt(self.h, _d(x), B, nthreads, out)
         return np.frombuffer(out, dtype=np.float64).reshape(B, _abi.STL_LIN_NSUMS).copy()
 
 

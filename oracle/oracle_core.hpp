@@ -20,6 +20,7 @@
 // order and g2o's SE3Quat::log are restated from their published sources and
 // are "parity unpinned" (see DESIGN.md §Oracle).
 #pragma once
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -664,12 +665,13 @@ class Oracle {
 
     // Evaluate all frozen blocks at x: Huber-corrected cost, g = J^T r, H = J^T J
     // (Ceres Corrector with rho'' <= 0: residual and Jacobian scaled by sqrt(rho'); A16).
-    void linearize(const double x[7], stl_lin_sums_t *out) const {
-        std::memset(out, 0, sizeof(*out));
+    // Adds blocks [i0, i1) into *out in block order.
+    void linearize_range(const double x[7], size_t i0, size_t i1, stl_lin_sums_t *out) const {
         typedef Dual<7> D;
         D xd[7];
         for (int i = 0; i < 7; ++i) xd[i] = D::var(x[i], i);
-        for (const Block &b : blocks_) {
+        for (size_t bi = i0; bi < i1; ++bi) {
+            const Block &b = blocks_[bi];
             D e[2 * STL_MAX_COVIS];
             const int nr = block_residuals<D>(b, xd, e);
             double sq = 0;
@@ -691,6 +693,32 @@ class Oracle {
             }
             out->n_residuals += nr;
             if (b.type == 0) out->n_blocks_2d += 1; else if (b.type == 1) out->n_blocks_pt += 1; else if (b.type == 2) out->n_blocks_pl += 1; else out->n_blocks_gpr += 1;
+        }
+    }
+
+    // serial, one accumulator in block order (the order the golden vectors were written in)
+    void linearize(const double x[7], stl_lin_sums_t *out) const {
+        std::memset(out, 0, sizeof(*out));
+        linearize_range(x, 0, blocks_.size(), out);
+    }
+
+    // Residual blocks evaluated by `nthreads` threads, as ceres::Problem::Evaluate does with
+    // options.num_threads = hardware_concurrency() (iba_local.cpp:439).  Fixed chunks of 256 blocks, partials
+    // added in chunk order: the result does not depend on the thread count (it differs from the serial
+    // order above only by the re-association of the fp64 sums).
+    void linearize_mt(const double x[7], int nthreads, stl_lin_sums_t *out) const {
+        const size_t nb = blocks_.size(), chunk = 256, nc = (nb + chunk - 1) / chunk;
+        std::vector<stl_lin_sums_t> part(nc);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads > 0 ? nthreads : nthreads_)
+        for (long long c = 0; c < (long long)nc; ++c) {
+            std::memset(&part[c], 0, sizeof(stl_lin_sums_t));
+            linearize_range(x, (size_t)c * chunk, std::min(nb, (size_t)(c + 1) * chunk), &part[c]);
+        }
+        std::memset(out, 0, sizeof(*out));
+        double *o = reinterpret_cast<double *>(out);
+        for (size_t c = 0; c < nc; ++c) {
+            const double *p = reinterpret_cast<const double *>(&part[c]);
+            for (int i = 0; i < STL_LIN_NSUMS; ++i) o[i] += p[i];
         }
     }
 

@@ -14,8 +14,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 STL_MAX_COVIS = 10
 STL_EVAL_NSUMS = 12
 STL_LIN_NSUMS = 62
+STL_STEP_NSUMS = STL_EVAL_NSUMS + STL_LIN_NSUMS
+STL_COMM_ID_BYTES = 128
 STL_NSTAGES = 8
-STAGE_NAMES = ("assoc2d", "knn3d", "reduce", "linearize", "build", "assoc_lm", "s6", "s7")
+STAGE_NAMES = ("assoc2d", "knn3d", "reduce", "linearize", "build", "assoc_lm", "allreduce", "plane_index")
 
 STATUS = {0: "STL_OK", 1: "STL_ERR_INVALID", 2: "STL_ERR_CUDA", 3: "STL_ERR_NO_DEVICE",
           4: "STL_ERR_STATE", 5: "STL_ERR_CAPACITY"}
@@ -94,6 +96,10 @@ class LinSums(C.Structure):
                 ("n_blocks_pl", C.c_double), ("n_residuals", C.c_double), ("n_blocks_gpr", C.c_double)]
 
 
+class StepSums(C.Structure):
+    _fields_ = [("eval", EvalSums), ("lin", LinSums)]
+
+
 class SynthCfg(C.Structure):
     _fields_ = [
         ("n_kf", C.c_int32), ("kf_begin", C.c_int32), ("n_kf_total", C.c_int32),
@@ -129,6 +135,12 @@ CALIB_SYMBOLS = {
     "stl_linearize_batch": (C.c_int, [_vp, _dp, C.c_int32, C.POINTER(LinSums)]),
     "stl_linearize_batch_device": (C.c_int, [_vp, _dp, C.c_int32, _vp, _vp]),
     "stl_eval_blocks": (C.c_int, [_vp, _dp, C.c_int32, C.c_int64, _i32p, _i32p, _i32p, _i32p, _dp, _dp, C.POINTER(C.c_int64)]),
+    "stl_block_counts": (C.c_int, [_vp, _i64p]),
+    "stl_step_batch": (C.c_int, [_vp, _dp, C.c_int32, C.c_int32, C.POINTER(StepSums)]),
+    "stl_step_batch_device": (C.c_int, [_vp, _dp, C.c_int32, C.c_int32, _vp, _vp]),
+    "stl_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "stl_comm_init": (C.c_int, [_vp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]),
+    "stl_comm_info": (C.c_int, [_vp, _i32p, _i32p]),
     "stl_debug_corrset": (C.c_int, [_vp, C.c_int32, C.c_int32, _u32p, _u32p, C.c_int32, _i32p]),
     "stl_debug_align": (C.c_int, [_vp, C.c_int32, C.c_int32, _u32p, _u32p, _i32p, _i32p, _dp, _u32p,
                                   C.c_int32, _i32p]),

@@ -87,12 +87,58 @@ class Context:
         return tuple(out)
 
     # -- LM path -------------------------------------------------------------
-    def associate(self, x0):
+    def associate(self, x0, wait: bool = True):
+        """BuildProblem at x0.  wait=False enqueues only (block counts through :meth:`block_counts` later)."""
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        if not wait:
+            _check(self.lib, self.h, self.lib.stl_associate(self.h, x0.ctypes.data_as(_dp), None))
+            self.n_blocks = None
+            return None
         nb = np.zeros(4, np.int64)
         _check(self.lib, self.h, self.lib.stl_associate(self.h, x0.ctypes.data_as(_dp), nb.ctypes.data_as(_abi._i64p)))
         self.n_blocks = nb.copy()
         return nb
+
+    def block_counts(self):
+        nb = np.zeros(4, np.int64)
+        _check(self.lib, self.h, self.lib.stl_block_counts(self.h, nb.ctypes.data_as(_abi._i64p)))
+        self.n_blocks = nb.copy()
+        return nb
+
+    def step(self, x, reassociate: bool = True) -> np.ndarray:
+        """BAError sums + (BuildProblem at x[0]) + linearisation of x [B,7] in one call -> [B,74] (host):
+        columns 0..11 the evaluation sums, 12..73 the linearisation record."""
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        B = x.shape[0]
+        out = np.empty((B, _abi.STL_STEP_NSUMS), dtype=np.float64)
+        _check(self.lib, self.h, self.lib.stl_step_batch(self.h, x.ctypes.data_as(_dp), B, int(reassociate),
+                                                         out.ctypes.data_as(C.POINTER(_abi.StepSums))))
+        self.n_blocks = None
+        return out
+
+    def step_device(self, x, d_out_ptr: int, stream_ptr: int = 0, reassociate: bool = True):
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        _check(self.lib, self.h, self.lib.stl_step_batch_device(self.h, x.ctypes.data_as(_dp), x.shape[0], int(reassociate),
+                                                                C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr)))
+        self.n_blocks = None
+
+    # -- multi-GPU -------------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        """ncclGetUniqueId (call on one rank, hand the bytes to the others)."""
+        buf = (C.c_uint8 * _abi.STL_COMM_ID_BYTES)()
+        _check(self.lib, self.h, self.lib.stl_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes, rank: int, n_ranks: int):
+        """Attach an NCCL communicator: this context holds keyframe shard `rank` of `n_ranks`; every
+        evaluation / linearisation / step then returns the all-reduced totals."""
+        buf = (C.c_uint8 * _abi.STL_COMM_ID_BYTES).from_buffer_copy(uid)
+        _check(self.lib, self.h, self.lib.stl_comm_init(self.h, buf, rank, n_ranks))
+
+    def comm_info(self):
+        r, n = C.c_int32(0), C.c_int32(1)
+        _check(self.lib, self.h, self.lib.stl_comm_info(self.h, C.byref(r), C.byref(n)))
+        return r.value, n.value
 
     def linearize(self, x) -> np.ndarray:
         x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
@@ -114,7 +160,9 @@ class Context:
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(7)
         ncov = int(self.pack.n_covis) if self.pack is not None else _abi.STL_MAX_COVIS
         rmax = int(rmax) if rmax else max(3, 2 * ncov)
-        nb = int(self.n_blocks.sum()) if getattr(self, "n_blocks", None) is not None else 0
+        if getattr(self, "n_blocks", None) is None:
+            self.block_counts()
+        nb = int(self.n_blocks.sum())
         cap = max(nb, 1)
         out = dict(type=np.zeros(cap, np.int32), kf=np.zeros(cap, np.int32), kp=np.zeros(cap, np.int32), n_res=np.zeros(cap, np.int32),
                    residuals=np.zeros((cap, rmax)), jacobians=np.zeros((cap, rmax, 7)))
@@ -186,4 +234,5 @@ class Context:
     def work_counters(self):
         out = np.zeros(8)
         _check(self.lib, self.h, self.lib.stl_work_counters(self.h, out.ctypes.data_as(_dp)))
-        return dict(points=out[0], q2d=out[1], q3d_nn=out[2], q3d_knn=out[3], k1_bytes=out[4], launches=out[5], k1_overflow_units=out[6])
+        return dict(points=out[0], q2d=out[1], q3d_nn=out[2], q3d_knn=out[3], k1_bytes=out[4], launches=out[5], k1_overflow_units=out[6],
+                    assoc_reused=out[7])

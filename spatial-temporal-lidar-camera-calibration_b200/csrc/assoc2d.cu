@@ -18,6 +18,8 @@
 // keypoints staged in shared memory) and min-reduced per keypoint with (distance, original
 // index) order — the KD-tree 1-NN + threshold whenever no exact distance tie exists.
 // Bound: HBM for the stream, latency for the exact part.
+#include <mutex>
+
 #include "kernels.h"
 #include "se3.cuh"
 
@@ -480,6 +482,8 @@ size_t assoc2d_smem_bytes(int max_kp, int max_bm_words, int max_cells, int max_g
 // context of the process: only ever raise it.
 cudaError_t assoc2d_configure(size_t smem) {
     static size_t granted[64] = {0};
+    static std::mutex mu;  // contexts of different devices / threads share this table
+    std::lock_guard<std::mutex> lk(mu);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;

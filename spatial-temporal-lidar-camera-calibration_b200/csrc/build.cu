@@ -348,9 +348,10 @@ k_leaf_adj(const DevKf *__restrict__ kf, int kf_begin, const float4 *__restrict_
 }  // namespace
 
 cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int nkf, int kf_begin, const DevKf *h_kf, DevPack &pack,
-                             float adj_r2, cudaStream_t st) {
+                             float adj_r2, cudaStream_t st, float *kernel_ms) {
     const long long n = h_raw_off[nkf] - h_raw_off[0];
     cudaError_t err = cudaSuccess;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // device time of the build kernels alone (no allocation, no H2D copy)
     long long *d_off = nullptr;
     float *d_bbox = nullptr;
     unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
@@ -376,14 +377,22 @@ cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int
         STL_TRY(cudaMalloc(&d_vals, sizeof(uint32_t) * n));
         STL_TRY(cudaMalloc(&d_vals2, sizeof(uint32_t) * n));
     }
+    if (n > 0) {  // the sort scratch is sized before the timed part
+        int kf_bits0 = 1;
+        while ((1 << kf_bits0) < nkf) ++kf_bits0;
+        STL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, 48 + kf_bits0, st));
+        STL_TRY(cudaMalloc(&d_tmp, tmp_bytes));
+    }
+    if (kernel_ms) {
+        STL_TRY(cudaEventCreate(&ev0)); STL_TRY(cudaEventCreate(&ev1));
+        STL_TRY(cudaEventRecord(ev0, st));
+    }
     k_bbox<<<nkf, 512, 0, st>>>(d_raw, d_off, d_bbox, pack.kf, kf_begin);
     if (n > 0) {
         const int tiles = (max_pad + 256 * 8 - 1) / (256 * 8);
         k_morton<<<dim3(tiles, nkf), 256, 0, st>>>(d_raw, d_off, d_bbox, d_keys, d_vals);
         int kf_bits = 1;
         while ((1 << kf_bits) < nkf) ++kf_bits;
-        STL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, 48 + kf_bits, st));
-        STL_TRY(cudaMalloc(&d_tmp, tmp_bytes));
         STL_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, 48 + kf_bits, st));
     }
     {
@@ -407,9 +416,17 @@ cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int
                                                                     adj_r2 * (getenv("STL_ADJ_TRUNC") ? (float)atof(getenv("STL_ADJ_TRUNC")) : 1.f / 9.f));
     }
     STL_TRY(cudaGetLastError());
+    if (kernel_ms) STL_TRY(cudaEventRecord(ev1, st));
     STL_TRY(cudaStreamSynchronize(st));
+    if (kernel_ms) {
+        float ms = 0.f;
+        STL_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
+        *kernel_ms += ms;
+    }
 #undef STL_TRY
 done:
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
     free(h_rel);
     cudaFree(d_off); cudaFree(d_bbox); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_tmp);
     return err;

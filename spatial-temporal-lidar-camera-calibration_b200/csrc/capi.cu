@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 
+#include <nccl.h>
+
 #include "../../include/stlcalib.h"
 #include "hostmath.hpp"
 #include "kernels.h"
@@ -49,11 +51,17 @@ struct stl_ctx {
     cudaEvent_t h2d_done = nullptr;  // pinned candidate staging is reused only after its copies completed
     std::vector<double> last_x;
     int dbg_b = -1;
+    // which candidates' K1 results (correspondences, query lists) the workspace holds right now: rows of x, in slot order
+    std::vector<double> wk_x;
+    long long assoc_reused = 0;
+    // multi-GPU: keyframes sharded over the ranks of this communicator (owned)
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
     // LM path
     LmState lm;
     double *d_lin = nullptr;
     double *h_lin = nullptr;
-    int lin_cap = 0;
+    long long lin_cap = 0;  // doubles
     // profiling
     bool profiling = false;
     struct Ev { cudaEvent_t a, b; int stage; };
@@ -173,6 +181,9 @@ void drain_events(stl_ctx *c) {
     c->evs.clear();
 }
 
+// Workspace of one candidate chunk.  Allocation is all-or-nothing: a failure midway frees what was
+// obtained and leaves wk_cap == 0, so the next call starts over instead of using half a workspace.
+// The counters are cleared on the stream the context last used (any later stream waits for it).
 stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
     const DevPack &pk = ctx->pk;
     if (ctx->wk_cap == 0) {
@@ -186,38 +197,57 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
         w.Bc = cap;
         w.sub = getenv("STL_SUB") ? std::max(1, std::min(16, atoi(getenv("STL_SUB")))) : 4;
         const size_t nk = (size_t)std::max<long long>(pk.n_kp_total, 1) * cap, nf = (size_t)pk.n_kf * cap;
-        CK(cudaMalloc(&w.cand, sizeof(DevCand) * cap));
-        CK(cudaMalloc(&w.corr_kp, 4 * nk)); CK(cudaMalloc(&w.corr_pt, 4 * nk)); CK(cudaMalloc(&w.corr_sp, 4 * nk)); CK(cudaMalloc(&w.q_corr, 4 * nk)); CK(cudaMalloc(&w.q_kpsp, 8 * nk));
-        CK(cudaMalloc(&w.n_corr, 4 * nf)); CK(cudaMalloc(&w.n_q, 4 * nf));
-        CK(cudaMalloc(&w.k1_match, sizeof(ulonglong2) * 8192 * nf));
-        CK(cudaMalloc(&w.frame, sizeof(FrameRec) * nf)); CK(cudaMalloc(&w.align, sizeof(AlignRec) * nf * w.sub));
-        {
-            const size_t nm = (size_t)std::max<long long>(pk.n_mp_total, 1) * cap;
-            CK(cudaMalloc(&w.nn_pos, 4 * nm)); CK(cudaMalloc(&w.nb, 4 * nm * kMaxK)); CK(cudaMalloc(&w.nbx, sizeof(float4) * nm * kMaxK)); w.nbx_stride = (long long)nm; CK(cudaMalloc(&w.nb_m, 4 * nm)); CK(cudaMalloc(&w.nb_last, 8 * nm));
+        const size_t nm = (size_t)std::max<long long>(pk.n_mp_total, 1) * cap;
+        auto alloc_all = [&]() -> cudaError_t {
+            cudaError_t e;
+#define A_(p, bytes) do { e = cudaMalloc(&(p), (bytes)); if (e != cudaSuccess) return e; } while (0)
+            A_(w.cand, sizeof(DevCand) * cap);
+            A_(w.corr_kp, 4 * nk); A_(w.corr_pt, 4 * nk); A_(w.corr_sp, 4 * nk); A_(w.q_corr, 4 * nk); A_(w.q_kpsp, 8 * nk);
+            A_(w.n_corr, 4 * nf); A_(w.n_q, 4 * nf);
+            A_(w.k1_match, sizeof(ulonglong2) * 8192 * nf);
+            A_(w.frame, sizeof(FrameRec) * nf); A_(w.align, sizeof(AlignRec) * nf * w.sub);
+            A_(w.nn_pos, 4 * nm); A_(w.nb, 4 * nm * kMaxK); A_(w.nbx, sizeof(float4) * nm * kMaxK); A_(w.nb_m, 4 * nm); A_(w.nb_last, 8 * nm);
+            w.nbx_stride = (long long)nm;
+            if (getenv("STL_K1_CLK")) { A_(w.k1_clk, 64 * nf); e = cudaMemsetAsync(w.k1_clk, 0, 64 * nf, ctx->last_stream); if (e != cudaSuccess) return e; }
+            A_(w.overflow, 4);
+#undef A_
+            return cudaMemsetAsync(w.overflow, 0, 4, ctx->last_stream);
+        };
+        const cudaError_t e = alloc_all();
+        if (e != cudaSuccess) {
+            free_work(ctx);
+            return fail(ctx, STL_ERR_CUDA, "workspace allocation: %s", cudaGetErrorString(e));
         }
-        if (getenv("STL_K1_CLK")) { CK(cudaMalloc(&w.k1_clk, 64 * nf)); CK(cudaMemset(w.k1_clk, 0, 64 * nf)); }
-        CK(cudaMalloc(&w.overflow, 4));
-        CK(cudaMemset(w.overflow, 0, 4));
         ctx->wk_cap = cap;
     }
     if (debug && !ctx->dbg_alloc) {
         DevWork &w = ctx->wk;
         const size_t nk = (size_t)std::max<long long>(pk.n_kp_total, 1);
-        CK(cudaMalloc(&w.dbg_nn, 4 * nk)); CK(cudaMalloc(&w.dbg_m, 4 * nk)); CK(cudaMalloc(&w.dbg_plane, 4 * nk));
-        CK(cudaMalloc(&w.dbg_dist, 8 * nk)); CK(cudaMalloc(&w.dbg_knn, 4 * nk * kMaxK));
-        CK(cudaMalloc(&w.dbg_stats, 64)); CK(cudaMemset(w.dbg_stats, 0, 64));
+        cudaError_t e = cudaMalloc(&w.dbg_nn, 4 * nk);
+        if (e == cudaSuccess) e = cudaMalloc(&w.dbg_m, 4 * nk);
+        if (e == cudaSuccess) e = cudaMalloc(&w.dbg_plane, 4 * nk);
+        if (e == cudaSuccess) e = cudaMalloc(&w.dbg_dist, 8 * nk);
+        if (e == cudaSuccess) e = cudaMalloc(&w.dbg_knn, 4 * nk * kMaxK);
+        if (e == cudaSuccess) e = cudaMalloc(&w.dbg_stats, 64);
+        if (e == cudaSuccess) e = cudaMemsetAsync(w.dbg_stats, 0, 64, ctx->last_stream);
+        if (e != cudaSuccess) {
+            dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn); dfree(w.dbg_stats);
+            return fail(ctx, STL_ERR_CUDA, "debug workspace allocation: %s", cudaGetErrorString(e));
+        }
         ctx->dbg_alloc = true;
     }
     if (B > ctx->h_cap) {
         if (ctx->h_cand) cudaFreeHost(ctx->h_cand);
         if (ctx->h_sums) cudaFreeHost(ctx->h_sums);
         ctx->h_cand = nullptr; ctx->h_sums = nullptr;
+        ctx->h_cap = 0;
         CK(cudaMallocHost(&ctx->h_cand, sizeof(DevCand) * B));
         CK(cudaMallocHost(&ctx->h_sums, sizeof(double) * STL_EVAL_NSUMS * B));
         ctx->h_cap = B;
     }
     if (B > ctx->d_sums_cap) {
         dfree(ctx->d_sums);
+        ctx->d_sums_cap = 0;
         CK(cudaMalloc(&ctx->d_sums, sizeof(double) * STL_EVAL_NSUMS * B));
         ctx->d_sums_cap = B;
     }
@@ -225,7 +255,7 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
 }
 
 // Enqueues the evaluation of B candidates; d_out [B][STL_EVAL_NSUMS] device.
-stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, cudaStream_t st, bool debug) {
+stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, cudaStream_t st, bool debug, int out_stride = STL_EVAL_NSUMS) {
     stl_status_t s = ensure_work(ctx, B, debug);
     if (s != STL_OK) return s;
     if (!ctx->h2d_done) CK(cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming));
@@ -237,8 +267,9 @@ stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, c
         CK(cudaMemcpyAsync(ctx->wk.cand, ctx->h_cand + c0, sizeof(DevCand) * nb, cudaMemcpyHostToDevice, st));
         { StageTimer t(ctx, STL_STAGE_ASSOC2D, st); CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_smem, st)); }
         { StageTimer t(ctx, STL_STAGE_KNN3D, st); CK(launch_align3d(ctx->pk, ctx->wk, ctx->dpr, nb, debug ? 1 : 0, st)); }
-        { StageTimer t(ctx, STL_STAGE_REDUCE, st); CK(launch_reduce(ctx->pk, ctx->wk, ctx->dpr, nb, d_out + (size_t)c0 * STL_EVAL_NSUMS, st)); }
+        { StageTimer t(ctx, STL_STAGE_REDUCE, st); CK(launch_reduce(ctx->pk, ctx->wk, ctx->dpr, nb, d_out + (size_t)c0 * out_stride, st, out_stride)); }
         ctx->launches += 4;  // K1, K2a, K2b, K3
+        ctx->wk_x.assign(x + (size_t)c0 * 7, x + (size_t)(c0 + nb) * 7);
     }
     CK(cudaEventRecord(ctx->h2d_done, st));
     ctx->counters[0] = (double)ctx->n_pts_total * B;
@@ -246,6 +277,52 @@ stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, c
     ctx->counters[4] = ((double)ctx->n_pts_total * 12.0 + (double)ctx->pk.n_kp_total * 16.0) * B;
     ctx->last_x.assign(x, x + (size_t)B * 7);
     ctx->dbg_b = -1;
+    return STL_OK;
+}
+
+// The one exchange of the path: fp64 sum of the per-candidate record over the keyframe shards, in place, on the
+// compute stream (iba_global.cpp:239-251,274-275,318-326 are the sums it completes).
+stl_status_t allreduce_record(stl_ctx *ctx, double *d_buf, size_t count, cudaStream_t st) {
+    if (!ctx->comm || ctx->comm_size <= 1) return STL_OK;
+    StageTimer t(ctx, STL_STAGE_ALLREDUCE, st);
+    const ncclResult_t r = ncclAllReduce(d_buf, d_buf, count, ncclDouble, ncclSum, ctx->comm, st);
+    if (r != ncclSuccess) return fail(ctx, STL_ERR_CUDA, "ncclAllReduce: %s", ncclGetErrorString(r));
+    return STL_OK;
+}
+
+// Enqueues BuildProblem at x0 on `st`.  The 2-D association (FindProjectCorrespondences) is taken from the
+// workspace when the preceding evaluation left the correspondences of exactly this x0 there, else K1 runs.
+stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st) {
+    const DevPack &pk = ctx->pk;
+    int slot = -1;
+    for (size_t j = 0; j * 7 + 7 <= ctx->wk_x.size(); ++j)
+        if (memcmp(&ctx->wk_x[j * 7], x0, 7 * sizeof(double)) == 0) { slot = (int)j; break; }
+    if (getenv("STL_NO_ASSOC_REUSE")) slot = -1;
+    DevWork view = ctx->wk;
+    if (slot >= 0) {
+        const long long nk = pk.n_kp_total, F = pk.n_kf;
+        view.cand += slot;
+        view.corr_kp += slot * nk; view.corr_pt += slot * nk; view.corr_sp += slot * nk; view.q_corr += slot * nk; view.q_kpsp += slot * nk;
+        view.n_corr += slot * F; view.n_q += slot * F;
+        ctx->assoc_reused += 1;
+    } else {
+        DevCand *hc = ctx->h_cand;
+        if (!ctx->h2d_done) CK(cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming));
+        CK(cudaEventSynchronize(ctx->h2d_done));
+        make_candidate(x0, hc);
+        CK(cudaMemcpyAsync(ctx->wk.cand, hc, sizeof(DevCand), cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ctx->h2d_done, st));
+        // 2-D association at x0 (FindProjectCorrespondences, iba_local.cpp:191): K1 without the cost terms
+        { StageTimer t(ctx, STL_STAGE_ASSOC2D, st); CK(launch_assoc2d(pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, st, 0)); }
+        ctx->launches += 1;
+        ctx->wk_x.assign(x0, x0 + 7);
+    }
+    cudaError_t e;
+    { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st); }
+    if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "associate: %s", cudaGetErrorString(e));
+    ctx->launches += 5;  // four association kernels, k_count_types (cub select kernels not counted)
+    ctx->dbg_b = -1;
+    ctx->last_x.clear();
     return STL_OK;
 }
 
@@ -282,7 +359,7 @@ void stl_default_params(stl_params_t *p) {
     p->max_3d_dist = 1.0; p->robust_kernel_delta = 2.98; p->robust_kernel_3ddelta = 1.0;
     p->num_min_corr = 30; p->norm_max_pts = 30; p->norm_min_pts = 5; p->use_plane = 1;
     p->use_gpr = 0; p->gpr_sigma = 10.0; p->gpr_l = 10.0; p->gpr_sigma_noise = 1e-10;
-    p->plane_index = 0; p->variant = 0;
+    p->plane_index = 1; p->variant = 0;
 }
 
 stl_status_t stl_create(const stl_params_t *params, int32_t device, stl_ctx_t **out) {
@@ -292,7 +369,7 @@ stl_status_t stl_create(const stl_params_t *params, int32_t device, stl_ctx_t **
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) { cudaGetLastError(); return STL_ERR_NO_DEVICE; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return STL_ERR_NO_DEVICE;
-    if (prop.major != 10) return STL_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    if (prop.major != 10 || prop.minor != 0) return STL_ERR_NO_DEVICE;  // only sm_100a SASS is embedded (no PTX): a 10.3 part cannot run it
     if (params->norm_max_pts < 1 || params->norm_max_pts > kMaxK) return STL_ERR_CAPACITY;
     if (params->variant != 0 && params->variant != 1) return STL_ERR_INVALID;
     if (cudaSetDevice(device) != cudaSuccess) return STL_ERR_CUDA;
@@ -312,6 +389,7 @@ void stl_destroy(stl_ctx_t *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    if (c->comm) { ncclCommDestroy(c->comm); c->comm = nullptr; }
     drain_events(c);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     free_work(c);
@@ -341,16 +419,17 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     for (int f = 0; f < F; ++f)
         if (p->scan_offset[f + 1] < p->scan_offset[f] || p->kp_offset[f + 1] < p->kp_offset[f])
             return fail(ctx, STL_ERR_INVALID, "offsets must be non-decreasing (keyframe %d)", f);
-    free_work(ctx);
-    free_pack(ctx);
-    lm_free(ctx->lm);
-    cudaStream_t st = acquire_stream(ctx, nullptr);
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
-    cudaEventRecord(ev0, st);
+    if (p->scan_offset[F] > (1ll << 40) || p->kp_offset[F] > (1ll << 31))
+        return fail(ctx, STL_ERR_CAPACITY, "pack too large (%lld points, %lld keypoints)", (long long)p->scan_offset[F], (long long)p->kp_offset[F]);
+    if (p->scan_offset[F] > 0 && !p->scan_xyz) return fail(ctx, STL_ERR_INVALID, "scan_xyz is null");
+    if (p->kp_offset[F] > 0 && (!p->kp_xy || !p->kp_mappoint)) return fail(ctx, STL_ERR_INVALID, "kp_xy / kp_mappoint is null");
+    if (C > 0 && (!p->covis_relpose || !p->covis_valid || (p->kp_offset[F] > 0 && !p->covis_uv)))
+        return fail(ctx, STL_ERR_INVALID, "covis_relpose / covis_valid / covis_uv is null although n_covis > 0");
 
-    // ---- per-keyframe metadata
-    std::vector<DevKf> &hk = ctx->h_kf;
+    // ---- per-keyframe metadata (validated completely before the previous pack is released: a rejected pack
+    // leaves the context as it was)
+    std::vector<DevKf> hk_new;
+    std::vector<DevKf> &hk = hk_new;
     hk.assign(F, DevKf());
     long long pt = 0, nodes = 0, bmw = 0, gcells = 0, mp_total = 0;
     int max_kp = 0, max_bm = 0;
@@ -389,16 +468,31 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
         max_bm = std::max(max_bm, K.bm_wpr * K.bm_rows);
     }
     const long long NK = p->kp_offset[F];
-    ctx->max_kp = max_kp; ctx->max_bm_words = max_bm;
     int max_cells = 0, max_groups = 0;
     for (int f = 0; f < F; ++f) { max_cells = std::max(max_cells, hk[f].gw * hk[f].gh); max_groups = std::max(max_groups, hk[f].n_pad / 128); }
     if (max_kp > 65535) return fail(ctx, STL_ERR_CAPACITY, "more than 65535 keypoints in a keyframe");
-    ctx->k1_smem = assoc2d_smem_bytes(max_kp, max_bm, max_cells, max_groups);
+    const size_t k1_smem_new = assoc2d_smem_bytes(max_kp, max_bm, max_cells, max_groups);
     int smem_optin = 0;
     CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-    if (ctx->k1_smem > (size_t)smem_optin)
-        return fail(ctx, STL_ERR_CAPACITY, "K1 needs %zu B of shared memory (%d keypoints); device limit %d", ctx->k1_smem, max_kp, smem_optin);
-    CK(assoc2d_configure(ctx->k1_smem));
+    if (k1_smem_new > (size_t)smem_optin)
+        return fail(ctx, STL_ERR_CAPACITY, "K1 needs %zu B of shared memory (%d keypoints); device limit %d", k1_smem_new, max_kp, smem_optin);
+    CK(assoc2d_configure(k1_smem_new));
+
+    // ---- from here on the previous state is gone
+    free_work(ctx);
+    free_pack(ctx);
+    lm_free(ctx->lm);
+    ctx->h_kf.swap(hk_new);
+    std::vector<DevKf> &hk2 = ctx->h_kf;
+    ctx->max_kp = max_kp; ctx->max_bm_words = max_bm; ctx->k1_smem = k1_smem_new;
+    cudaStream_t st = acquire_stream(ctx, nullptr);
+    struct Scope {  // events and the raw-scan scratch are released on every exit path
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr; float *d_raw = nullptr;
+        ~Scope() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); if (d_raw) cudaFree(d_raw); }
+    } scope;
+    CK(cudaEventCreate(&scope.ev0)); CK(cudaEventCreate(&scope.ev1));
+    cudaEvent_t ev0 = scope.ev0, ev1 = scope.ev1;
+    CK(cudaEventRecord(ev0, st));
 
     // ---- variant 1 (iba_global_stable.cpp:67-80): the query pixel of a keypoint is its map point re-projected
     // with the SLAM pose, in fp64; keypoints without a map point are not queried (NaN).  A float32 copy
@@ -435,7 +529,7 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     const double Rdil = ctx->params.max_pixel_dist + (double)kFastErrPx + (ctx->params.variant == 1 ? 1e-3 : 0.0);
 #pragma omp parallel for schedule(dynamic, 8)
     for (int f = 0; f < F; ++f) {
-        const DevKf &K = hk[f];
+        const DevKf &K = hk2[f];
         uint32_t *bm = bitmap.data() + K.bm_off;
         uint32_t *gs = gstart.data() + K.grid_off;
         uint32_t *gk = gkp.data() + K.kp_off;
@@ -476,7 +570,7 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     CK(cudaMalloc(&pk.Tcw, 48 * (size_t)F)); CK(cudaMalloc(&pk.relpose, 48 * (size_t)std::max(F * C, 1)));
     CK(cudaMalloc(&pk.covis_valid, (size_t)std::max(F * C, 1))); CK(cudaMalloc(&pk.covis_uv, sizeof(float2) * std::max<size_t>(nkk * C, 1)));
     CK(cudaMalloc(&pk.he_Tc, 48 * (size_t)F)); CK(cudaMalloc(&pk.he_Tl, 96 * (size_t)F));
-    CK(cudaMemcpyAsync(pk.kf, hk.data(), sizeof(DevKf) * F, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(pk.kf, hk2.data(), sizeof(DevKf) * F, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(pk.bitmap, bitmap.data(), 4 * (size_t)bmw, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(pk.grid_start, gstart.data(), 4 * (size_t)gcells, cudaMemcpyHostToDevice, st));
     if (NK > 0) {
@@ -501,7 +595,8 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     // ---- scans: chunked upload + index build
     {
         const long long chunk_pts = 32ll << 20;
-        float *d_raw = nullptr;
+        float *&d_raw = scope.d_raw;
+        float k0_ms = 0.f;
         long long raw_cap = 0;
         int f0 = 0;
         while (f0 < F) {
@@ -512,24 +607,27 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
             if (n > 0) CK(cudaMemcpyAsync(d_raw, p->scan_xyz + p->scan_offset[f0] * 3, 12 * (size_t)n, cudaMemcpyHostToDevice, st));
             std::vector<long long> off(f1 - f0 + 1);
             for (int f = f0; f <= f1; ++f) off[f - f0] = p->scan_offset[f];
-            cudaError_t e = build_scan_index(d_raw, off.data(), f1 - f0, f0, hk.data(), pk, ctx->adj_r2, st);
-            if (e != cudaSuccess) { dfree(d_raw); return fail(ctx, STL_ERR_CUDA, "index build: %s", cudaGetErrorString(e)); }
+            cudaError_t e = build_scan_index(d_raw, off.data(), f1 - f0, f0, hk2.data(), pk, ctx->adj_r2, st, &k0_ms);
+            if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "index build: %s", cudaGetErrorString(e));
             f0 = f1;
         }
         dfree(d_raw);
+        // K0's own device time (kernels only); the wall time of the whole upload is the caller's to measure
+        ctx->stage_ms[STL_STAGE_BUILD] += k0_ms;
+        ctx->stage_n[STL_STAGE_BUILD] += 1;
     }
-    CK(cudaMemcpy(hk.data(), pk.kf, sizeof(DevKf) * F, cudaMemcpyDeviceToHost));  // pmax filled by the build
+    CK(cudaMemcpy(hk2.data(), pk.kf, sizeof(DevKf) * F, cudaMemcpyDeviceToHost));  // pmax filled by the build
     if (pk.adj && getenv("STL_DEBUG_STATS")) {  // how many real leaves got no adjacency row (> 32 neighbours)?
         long long real = 0, empty = 0, entries = 0, partial = 0;
         double cov_sum = 0;
         std::vector<uint16_t> row;
         std::vector<float> cov;
         for (int f = 0; f < F; f += std::max(1, F / 16)) {
-            const int nl = (hk[f].n_pts + kLeaf - 1) / kLeaf;
+            const int nl = (hk2[f].n_pts + kLeaf - 1) / kLeaf;
             row.resize((size_t)nl * 32);
-            CK(cudaMemcpy(row.data(), pk.adj + hk[f].node_off * 32, row.size() * 2, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(row.data(), pk.adj + hk2[f].node_off * 32, row.size() * 2, cudaMemcpyDeviceToHost));
             cov.resize((size_t)nl);
-            CK(cudaMemcpy(cov.data(), pk.adj_cov + hk[f].node_off, cov.size() * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(cov.data(), pk.adj_cov + hk2[f].node_off, cov.size() * 4, cudaMemcpyDeviceToHost));
             for (int l = 0; l < nl; ++l) if (cov[l] >= 0 && cov[l] < 1e30f) { ++partial; cov_sum += std::sqrt((double)cov[l]); }
             for (int l = 0; l < nl; ++l) {
                 int c = 0;
@@ -544,23 +642,22 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     if (ctx->params.plane_index) {
         CK(cudaMalloc(&pk.pl_rec, sizeof(PlaneRec) * npt));
         CK(cudaMalloc(&pk.pl_m, 4 * npt));
+        CK(cudaEventRecord(ev0, st));
         for (int f0 = 0; f0 < F;) {  // bounded scratch: a few million points at a time
             int f1 = f0 + 1;
-            long long pts = hk[f0].n_pad;
-            while (f1 < F && pts + hk[f1].n_pad <= (4ll << 20)) pts += hk[f1++].n_pad;
-            cudaError_t e = build_plane_index(pk, hk.data(), f0, f1 - f0, ctx->dpr, st);
+            long long pts = hk2[f0].n_pad;
+            while (f1 < F && pts + hk2[f1].n_pad <= (4ll << 20)) pts += hk2[f1++].n_pad;
+            cudaError_t e = build_plane_index(pk, hk2.data(), f0, f1 - f0, ctx->dpr, st);
             if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "plane index: %s", cudaGetErrorString(e));
             f0 = f1;
         }
+        CK(cudaEventRecord(ev1, st));
         CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ev0, ev1));
+        ctx->stage_ms[STL_STAGE_PLANE_INDEX] += ms;
+        ctx->stage_n[STL_STAGE_PLANE_INDEX] += 1;
     }
-    cudaEventRecord(ev1, st);
-    cudaEventSynchronize(ev1);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ev0, ev1);
-    ctx->stage_ms[STL_STAGE_BUILD] += ms;
-    ctx->stage_n[STL_STAGE_BUILD] += 1;
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     ctx->has_pack = true;
     return STL_OK;
 }
@@ -570,7 +667,10 @@ stl_status_t stl_eval_batch_device(stl_ctx_t *ctx, const double *x, int32_t B, d
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!ctx->has_pack) return fail(ctx, STL_ERR_STATE, "stl_upload_pack has not been called");
     CK(cudaSetDevice(ctx->device));
-    return enqueue_eval(ctx, x, B, d_sums, acquire_stream(ctx, stream), false);
+    cudaStream_t st = acquire_stream(ctx, stream);
+    stl_status_t s = enqueue_eval(ctx, x, B, d_sums, st, false);
+    if (s != STL_OK) return s;
+    return allreduce_record(ctx, d_sums, (size_t)B * STL_EVAL_NSUMS, st);
 }
 
 stl_status_t stl_eval_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl_eval_sums_t *sums) {
@@ -582,6 +682,8 @@ stl_status_t stl_eval_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl_eval
     if (s != STL_OK) return s;
     cudaStream_t st = acquire_stream(ctx, nullptr);
     s = enqueue_eval(ctx, x, B, ctx->d_sums, st, false);
+    if (s != STL_OK) return s;
+    s = allreduce_record(ctx, ctx->d_sums, (size_t)B * STL_EVAL_NSUMS, st);
     if (s != STL_OK) return s;
     CK(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums, sizeof(double) * STL_EVAL_NSUMS * B, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -721,30 +823,87 @@ stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[4]
     stl_status_t s = ensure_work(ctx, 1, false);
     if (s != STL_OK) return s;
     cudaStream_t st = acquire_stream(ctx, nullptr);
-    DevCand *hc = ctx->h_cand;
-    if (!ctx->h2d_done) CK(cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming));
-    CK(cudaEventSynchronize(ctx->h2d_done));
-    make_candidate(x0, hc);
-    CK(cudaMemcpyAsync(ctx->wk.cand, hc, sizeof(DevCand), cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(ctx->h2d_done, st));
-    // 2-D association at x0 (FindProjectCorrespondences, iba_local.cpp:191) reuses K1
-    { StageTimer t(ctx, STL_STAGE_ASSOC2D, st); CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, st, 0)); }
-    cudaError_t e;
-    { StageTimer t(ctx, 5, st); e = lm_associate(ctx->pk, ctx->wk, ctx->dpr, ctx->lm, st); }
-    if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "associate: %s", cudaGetErrorString(e));
-    ctx->launches += 6;  // K1, four association kernels, k_count_types (cub select kernels not counted)
-    if (n_blocks) for (int i = 0; i < 4; ++i) n_blocks[i] = ctx->lm.n_blocks[i];
-    ctx->dbg_b = -1;
-    ctx->last_x.clear();
+    s = enqueue_associate(ctx, x0, st);
+    if (s != STL_OK) return s;
+    if (n_blocks) {  // BuildProblem returns the block counts: the one host round trip of the association
+        const cudaError_t e = lm_block_counts(ctx->lm);
+        if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "associate: %s", cudaGetErrorString(e));
+        for (int i = 0; i < 4; ++i) n_blocks[i] = ctx->lm.n_blocks[i];
+    }
     return STL_OK;
 }
 
-static stl_status_t lin_enqueue(stl_ctx *ctx, const double *x, int B, double *d_out, cudaStream_t st) {
+stl_status_t stl_block_counts(stl_ctx_t *ctx, int64_t n_blocks[4]) {
+    if (!ctx || !n_blocks) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->lm.ready) return fail(ctx, STL_ERR_STATE, "stl_associate has not been called");
+    CK(cudaSetDevice(ctx->device));
+    const cudaError_t e = lm_block_counts(ctx->lm);
+    if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "block counts: %s", cudaGetErrorString(e));
+    for (int i = 0; i < 4; ++i) n_blocks[i] = ctx->lm.n_blocks[i];
+    return STL_OK;
+}
+
+static stl_status_t lin_enqueue(stl_ctx *ctx, const double *x, int B, double *d_out, cudaStream_t st, int out_stride = STL_LIN_NSUMS) {
     if (!ctx->lm.ready) return fail(ctx, STL_ERR_STATE, "stl_associate has not been called");
     cudaError_t e;
-    { StageTimer t(ctx, STL_STAGE_LINEARIZE, st); e = lm_linearize(ctx->pk, ctx->dpr, ctx->lm, x, B, d_out, st); }
+    { StageTimer t(ctx, STL_STAGE_LINEARIZE, st); e = lm_linearize(ctx->pk, ctx->dpr, ctx->lm, x, B, d_out, st, nullptr, out_stride); }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "linearize: %s", cudaGetErrorString(e));
-    ctx->launches += 2 + (ctx->lm.nG > 0 ? 1 : 0);  // k_linearize, (k_linearize_gpr,) k_lin_finish
+    ctx->launches += 2 + (ctx->lm.use_gpr ? 1 : 0);  // k_linearize, (k_linearize_gpr,) k_lin_finish
+    return STL_OK;
+}
+
+static stl_status_t ensure_lin(stl_ctx *ctx, int B, int width) {
+    if ((long long)B * width > ctx->lin_cap) {
+        dfree(ctx->d_lin);
+        if (ctx->h_lin) cudaFreeHost(ctx->h_lin);
+        ctx->h_lin = nullptr;
+        ctx->lin_cap = 0;
+        CK(cudaMalloc(&ctx->d_lin, sizeof(double) * width * B));
+        CK(cudaMallocHost(&ctx->h_lin, sizeof(double) * width * B));
+        ctx->lin_cap = (long long)B * width;
+    }
+    return STL_OK;
+}
+
+static stl_status_t step_enqueue(stl_ctx *ctx, const double *x, int B, int reassociate, double *d_out, cudaStream_t st) {
+    stl_status_t s = enqueue_eval(ctx, x, B, d_out, st, false, STL_STEP_NSUMS);
+    if (s != STL_OK) return s;
+    if (reassociate) {
+        s = enqueue_associate(ctx, x, st);
+        if (s != STL_OK) return s;
+    }
+    s = lin_enqueue(ctx, x, B, d_out + STL_EVAL_NSUMS, st, STL_STEP_NSUMS);
+    if (s != STL_OK) return s;
+    ctx->last_x.assign(x, x + (size_t)B * 7);  // the evaluation part stays inspectable through the debug getters
+    return allreduce_record(ctx, d_out, (size_t)B * STL_STEP_NSUMS, st);
+}
+
+stl_status_t stl_step_batch_device(stl_ctx_t *ctx, const double *x, int32_t B, int32_t reassociate, double *d_out, void *stream) {
+    if (!ctx || !x || !d_out || B <= 0) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->has_pack) return fail(ctx, STL_ERR_STATE, "stl_upload_pack has not been called");
+    if (ctx->params.variant != 0) return fail(ctx, STL_ERR_STATE, "stl_step_batch needs variant = 0 (iba_local.cpp has no iba_global_stable variant)");
+    if (!reassociate && !ctx->lm.ready) return fail(ctx, STL_ERR_STATE, "stl_step_batch without reassociate needs a previous association");
+    CK(cudaSetDevice(ctx->device));
+    return step_enqueue(ctx, x, B, reassociate, d_out, acquire_stream(ctx, stream));
+}
+
+stl_status_t stl_step_batch(stl_ctx_t *ctx, const double *x, int32_t B, int32_t reassociate, stl_step_sums_t *out) {
+    if (!ctx || !x || !out || B <= 0) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->has_pack) return fail(ctx, STL_ERR_STATE, "stl_upload_pack has not been called");
+    if (ctx->params.variant != 0) return fail(ctx, STL_ERR_STATE, "stl_step_batch needs variant = 0 (iba_local.cpp has no iba_global_stable variant)");
+    if (!reassociate && !ctx->lm.ready) return fail(ctx, STL_ERR_STATE, "stl_step_batch without reassociate needs a previous association");
+    CK(cudaSetDevice(ctx->device));
+    stl_status_t s = ensure_lin(ctx, B, STL_STEP_NSUMS);
+    if (s != STL_OK) return s;
+    cudaStream_t st = acquire_stream(ctx, nullptr);
+    s = step_enqueue(ctx, x, B, reassociate, ctx->d_lin, st);
+    if (s != STL_OK) return s;
+    CK(cudaMemcpyAsync(ctx->h_lin, ctx->d_lin, sizeof(double) * STL_STEP_NSUMS * B, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(out, ctx->h_lin, sizeof(double) * STL_STEP_NSUMS * B);
     return STL_OK;
 }
 
@@ -752,23 +911,22 @@ stl_status_t stl_linearize_batch_device(stl_ctx_t *ctx, const double *x, int32_t
     if (!ctx || !x || !d_out || B <= 0) return STL_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
-    return lin_enqueue(ctx, x, B, d_out, acquire_stream(ctx, stream));
+    cudaStream_t st = acquire_stream(ctx, stream);
+    stl_status_t s = lin_enqueue(ctx, x, B, d_out, st);
+    if (s != STL_OK) return s;
+    return allreduce_record(ctx, d_out, (size_t)B * STL_LIN_NSUMS, st);
 }
 
 stl_status_t stl_linearize_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl_lin_sums_t *out) {
     if (!ctx || !x || !out || B <= 0) return STL_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
-    if (B > ctx->lin_cap) {
-        dfree(ctx->d_lin);
-        if (ctx->h_lin) cudaFreeHost(ctx->h_lin);
-        ctx->h_lin = nullptr;
-        CK(cudaMalloc(&ctx->d_lin, sizeof(double) * STL_LIN_NSUMS * B));
-        CK(cudaMallocHost(&ctx->h_lin, sizeof(double) * STL_LIN_NSUMS * B));
-        ctx->lin_cap = B;
-    }
+    stl_status_t s = ensure_lin(ctx, B, STL_LIN_NSUMS);
+    if (s != STL_OK) return s;
     cudaStream_t st = acquire_stream(ctx, nullptr);
-    stl_status_t s = lin_enqueue(ctx, x, B, ctx->d_lin, st);
+    s = lin_enqueue(ctx, x, B, ctx->d_lin, st);
+    if (s != STL_OK) return s;
+    s = allreduce_record(ctx, ctx->d_lin, (size_t)B * STL_LIN_NSUMS, st);
     if (s != STL_OK) return s;
     CK(cudaMemcpyAsync(ctx->h_lin, ctx->d_lin, sizeof(double) * STL_LIN_NSUMS * B, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -782,6 +940,8 @@ stl_status_t stl_eval_blocks(stl_ctx_t *ctx, const double *x, int32_t rmax, int6
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!ctx->lm.ready) return fail(ctx, STL_ERR_STATE, "stl_associate has not been called");
     if (rmax < 3 || rmax < 2 * ctx->pk.n_covis) return fail(ctx, STL_ERR_INVALID, "rmax = %d is smaller than max(3, 2 * n_covis = %d)", rmax, 2 * ctx->pk.n_covis);
+    CK(cudaSetDevice(ctx->device));
+    CK(lm_block_counts(ctx->lm));
     const long long nb = (long long)ctx->lm.n2d + ctx->lm.n3d + ctx->lm.nG;
     if (n_blocks_out) *n_blocks_out = nb;
     if (nb > cap_blocks) return fail(ctx, STL_ERR_CAPACITY, "%lld residual blocks, room for %lld", nb, (long long)cap_blocks);
@@ -795,14 +955,15 @@ stl_status_t stl_eval_blocks(stl_ctx_t *ctx, const double *x, int32_t rmax, int6
     cudaError_t e = cudaMalloc(&d_i, 4 * 4 * nbs);
     if (e == cudaSuccess) e = cudaMalloc(&d_d, 8 * nbs * rmax * 8);
     if (e == cudaSuccess) e = cudaMalloc(&d_sums, sizeof(double) * STL_LIN_NSUMS);
-    if (e == cudaSuccess) e = cudaMemset(d_d, 0, 8 * nbs * rmax * 8);  // rows past n_res stay zero (g2o's zero padding, IBACalib.hpp:133-137)
     stl_status_t s = STL_OK;
+    cudaStream_t st = acquire_stream(ctx, nullptr);
+    // rows past n_res stay zero (g2o's zero padding, IBACalib.hpp:133-137); cleared on the stream the kernel runs on
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_d, 0, 8 * nbs * rmax * 8, st);
     if (e == cudaSuccess) {
         bo.type = d_i; bo.kf = d_i + nbs; bo.kp = d_i + 2 * nbs; bo.nres = d_i + 3 * nbs;
         bo.res = d_d; bo.jac = d_d + nbs * rmax;
-        cudaStream_t st = acquire_stream(ctx, nullptr);
         e = lm_linearize(ctx->pk, ctx->dpr, ctx->lm, x, 1, d_sums, st, &bo);
-        ctx->launches += 2 + (ctx->lm.nG > 0 ? 1 : 0);
+        ctx->launches += 2 + (ctx->lm.use_gpr ? 1 : 0);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e == cudaSuccess) e = cudaMemcpy(type, bo.type, 4 * nbs, cudaMemcpyDeviceToHost);
         if (e == cudaSuccess) e = cudaMemcpy(kf, bo.kf, 4 * nbs, cudaMemcpyDeviceToHost);
@@ -855,7 +1016,41 @@ stl_status_t stl_work_counters(stl_ctx_t *ctx, double out[8]) {
         cudaSetDevice(ctx->device);
         if (cudaMemcpy(&ov, ctx->wk.overflow, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) ctx->counters[6] = (double)ov;
     }
+    ctx->counters[7] = (double)ctx->assoc_reused;
     memcpy(out, ctx->counters, sizeof(ctx->counters));
+    return STL_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------
+
+stl_status_t stl_comm_unique_id(uint8_t id[STL_COMM_ID_BYTES]) {
+    if (!id) return STL_ERR_INVALID;
+    static_assert(sizeof(ncclUniqueId) <= STL_COMM_ID_BYTES, "ncclUniqueId does not fit STL_COMM_ID_BYTES");
+    ncclUniqueId u;
+    if (ncclGetUniqueId(&u) != ncclSuccess) return STL_ERR_CUDA;
+    memset(id, 0, STL_COMM_ID_BYTES);
+    memcpy(id, &u, sizeof(u));
+    return STL_OK;
+}
+
+stl_status_t stl_comm_init(stl_ctx_t *ctx, const uint8_t id[STL_COMM_ID_BYTES], int32_t rank, int32_t n_ranks) {
+    if (!ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->comm) return fail(ctx, STL_ERR_STATE, "a communicator is already attached");
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    const ncclResult_t r = ncclCommInitRank(&ctx->comm, n_ranks, u, rank);
+    if (r != ncclSuccess) { ctx->comm = nullptr; return fail(ctx, STL_ERR_CUDA, "ncclCommInitRank: %s", ncclGetErrorString(r)); }
+    ctx->comm_rank = rank; ctx->comm_size = n_ranks;
+    return STL_OK;
+}
+
+stl_status_t stl_comm_info(stl_ctx_t *ctx, int32_t *rank, int32_t *n_ranks) {
+    if (!ctx) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (rank) *rank = ctx->comm ? ctx->comm_rank : 0;
+    if (n_ranks) *n_ranks = ctx->comm ? ctx->comm_size : 1;
     return STL_OK;
 }
 

@@ -70,8 +70,9 @@ struct DevWork {
 // ---- index build (build.cu) ---------------------------------------------------
 // raw: [n][3] float32 device points of a chunk of keyframes; raw_off[nkf+1] host offsets.
 // adj_r2: squared radius of the leaf adjacency lists (<= 0: none are built)
+// kernel_ms (optional): the device time of the build kernels of this chunk is ADDED to it
 cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int nkf, int kf_begin, const DevKf *h_kf,
-                             DevPack &pack, float adj_r2, cudaStream_t st);
+                             DevPack &pack, float adj_r2, cudaStream_t st, float *kernel_ms = nullptr);
 
 // plane index (knn3d.cu): k-NN + plane of every point of keyframes [kf_begin, kf_begin + nkf)
 cudaError_t build_plane_index(const DevPack &pk, const DevKf *h_kf, int kf_begin, int nkf, const DevParams &pr, cudaStream_t st);
@@ -90,7 +91,7 @@ cudaError_t launch_knn3d(const DevPack &pk, int kf, const double *d_q, int nq, i
                          int *d_cnt, cudaStream_t st);
 
 // ---- K3 (reduce.cu) ----------------------------------------------------------------
-// out: [B][STL_EVAL_NSUMS] fp64, written (not accumulated)
-cudaError_t launch_reduce(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, double *d_out, cudaStream_t st);
+// out: [B][out_stride] fp64 (first STL_EVAL_NSUMS of each row), written (not accumulated); out_stride 0 = STL_EVAL_NSUMS
+cudaError_t launch_reduce(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, double *d_out, cudaStream_t st, int out_stride = 0);
 
 }  // namespace stl

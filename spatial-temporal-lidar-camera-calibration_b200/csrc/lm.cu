@@ -297,8 +297,10 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
     const int C = pk.n_covis;
     const int stride = gridDim.x * kLinThreads, t0 = blockIdx.x * kLinThreads + threadIdx.x;
 
+    // block counts live on the device (written by the selects of the association on this stream): no host round trip
+    const int n2d = lm.d_counts[0], n3d = lm.d_counts[1];
     // ---- 3-D/2-D blocks: IBA_PlaneFactor (IBACalib2.hpp:152-184)
-    for (int it = t0; it < lm.n2d; it += stride) {
+    for (int it = t0; it < n2d; it += stride) {
         const int slot = lm.idx2d[it];
         const int f = lm.slot_kf[slot];
         const uint32_t kp = lm.slot_kp[slot];
@@ -360,7 +362,7 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
     }
 
     // ---- 3-D/3-D blocks: Point2Point_Factor / Point2Plane_Factor (IBACalib2.hpp:570-584,611-625)
-    for (int it = t0; it < lm.n3d; it += stride) {
+    for (int it = t0; it < n3d; it += stride) {
         const int slot = lm.idx3d[it];
         const double *g = lm.geo3d + (long long)slot * 9;
         const D7 Ms[3] = {c.s * g[0], c.s * g[1], c.s * g[2]};  // MapPoint * s
@@ -378,7 +380,7 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
             A.v[37] += 1.0;
             A.v[39] += 3.0;
             if (WB) {
-                const long long blk = (long long)lm.n2d + it;
+                const long long blk = (long long)n2d + it;
                 put_row(bo, blk, 0, d[0]); put_row(bo, blk, 1, d[1]); put_row(bo, blk, 2, d[2]);
                 put_head(bo, blk, 1, lm.slot_kf[slot], lm.slot_kp[slot], 3);
             }
@@ -389,7 +391,7 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
             A.v[38] += 1.0;
             A.v[39] += 1.0;
             if (WB) {
-                const long long blk = (long long)lm.n2d + it;
+                const long long blk = (long long)n2d + it;
                 put_row(bo, blk, 0, e);
                 put_head(bo, blk, 2, lm.slot_kf[slot], lm.slot_kp[slot], 1);
             }
@@ -469,11 +471,12 @@ k_linearize_gpr(const DevPack pk, const DevParams pr, const LmState lm, const Lm
     for (int i = 0; i < kLinVals; ++i) A.v[i] = 0.0;
     const int C = pk.n_covis;
     const double sigma2 = pr.gpr_sigma * pr.gpr_sigma, coef = -0.5 / (pr.gpr_l * pr.gpr_l);
-    for (int it = blockIdx.x * kGprWarps + warp; it < lm.nG; it += gridDim.x * kGprWarps) {
+    const int nG = lm.d_counts[3];
+    for (int it = blockIdx.x * kGprWarps + warp; it < nG; it += gridDim.x * kGprWarps) {
         const int cs = lm.idxG[it];
         const int f = lm.slot_kf[cs];
         const uint32_t kp = lm.slot_kp[cs];
-        const long long gblk = (long long)lm.n2d + lm.n3d + it;  // block index in stl_eval_blocks order
+        const long long gblk = (long long)lm.d_counts[0] + lm.d_counts[1] + it;  // block index in stl_eval_blocks order
         const long long ms = lm.slot_mp[cs];
         const int n = lm.gpr_m[ms];
         const DevKf &K = pk.kf[f];
@@ -604,7 +607,7 @@ k_linearize_gpr(const DevPack pk, const DevParams pr, const LmState lm, const Lm
 // one CTA of 1024 threads per candidate: warp w sums values w, w+32 over the chunks (lane-strided partial
 // sums, then a shuffle tree: a fixed order, so the result is reproducible)
 __global__ void __launch_bounds__(1024)
-k_lin_finish(const double *__restrict__ partial, int nchunks, double *__restrict__ out) {
+k_lin_finish(const double *__restrict__ partial, int nchunks, double *__restrict__ out, int out_stride) {
     __shared__ double tot[kLinVals];
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int v = warp; v < kLinVals; v += 32) {
@@ -615,7 +618,7 @@ k_lin_finish(const double *__restrict__ partial, int nchunks, double *__restrict
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double *o = out + (long long)b * STL_LIN_NSUMS;
+        double *o = out + (long long)b * out_stride;
         o[0] = tot[0];
         for (int a = 0; a < 7; ++a) o[1 + a] = tot[1 + a];
         int h = 8;
@@ -630,44 +633,52 @@ template <class T> void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
 }  // namespace
 
 void lm_free(LmState &lm) {
-    dfree(lm.slot_kf); dfree(lm.slot_kp); dfree(lm.flag2d); dfree(lm.type3d); dfree(lm.flag3d); dfree(lm.geo2d); dfree(lm.geo3d);
-    dfree(lm.flagG); dfree(lm.idxG); dfree(lm.slot_mp); dfree(lm.gpr_nb); dfree(lm.gpr_m);
+    dfree(lm.slot_kf); dfree(lm.slot_kp); dfree(lm.flags); dfree(lm.geo2d); dfree(lm.geo3d);
+    dfree(lm.idxG); dfree(lm.slot_mp); dfree(lm.gpr_nb); dfree(lm.gpr_m);
     dfree(lm.stage); dfree(lm.plane_a); dfree(lm.nnb_pos); dfree(lm.nbb); dfree(lm.nbbx); dfree(lm.nbb_m); dfree(lm.nbb_last);
-    dfree(lm.idx2d); dfree(lm.idx3d); dfree(lm.d_counts); dfree(lm.d_tmp); dfree(lm.partial); dfree(lm.d_cand);
+    dfree(lm.idx2d); dfree(lm.idx3d); dfree(lm.d_tmp); dfree(lm.partial); dfree(lm.d_cand);
     if (lm.h_cand) cudaFreeHost(lm.h_cand);
+    if (lm.h_counts) cudaFreeHost(lm.h_counts);
     if (lm.h2d_done) cudaEventDestroy(lm.h2d_done);
+    if (lm.counts_done) cudaEventDestroy(lm.counts_done);
     lm = LmState();
 }
 
+// Enqueues BuildProblem on `st` and returns without waiting: the block counts stay on the device
+// (d_counts: plane, 3-D, point-to-point, GPR), where the linearisation kernels read them; a copy lands
+// in pinned host memory behind `counts_done` for callers that want the numbers (lm_block_counts).
 cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st) {
     cudaError_t e;
 #define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
     const long long ns = pk.n_kp_total > 0 ? pk.n_kp_total : 1;
     if (lm.n_slots != ns) {
-        lm_free(lm);
-        lm.n_slots = ns;
+        lm_free(lm);  // n_slots stays 0 until every allocation below succeeded: a failure midway starts over next time
         TRY(cudaMalloc(&lm.slot_kf, 4 * ns)); TRY(cudaMalloc(&lm.slot_kp, 4 * ns));
-        TRY(cudaMalloc(&lm.flag2d, ns)); TRY(cudaMalloc(&lm.type3d, ns)); TRY(cudaMalloc(&lm.flag3d, ns));
+        // the four per-slot flag arrays and the counters are one allocation: one memset per association
+        const long long nsa = (ns + 15) / 16 * 16;
+        lm.flags_bytes = (size_t)(4 * nsa + 16);
+        TRY(cudaMalloc(&lm.flags, lm.flags_bytes));
+        lm.flag2d = lm.flags; lm.type3d = lm.flags + nsa; lm.flag3d = lm.flags + 2 * nsa; lm.flagG = lm.flags + 3 * nsa;
+        lm.d_counts = reinterpret_cast<int *>(lm.flags + 4 * nsa);
         TRY(cudaMalloc(&lm.geo2d, 48 * ns)); TRY(cudaMalloc(&lm.geo3d, 72 * ns));
         TRY(cudaMalloc(&lm.idx2d, 4 * ns)); TRY(cudaMalloc(&lm.idx3d, 4 * ns));
-        TRY(cudaMalloc(&lm.d_counts, 16));
         const long long nm = pk.n_mp_total > 0 ? pk.n_mp_total : 1;
         TRY(cudaMalloc(&lm.stage, nm)); TRY(cudaMalloc(&lm.plane_a, 32 * nm)); TRY(cudaMalloc(&lm.nnb_pos, 4 * nm));
         TRY(cudaMalloc(&lm.nbb, 4 * nm * kMaxK)); TRY(cudaMalloc(&lm.nbbx, sizeof(float4) * nm * kMaxK)); lm.nbbx_stride = (long long)nm; TRY(cudaMalloc(&lm.nbb_m, 4 * nm)); TRY(cudaMalloc(&lm.nbb_last, 8 * nm));
-        TRY(cudaMalloc(&lm.flagG, ns)); TRY(cudaMalloc(&lm.idxG, 4 * ns)); TRY(cudaMalloc(&lm.slot_mp, 4 * ns));
+        TRY(cudaMalloc(&lm.idxG, 4 * ns)); TRY(cudaMalloc(&lm.slot_mp, 4 * ns));
         if (pr.use_gpr) { TRY(cudaMalloc(&lm.gpr_nb, 4 * nm * kMaxK)); TRY(cudaMalloc(&lm.gpr_m, 4 * nm)); }
         size_t tb = 0;
         cub::CountingInputIterator<int> it(0);
         TRY(cub::DeviceSelect::Flagged(nullptr, tb, it, lm.flag2d, lm.idx2d, lm.d_counts, (int)ns, st));
         lm.tmp_bytes = tb;
         TRY(cudaMalloc(&lm.d_tmp, tb));
+        TRY(cudaMallocHost(&lm.h_counts, 16));
+        TRY(cudaEventCreateWithFlags(&lm.counts_done, cudaEventDisableTiming));
+        lm.n_slots = ns;
+        lm.max_blocks = nm;
     }
     lm.ready = false;
-    TRY(cudaMemsetAsync(lm.flag2d, 0, ns, st));
-    TRY(cudaMemsetAsync(lm.type3d, 0, ns, st));
-    TRY(cudaMemsetAsync(lm.flag3d, 0, ns, st));
-    TRY(cudaMemsetAsync(lm.flagG, 0, ns, st));
-    TRY(cudaMemsetAsync(lm.d_counts, 0, 16, st));
+    TRY(cudaMemsetAsync(lm.flags, 0, lm.flags_bytes, st));
     k_lm_knn_a<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
     k_lm_plane_a<<<(unsigned)(pk.n_kf * kPlaneSub), 128, 0, st>>>(pk, wk, pr, lm);
     k_lm_knn_b<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
@@ -684,19 +695,32 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
     }
     k_count_types<<<64, 256, 0, st>>>(lm.type3d, lm.idx3d, lm.d_counts + 1, lm.d_counts + 2);
     TRY(cudaGetLastError());
-    int h[4] = {0, 0, 0, 0};
-    TRY(cudaMemcpyAsync(h, lm.d_counts, 16, cudaMemcpyDeviceToHost, st));
-    TRY(cudaStreamSynchronize(st));  // the one host round trip of the association: BuildProblem returns the block counts
-    lm.n2d = h[0]; lm.n3d = h[1]; lm.nG = pr.use_gpr ? h[3] : 0;
-    const int npt = h[2];
-    lm.n_blocks[0] = lm.n2d; lm.n_blocks[1] = npt; lm.n_blocks[2] = lm.n3d - npt; lm.n_blocks[3] = lm.nG;
+    TRY(cudaMemcpyAsync(lm.h_counts, lm.d_counts, 16, cudaMemcpyDeviceToHost, st));
+    TRY(cudaEventRecord(lm.counts_done, st));
+    lm.counts_valid = false;
+    lm.use_gpr = pr.use_gpr != 0;
     lm.ready = true;
     return cudaSuccess;
 }
 
+// Host copy of the block counts of the last association (waits for it to finish).
+cudaError_t lm_block_counts(LmState &lm) {
+    if (!lm.ready) return cudaErrorNotReady;
+    if (lm.counts_valid) return cudaSuccess;
+    cudaError_t e = cudaEventSynchronize(lm.counts_done);
+    if (e != cudaSuccess) return e;
+    const int *h = lm.h_counts;
+    lm.n2d = h[0]; lm.n3d = h[1]; lm.nG = lm.use_gpr ? h[3] : 0;
+    const int npt = h[2];
+    lm.n_blocks[0] = lm.n2d; lm.n_blocks[1] = npt; lm.n_blocks[2] = lm.n3d - npt; lm.n_blocks[3] = lm.nG;
+    lm.counts_valid = true;
+    return cudaSuccess;
+}
+
 cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
-                         const BlockOut *blocks) {
+                         const BlockOut *blocks, int out_stride) {
     cudaError_t e;
+#define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
     if (B > lm.cand_cap) {
         dfree(lm.d_cand);
         if (lm.h_cand) cudaFreeHost(lm.h_cand);
@@ -711,12 +735,15 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
     for (int b = 0; b < B; ++b) make_lm_candidate(x + (size_t)b * 7, hc + b);
     TRY(cudaMemcpyAsync(lm.d_cand, hc, sizeof(LmCand) * B, cudaMemcpyHostToDevice, st));
     TRY(cudaEventRecord(lm.h2d_done, st));
-    const int work = lm.n2d > lm.n3d ? lm.n2d : lm.n3d;
-    int chunks = (work + kLinThreads * 2 - 1) / (kLinThreads * 2);
-    if (chunks < 1) chunks = 1;
-    if (chunks > 148 * 8) chunks = 148 * 8;
-    int gchunks = lm.nG > 0 ? (lm.nG + kGprWarps * 4 - 1) / (kGprWarps * 4) : 0;
-    if (gchunks > 148 * 8) gchunks = 148 * 8;
+    // grids are sized from the host-side upper bound of the block count (one block per map-point-carrying
+    // keypoint at most), or from the real counts when the host already has them; the kernels read the
+    // exact counts from the device
+    const long long work = lm.counts_valid ? (lm.n2d > lm.n3d ? lm.n2d : lm.n3d) : lm.max_blocks;
+    long long chunks_ll = (work + kLinThreads * 2 - 1) / (kLinThreads * 2);
+    int chunks = (int)(chunks_ll < 1 ? 1 : (chunks_ll > 148 * 8 ? 148 * 8 : chunks_ll));
+    const long long gwork = !lm.use_gpr ? 0 : (lm.counts_valid ? lm.nG : lm.max_blocks);
+    long long gchunks_ll = gwork > 0 ? (gwork + kGprWarps * 4 - 1) / (kGprWarps * 4) : 0;
+    int gchunks = (int)(gchunks_ll > 148 * 8 ? 148 * 8 : gchunks_ll);
     const int stride = chunks + gchunks;
     const long long need = (long long)B * stride * kLinVals;
     if (need > lm.partial_cap) {
@@ -733,7 +760,7 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
         else k_linearize_gpr<false><<<dim3(gchunks, B), kGprWarps * 32, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, chunks, bo);
         TRY(cudaGetLastError());
     }
-    k_lin_finish<<<B, 1024, 0, st>>>(lm.partial, stride, d_out);
+    k_lin_finish<<<B, 1024, 0, st>>>(lm.partial, stride, d_out, out_stride > 0 ? out_stride : STL_LIN_NSUMS);
     TRY(cudaGetLastError());
 #undef TRY
     return cudaSuccess;

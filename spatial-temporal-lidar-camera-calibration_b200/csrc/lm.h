@@ -14,6 +14,8 @@ struct LmState {
     long long n_slots = 0;
     int *slot_kf = nullptr;       // [n_slots]
     uint32_t *slot_kp = nullptr;  // [n_slots]
+    uint8_t *flags = nullptr;     // one allocation: flag2d | type3d | flag3d | flagG | d_counts (cleared by one memset)
+    size_t flags_bytes = 0;
     uint8_t *flag2d = nullptr;    // [n_slots] 1 = plane block
     uint8_t *type3d = nullptr;    // [n_slots] 0 none, 1 point-to-point, 2 point-to-plane
     uint8_t *flag3d = nullptr;    // [n_slots] type3d != 0
@@ -35,7 +37,12 @@ struct LmState {
     uint32_t *gpr_nb = nullptr;   // [n_mp][32]
     int *gpr_m = nullptr;         // [n_mp]
     int nG = 0;
-    int *d_counts = nullptr;      // [2]
+    int *d_counts = nullptr;      // [4] device: plane blocks, 3-D blocks, point-to-point among them, GPR blocks
+    int *h_counts = nullptr;      // pinned copy, valid behind counts_done
+    cudaEvent_t counts_done = nullptr;
+    bool counts_valid = false;    // n2d / n3d / nG / n_blocks below mirror the device counts
+    bool use_gpr = false;
+    long long max_blocks = 0;     // upper bound of any block count (map-point-carrying keypoints)
     int n2d = 0, n3d = 0;
     void *d_tmp = nullptr;        // cub scratch
     size_t tmp_bytes = 0;
@@ -59,7 +66,10 @@ struct BlockOut {
     int rmax = 0;
 };
 
+// out_stride: doubles between the records of consecutive candidates in d_out (0 = STL_LIN_NSUMS)
 cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
-                         const BlockOut *blocks = nullptr);
+                         const BlockOut *blocks = nullptr, int out_stride = 0);
+// waits for the last association and mirrors its block counts into lm.n2d / n3d / nG / n_blocks
+cudaError_t lm_block_counts(LmState &lm);
 
 }  // namespace stl

@@ -10,7 +10,7 @@ namespace {
 
 constexpr int kT = 256;
 
-__global__ void __launch_bounds__(kT) k_reduce(const DevPack pk, const DevWork wk, const DevParams pr, double *__restrict__ out) {
+__global__ void __launch_bounds__(kT) k_reduce(const DevPack pk, const DevWork wk, const DevParams pr, double *__restrict__ out, const int out_stride) {
     const int b = blockIdx.x;
     const int F = pk.n_kf, sub = wk.sub;
     double v[STL_EVAL_NSUMS];
@@ -40,15 +40,15 @@ __global__ void __launch_bounds__(kT) k_reduce(const DevPack pk, const DevWork w
     if (threadIdx.x < STL_EVAL_NSUMS) {
         double x = 0;
         for (int w = 0; w < kT / 32; ++w) x += red[threadIdx.x][w];
-        out[(long long)b * STL_EVAL_NSUMS + threadIdx.x] = x;
+        out[(long long)b * out_stride + threadIdx.x] = x;
     }
 }
 
 }  // namespace
 
-cudaError_t launch_reduce(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, double *d_out, cudaStream_t st) {
+cudaError_t launch_reduce(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, double *d_out, cudaStream_t st, int out_stride) {
     if (B <= 0) return cudaSuccess;
-    k_reduce<<<B, kT, 0, st>>>(pk, wk, pr, d_out);
+    k_reduce<<<B, kT, 0, st>>>(pk, wk, pr, d_out, out_stride > 0 ? out_stride : STL_EVAL_NSUMS);
     return cudaGetLastError();
 }
 

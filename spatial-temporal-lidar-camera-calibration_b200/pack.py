@@ -159,6 +159,6 @@ def default_params() -> _abi.Params:
     p.use_plane = 1
     p.use_gpr = 0
     p.gpr_sigma, p.gpr_l, p.gpr_sigma_noise = 10.0, 10.0, 1e-10
-    p.plane_index = 0
+    p.plane_index = 1
     p.variant = 0
     return p

@@ -54,12 +54,16 @@ def has_cuda():
         return False
 
 
-@pytest.fixture(scope="session")
-def gpu_ctx(pkg, small_pack):
+@pytest.fixture(scope="session", params=[1, 0], ids=["plane-index", "plane-fit"])
+def gpu_ctx(request, pkg, small_pack):
+    """One context per flavour of the plane fit: looked up in the index built at upload (the default), or fitted
+    per query at evaluation time (params.plane_index = 0, the reference's order of work)."""
     if not has_cuda():
         pytest.skip("no CUDA device")
     capi = importlib.import_module(PKG + ".capi")
-    ctx = capi.Context()
+    p = pkg.default_params()
+    p.plane_index = request.param
+    ctx = capi.Context(params=p)
     ctx.upload(small_pack[0])
     yield ctx
     ctx.close()

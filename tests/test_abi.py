@@ -21,7 +21,7 @@ def test_calib_exports_every_declared_symbol(pkg):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in stlcalib.h but not exported"
     assert set(names) == set(pkg._abi.CALIB_SYMBOLS), "python symbol table out of sync with the header"
-    assert lib.stl_abi_version() == 1
+    assert lib.stl_abi_version() == 2
 
 
 def test_synth_exports_every_declared_symbol(pkg):

@@ -58,8 +58,9 @@ def test_alignment_indices_bit_exact(gpu_ctx, orc, small_candidates, small_pack)
             assert np.array_equal(a["nn"], d["align_nn"])
             assert np.array_equal(a["m"], d["align_m"])
             assert np.array_equal(a["is_plane"], d["align_is_plane"])
-            for i in range(len(a["m"])):
-                assert np.array_equal(a["knn"][i][: a["m"][i]], d["align_knn"][i][: d["align_m"][i]]), (b, kf, i)
+            if not gpu_ctx.params.plane_index:   # with the index the lists are consumed at upload, not kept per query
+                for i in range(len(a["m"])):
+                    assert np.array_equal(a["knn"][i][: a["m"][i]], d["align_knn"][i][: d["align_m"][i]]), (b, kf, i)
             assert np.allclose(a["dist"], d["align_dist"], rtol=1e-10, atol=1e-12)
             fg, fo = gpu_ctx.debug_frame(b, kf), orc.frame_sums(small_candidates[b], kf)
             for key in fo:
@@ -228,11 +229,13 @@ def test_large_shape_properties(pkg, synth, nkf, ncand):
     assert np.array_equal(acc[:, COUNTERS], full[:, COUNTERS]) and np.allclose(acc[:, :3], full[:, :3], rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("plane_index", [1, 0])
 @pytest.mark.parametrize("variant", ["k20", "tight", "covis1"])
-def test_parameter_variants(oracle_mod, pkg, small_pack, small_candidates, variant):
+def test_parameter_variants(oracle_mod, pkg, small_pack, small_candidates, variant, plane_index):
     """BASELINE config 3 (k = 20 plane variant) and other IBAGlobalParams settings: same parity bar."""
     capi = importlib.import_module(PKG + ".capi")
     p = pkg.default_params()
+    p.plane_index = plane_index
     pack = small_pack[0].shard(1, 4)
     if variant == "k20":
         p.norm_max_pts = 20
@@ -252,7 +255,9 @@ def test_parameter_variants(oracle_mod, pkg, small_pack, small_candidates, varia
         c.eval_sums(small_candidates[:3])
         a = c.debug_align(1, 1)
         assert np.array_equal(a["nn"], d["align_nn"]) and np.array_equal(a["m"], d["align_m"])
-        assert all(np.array_equal(a["knn"][i][: a["m"][i]], d["align_knn"][i][: d["align_m"][i]]) for i in range(len(a["m"])))
+        assert np.array_equal(a["is_plane"], d["align_is_plane"]) and np.allclose(a["dist"], d["align_dist"], rtol=1e-10, atol=1e-12)
+        if not plane_index:
+            assert all(np.array_equal(a["knn"][i][: a["m"][i]], d["align_knn"][i][: d["align_m"][i]]) for i in range(len(a["m"])))
         nb_o, _ = orc.associate(small_candidates[0])
         nb_g = c.associate(small_candidates[0])
         assert np.array_equal(nb_g, nb_o)
@@ -282,18 +287,20 @@ def test_config5_shape_128_beam_scans(oracle_mod, pkg, synth):
 
 
 def test_plane_index_option_gives_identical_results(oracle_mod, pkg, small_pack, small_candidates):
-    """params.plane_index: the local plane of every scan point is fitted once at upload (it does not
-    depend on the candidate) and only looked up afterwards — every number must stay the same."""
+    """params.plane_index (the default): the local plane of every scan point is fitted once at upload (it does
+    not depend on the candidate) and only looked up afterwards — every number must equal the per-query fit
+    (plane_index = 0), bit for bit."""
     capi = importlib.import_module(PKG + ".capi")
-    p = pkg.default_params(); p.plane_index = 1
+    p0 = pkg.default_params(); p0.plane_index = 0
+    assert pkg.default_params().plane_index == 1
     pack = small_pack[0].shard(0, 3)
     orc = oracle_mod.Oracle(pack, kind="best")
     want, _, _ = orc.ba_error_sums(small_candidates, mode=0)
-    with capi.Context(params=p) as c:
+    with capi.Context() as c:
         c.upload(pack)
         got = c.eval_sums(small_candidates)
         _check_sums(got, want)
-        with capi.Context() as plain:      # and bit-identical to the on-the-fly path
+        with capi.Context(params=p0) as plain:      # and bit-identical to the on-the-fly path
             plain.upload(pack)
             assert np.array_equal(plain.eval_sums(small_candidates), got)
             nb0 = plain.associate(small_candidates[1]); L0 = plain.linearize(small_candidates[:2])
@@ -366,13 +373,14 @@ def test_concurrent_callers_are_serialised(gpu_ctx, small_candidates):
         assert np.array_equal(got[i], want[i % 4])
 
 
+@pytest.mark.parametrize("plane_index", [0, 1])
 @pytest.mark.parametrize("radius", [0.6, 1.5])
-def test_leaf_adjacency_scan_equals_tree_descent(oracle_mod, pkg, small_pack, small_candidates, radius, monkeypatch):
+def test_leaf_adjacency_scan_equals_tree_descent(oracle_mod, pkg, small_pack, small_candidates, radius, plane_index, monkeypatch):
     """The adjacency lists (K0) only change HOW neighbourhoods are searched.  radius = 1.5 m makes most rows
     truncated or empty, so the coverage test, the restart and the descent fallback all run; a far-off
     candidate makes the 1-NN of the map points leave the covered range."""
     capi = importlib.import_module(PKG + ".capi")
-    p = pkg.default_params(); p.norm_radius = radius
+    p = pkg.default_params(); p.norm_radius = radius; p.plane_index = plane_index
     pack = small_pack[0].shard(1, 4)
     X = np.concatenate([small_candidates[:3], small_candidates[3:4] + np.array([0.03, -0.02, 0.02, 0.4, -0.3, 0.2, 0.0])])
     with capi.Context(params=p) as c:
@@ -413,7 +421,16 @@ def test_exact_ties_are_broken_by_original_index(oracle_mod, pkg, small_pack, sm
     want, ties, _ = orc.ba_error_sums(x, mode=0)
     assert ties[0] > 0 and ties[2] > 0                                     # the ties are really there
     d = orc.frame_debug(x, 0)
-    with capi.Context() as c:
+    for plane_index in (0, 1):
+        pp = pkg.default_params(); pp.plane_index = plane_index
+        with capi.Context(params=pp) as c:
+            c.upload(one)
+            _check_sums(c.eval_sums(x), want)
+            a = c.debug_align(0, 0)
+            assert np.array_equal(a["nn"], d["align_nn"]) and np.array_equal(a["m"], d["align_m"])
+            assert np.array_equal(a["is_plane"], d["align_is_plane"])
+    pp = pkg.default_params(); pp.plane_index = 0
+    with capi.Context(params=pp) as c:
         c.upload(one)
         got = c.eval_sums(x)
         _check_sums(got, want)
@@ -453,3 +470,94 @@ def test_survivor_and_match_list_overflow_fallbacks(oracle_mod, pkg, small_pack,
             d = orc.frame_debug(X[b], f)
             kp, pt = c.debug_corrset(b, f)
             assert np.array_equal(kp, d["corr_kp"]) and np.array_equal(pt, d["corr_pt"])
+
+
+@pytest.mark.parametrize("nkf,mode", [(50, 0), (1500, 1)], ids=["configs0-50kf", "configs1-1500kf"])
+def test_oracle_diff_at_baseline_shapes(oracle_mod, pkg, synth, nkf, mode):
+    """BASELINE configs[0] (50 keyframes x 1 candidate) and configs[1] (the full 1500-keyframe KITTI-00 shape x 1
+    candidate) against the oracle itself — real nanoflann when oracle/_ref is there; the 1500-keyframe case in the
+    oracle's OpenMP-over-keyframes mode (iba_func.cpp:203), which only re-associates the fp64 sums.  Counters exact,
+    sums to 1e-9; then the LM problem built at the same x: block counts exact, cost / J^T r / J^T J to 1e-9."""
+    capi = importlib.import_module(PKG + ".capi")
+    pack, x_gt, _ = synth.generate(n_kf=nkf, seed=1000)
+    x = synth.candidates(x_gt, 3, 0.2)[2:3]
+    orc = oracle_mod.Oracle(pack, kind="best")
+    want, ties, _ = orc.ba_error_sums(x, mode=mode)
+    assert ties.sum() == 0
+    nb_o, _ = orc.associate(x[0])
+    L_o = orc.linearize(x, nthreads=0)
+    orc.close()
+    with capi.Context() as c:
+        c.upload(pack)
+        got = c.eval_sums(x)
+        _check_sums(got, want)
+        assert got[0, 10] == nkf
+        nb = c.associate(x[0])
+        assert np.array_equal(nb, nb_o)
+        assert c.work_counters()["assoc_reused"] == 1          # BuildProblem at the x just evaluated: no second K1
+        L = c.linearize(x)
+        assert np.array_equal(L[:, 57:], L_o[:, 57:])
+        assert np.allclose(L[:, 0], L_o[:, 0], rtol=1e-9, atol=0)
+        sg, sh = np.abs(L_o[:, 1:8]).max(), np.abs(L_o[:, 8:57]).max()
+        assert np.allclose(L[:, 1:8], L_o[:, 1:8], rtol=1e-6, atol=1e-9 * sg)
+        assert np.allclose(L[:, 8:57], L_o[:, 8:57], rtol=1e-6, atol=1e-9 * sh)
+        S = c.step(x, reassociate=True)                          # the fused call gives the same record
+        assert np.array_equal(S[:, :12], got) and np.array_equal(S[:, 12:], L)
+
+
+def test_step_batch_equals_separate_calls(pkg, small_pack, small_candidates, monkeypatch):
+    """stl_step_batch = stl_eval_batch + stl_associate(x[0]) + stl_linearize_batch, bit for bit; the association
+    re-uses the evaluation's 2-D correspondences (same results as running K1 again); nothing waits on the host
+    in between (asynchronous association, block counts fetched afterwards)."""
+    capi = importlib.import_module(PKG + ".capi")
+    pack = small_pack[0].shard(0, 4)
+    X = small_candidates
+    with capi.Context() as c:
+        c.upload(pack)
+        e = c.eval_sums(X)
+        r0 = c.work_counters()["assoc_reused"]
+        nb = c.associate(X[2])                                   # X[2] sits at slot 2 of the evaluation just made
+        assert c.work_counters()["assoc_reused"] == r0 + 1
+        L = c.linearize(X)
+        c.eval_sums(X[:1])
+        nb_fresh = c.associate(X[2])                             # not in the workspace any more: K1 runs again
+        assert c.work_counters()["assoc_reused"] == r0 + 1
+        assert np.array_equal(nb, nb_fresh) and np.array_equal(c.linearize(X), L)
+        # fused: association at X[0]
+        S = c.step(X, reassociate=True)
+        nb0 = c.block_counts()
+        assert np.array_equal(S[:, :12], e)
+        c.eval_sums(X[3:4])
+        assert np.array_equal(c.associate(X[0]), nb0)
+        L0 = c.linearize(X)
+        assert np.array_equal(S[:, 12:], L0)
+        assert np.array_equal(S[:, 12 + 57], np.full(len(X), nb0[0])) and np.array_equal(S[:, 12 + 61], np.full(len(X), nb0[3]))
+        # frozen association, batch of candidates (the NOMAD poll shape)
+        S2 = c.step(X[1:], reassociate=False)
+        assert np.array_equal(S2[:, :12], e[1:]) and np.array_equal(S2[:, 12:], L0[1:])
+        # asynchronous association
+        c.associate(X[1], wait=False)
+        La = c.linearize(X[:2])
+        nba = c.block_counts()
+        assert np.array_equal(c.associate(X[1]), nba) and np.array_equal(c.linearize(X[:2]), La)
+        B = c.eval_blocks(X[1])
+        assert len(B["type"]) == nba.sum()
+    monkeypatch.setenv("STL_NO_ASSOC_REUSE", "1")
+    with capi.Context() as c:
+        c.upload(pack)
+        assert np.array_equal(c.step(X, reassociate=True), S)
+        assert c.work_counters()["assoc_reused"] == 0
+
+
+def test_rejected_pack_keeps_the_previous_state(pkg, small_pack, small_candidates):
+    """A pack that fails validation must not destroy the pack already uploaded."""
+    capi = importlib.import_module(PKG + ".capi")
+    pack = small_pack[0].shard(0, 2)
+    with capi.Context() as c:
+        c.upload(pack)
+        want = c.eval_sums(small_candidates[:1])
+        bad = small_pack[0].shard(0, 1)
+        bad.image_wh = bad.image_wh.copy(); bad.image_wh[0, 0] = 0
+        with pytest.raises(pkg._abi.StlError):
+            c.upload(bad)
+        assert np.array_equal(c.eval_sums(small_candidates[:1]), want)

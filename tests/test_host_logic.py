@@ -21,7 +21,6 @@ def test_shard_bounds_partition():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [e - s for s, e in b]
             assert max(sizes) - min(sizes) <= 1
-    assert par.candidate_tiles(10, 4) == [(0, 4), (4, 8), (8, 10)]
 
 
 def test_partial_sums_are_additive_over_keyframe_shards(oracle_mod, small_pack, small_candidates):
