@@ -338,6 +338,9 @@ def main():
     ctx = capi.Context(params=params, device=local_rank)
     if by_kf:   # the library owns the communicator; torch.distributed only carries the 128-byte id
         par.attach_communicator(ctx, rank, world, exchange=par.torch_exchange())
+    # a few keyframes first: loads the CUDA modules of the build (lazy loading would otherwise be timed as "K0")
+    ctx.upload(pack.shard(0, min(4, pack.n_kf)))
+    ctx.stage_stats()
     free0 = torch.cuda.mem_get_info()[0]
     t0 = time.time()
     ctx.upload(pack)
@@ -538,7 +541,8 @@ def main():
             arm = CpuArm(cpack, params, mode, cores)
             if mode == "poll":
                 arm.freeze(cands(0)[0])
-            t_tot, reps, worst, ok, checked = 0.0, 0, 0.0, True, 0
+            t_tot, reps, ok, checked = 0.0, 0, True, 0
+            errs = {"sum_3d2d": 0.0, "sum_3d3d": 0.0, "sum_he": 0.0, "lm_cost": 0.0, "lm_JtR": 0.0, "lm_JtJ": 0.0}
             while reps < args.steps and (t_tot < args.cpu_seconds or reps < 2):
                 Xs = cands(args.warmup + reps)[:B_s]
                 t0 = time.perf_counter()
@@ -547,18 +551,20 @@ def main():
                 if nkf_s == F:          # full keyframe set: the GPU record of this very step must match
                     g = rec[reps][:B_s]
                     ok &= bool(np.array_equal(g[:, 3:12], s_cpu[:, 3:12]))
-                    with np.errstate(divide="ignore", invalid="ignore"):
-                        r = np.abs(g[:, :3] - s_cpu[:, :3]) / np.abs(s_cpu[:, :3])
-                    worst = max(worst, float(np.nanmax(r)))
+                    for j, name in enumerate(("sum_3d2d", "sum_3d3d", "sum_he")):
+                        den = np.maximum(np.abs(s_cpu[:, j]), 1e-300)
+                        errs[name] = max(errs[name], float((np.abs(g[:, j] - s_cpu[:, j]) / den).max()))
                     if l_cpu is not None:
                         gl = g[:, 12:]
                         ok &= bool(np.array_equal(gl[:, 57:], l_cpu[:, 57:]))
-                        worst = max(worst, float(np.abs(gl[:, 0] - l_cpu[:, 0]).max() / np.abs(l_cpu[:, 0]).max()))
-                        scale_h = np.abs(l_cpu[:, 8:57]).max(axis=1, keepdims=True)
-                        worst_h = float((np.abs(gl[:, 8:57] - l_cpu[:, 8:57]) / scale_h).max())
-                        ok &= worst_h < 1e-6
+                        errs["lm_cost"] = max(errs["lm_cost"], float((np.abs(gl[:, 0] - l_cpu[:, 0]) / np.abs(l_cpu[:, 0])).max()))
+                        sg = np.abs(l_cpu[:, 1:8]).max(axis=1, keepdims=True)
+                        sh = np.abs(l_cpu[:, 8:57]).max(axis=1, keepdims=True)
+                        errs["lm_JtR"] = max(errs["lm_JtR"], float((np.abs(gl[:, 1:8] - l_cpu[:, 1:8]) / sg).max()))
+                        errs["lm_JtJ"] = max(errs["lm_JtJ"], float((np.abs(gl[:, 8:57] - l_cpu[:, 8:57]) / sh).max()))
                     checked += 1
                 reps += 1
+            worst = max(errs.values())
             ok &= worst < 1e-6
             frac = (nkf_s / F) * (B_s / B)
             cpu_val = B * frac / (t_tot / reps)
@@ -568,8 +574,9 @@ def main():
                           + (" (the whole workload, no extrapolation)" if frac == 1.0 else f" (extrapolated linearly, x{1 / frac:.1f})")
                           + f"; OpenMP over keyframes / residual blocks, {cores} threads; KNN = {arm.describe()}; KD-tree build {arm.build_s:.2f}s excluded",
             }
-            line["oracle_check"] = {"steps_checked": checked, "ok": bool(ok) if checked else None, "max_rel_err": worst,
-                                    "what": "timed GPU records vs the CPU oracle on the same candidates: counters exact, sums and cost <= 1e-6 rel (observed above)"}
+            line["oracle_check"] = {"steps_checked": checked, "ok": bool(ok) if checked else None, "max_rel_err": worst, "rel_err": errs,
+                                    "what": "timed GPU records vs the CPU oracle on the same candidates: counters and block counts exact; sums, cost, "
+                                            "J^T r, J^T J (relative to their largest entry) within 1e-6"}
             if checked and not ok:
                 rc = 3
             if args.config == "c2":

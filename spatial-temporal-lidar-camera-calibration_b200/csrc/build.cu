@@ -348,7 +348,7 @@ k_leaf_adj(const DevKf *__restrict__ kf, int kf_begin, const float4 *__restrict_
 }  // namespace
 
 cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int nkf, int kf_begin, const DevKf *h_kf, DevPack &pack,
-                             float adj_r2, cudaStream_t st, float *kernel_ms) {
+                             float adj_r2, cudaStream_t st, BuildScratch &scr, float *kernel_ms) {
     const long long n = h_raw_off[nkf] - h_raw_off[0];
     cudaError_t err = cudaSuccess;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // device time of the build kernels alone (no allocation, no H2D copy)
@@ -368,20 +368,20 @@ cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int
     long long *h_rel = (long long *)malloc(sizeof(long long) * (nkf + 1));
     for (int f = 0; f <= nkf; ++f) h_rel[f] = h_raw_off[f] - h_raw_off[0];
 #define STL_TRY(x) do { err = (x); if (err != cudaSuccess) goto done; } while (0)
-    STL_TRY(cudaMalloc(&d_off, sizeof(long long) * (nkf + 1)));
+    STL_TRY(scr.need(0, sizeof(long long) * (nkf + 1))); d_off = (long long *)scr.buf[0];
     STL_TRY(cudaMemcpyAsync(d_off, h_rel, sizeof(long long) * (nkf + 1), cudaMemcpyHostToDevice, st));
-    STL_TRY(cudaMalloc(&d_bbox, sizeof(float) * 6 * nkf));
+    STL_TRY(scr.need(1, sizeof(float) * 6 * nkf)); d_bbox = (float *)scr.buf[1];
     if (n > 0) {
-        STL_TRY(cudaMalloc(&d_keys, sizeof(unsigned long long) * n));
-        STL_TRY(cudaMalloc(&d_keys2, sizeof(unsigned long long) * n));
-        STL_TRY(cudaMalloc(&d_vals, sizeof(uint32_t) * n));
-        STL_TRY(cudaMalloc(&d_vals2, sizeof(uint32_t) * n));
+        STL_TRY(scr.need(2, sizeof(unsigned long long) * n)); d_keys = (unsigned long long *)scr.buf[2];
+        STL_TRY(scr.need(3, sizeof(unsigned long long) * n)); d_keys2 = (unsigned long long *)scr.buf[3];
+        STL_TRY(scr.need(4, sizeof(uint32_t) * n)); d_vals = (uint32_t *)scr.buf[4];
+        STL_TRY(scr.need(5, sizeof(uint32_t) * n)); d_vals2 = (uint32_t *)scr.buf[5];
     }
     if (n > 0) {  // the sort scratch is sized before the timed part
         int kf_bits0 = 1;
         while ((1 << kf_bits0) < nkf) ++kf_bits0;
         STL_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, 48 + kf_bits0, st));
-        STL_TRY(cudaMalloc(&d_tmp, tmp_bytes));
+        STL_TRY(scr.need(6, tmp_bytes)); d_tmp = scr.buf[6];
     }
     if (kernel_ms) {
         STL_TRY(cudaEventCreate(&ev0)); STL_TRY(cudaEventCreate(&ev1));
@@ -428,7 +428,6 @@ done:
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     free(h_rel);
-    cudaFree(d_off); cudaFree(d_bbox); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_vals); cudaFree(d_vals2); cudaFree(d_tmp);
     return err;
 }
 

@@ -53,6 +53,7 @@ struct stl_ctx {
     int dbg_b = -1;
     // which candidates' K1 results (correspondences, query lists) the workspace holds right now: rows of x, in slot order
     std::vector<double> wk_x;
+    bool wk_has_nn = false;  // ... and the 1-NN positions of their 3-D queries (K2a)
     long long assoc_reused = 0;
     // multi-GPU: keyframes sharded over the ranks of this communicator (owned)
     ncclComm_t comm = nullptr;
@@ -270,6 +271,7 @@ stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, c
         { StageTimer t(ctx, STL_STAGE_REDUCE, st); CK(launch_reduce(ctx->pk, ctx->wk, ctx->dpr, nb, d_out + (size_t)c0 * out_stride, st, out_stride)); }
         ctx->launches += 4;  // K1, K2a, K2b, K3
         ctx->wk_x.assign(x + (size_t)c0 * 7, x + (size_t)(c0 + nb) * 7);
+        ctx->wk_has_nn = true;  // K2a runs for every query of a kept frame and writes its nn_pos
     }
     CK(cudaEventRecord(ctx->h2d_done, st));
     ctx->counters[0] = (double)ctx->n_pts_total * B;
@@ -299,11 +301,13 @@ stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st) 
         if (memcmp(&ctx->wk_x[j * 7], x0, 7 * sizeof(double)) == 0) { slot = (int)j; break; }
     if (getenv("STL_NO_ASSOC_REUSE")) slot = -1;
     DevWork view = ctx->wk;
+    const uint32_t *nn_hint = nullptr;
     if (slot >= 0) {
         const long long nk = pk.n_kp_total, F = pk.n_kf;
         view.cand += slot;
         view.corr_kp += slot * nk; view.corr_pt += slot * nk; view.corr_sp += slot * nk; view.q_corr += slot * nk; view.q_kpsp += slot * nk;
         view.n_corr += slot * F; view.n_q += slot * F;
+        if (ctx->wk_has_nn) nn_hint = ctx->wk.nn_pos + slot * pk.n_mp_total;  // K2a's 1-NN of the same map points at this x
         ctx->assoc_reused += 1;
     } else {
         DevCand *hc = ctx->h_cand;
@@ -316,11 +320,12 @@ stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st) 
         { StageTimer t(ctx, STL_STAGE_ASSOC2D, st); CK(launch_assoc2d(pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, st, 0)); }
         ctx->launches += 1;
         ctx->wk_x.assign(x0, x0 + 7);
+        ctx->wk_has_nn = false;
     }
     cudaError_t e;
-    { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st); }
+    { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint); }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "associate: %s", cudaGetErrorString(e));
-    ctx->launches += 5;  // four association kernels, k_count_types (cub select kernels not counted)
+    ctx->launches += (ctx->dpr.plane_index && !ctx->dpr.use_gpr) ? 3 : 4;  // the association kernels (cub select kernels not counted)
     ctx->dbg_b = -1;
     ctx->last_x.clear();
     return STL_OK;
@@ -487,8 +492,8 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     ctx->max_kp = max_kp; ctx->max_bm_words = max_bm; ctx->k1_smem = k1_smem_new;
     cudaStream_t st = acquire_stream(ctx, nullptr);
     struct Scope {  // events and the raw-scan scratch are released on every exit path
-        cudaEvent_t ev0 = nullptr, ev1 = nullptr; float *d_raw = nullptr;
-        ~Scope() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); if (d_raw) cudaFree(d_raw); }
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr; float *d_raw = nullptr; BuildScratch scr;
+        ~Scope() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); if (d_raw) cudaFree(d_raw); scr.release(); }
     } scope;
     CK(cudaEventCreate(&scope.ev0)); CK(cudaEventCreate(&scope.ev1));
     cudaEvent_t ev0 = scope.ev0, ev1 = scope.ev1;
@@ -607,7 +612,7 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
             if (n > 0) CK(cudaMemcpyAsync(d_raw, p->scan_xyz + p->scan_offset[f0] * 3, 12 * (size_t)n, cudaMemcpyHostToDevice, st));
             std::vector<long long> off(f1 - f0 + 1);
             for (int f = f0; f <= f1; ++f) off[f - f0] = p->scan_offset[f];
-            cudaError_t e = build_scan_index(d_raw, off.data(), f1 - f0, f0, hk2.data(), pk, ctx->adj_r2, st, &k0_ms);
+            cudaError_t e = build_scan_index(d_raw, off.data(), f1 - f0, f0, hk2.data(), pk, ctx->adj_r2, st, scope.scr, &k0_ms);
             if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "index build: %s", cudaGetErrorString(e));
             f0 = f1;
         }
@@ -647,7 +652,7 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
             int f1 = f0 + 1;
             long long pts = hk2[f0].n_pad;
             while (f1 < F && pts + hk2[f1].n_pad <= (4ll << 20)) pts += hk2[f1++].n_pad;
-            cudaError_t e = build_plane_index(pk, hk2.data(), f0, f1 - f0, ctx->dpr, st);
+            cudaError_t e = build_plane_index(pk, hk2.data(), f0, f1 - f0, ctx->dpr, st, scope.scr);
             if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "plane index: %s", cudaGetErrorString(e));
             f0 = f1;
         }

@@ -67,15 +67,34 @@ struct DevWork {
     int *overflow = nullptr;      // K1 survivor-list overflow counter (diagnostic)
 };
 
+// Device scratch of the index build, grown on demand and kept for the whole upload (a cudaMalloc / cudaFree
+// pair per chunk of keyframes costs tens of milliseconds at these sizes).
+struct BuildScratch {
+    void *buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaError_t need(int i, size_t bytes) {
+        if (bytes <= cap[i]) return cudaSuccess;
+        if (buf[i]) cudaFree(buf[i]);
+        buf[i] = nullptr; cap[i] = 0;
+        const cudaError_t e = cudaMalloc(&buf[i], bytes);
+        if (e == cudaSuccess) cap[i] = bytes;
+        return e;
+    }
+    void release() {
+        for (int i = 0; i < 8; ++i) { if (buf[i]) cudaFree(buf[i]); buf[i] = nullptr; cap[i] = 0; }
+    }
+};
+
 // ---- index build (build.cu) ---------------------------------------------------
 // raw: [n][3] float32 device points of a chunk of keyframes; raw_off[nkf+1] host offsets.
 // adj_r2: squared radius of the leaf adjacency lists (<= 0: none are built)
 // kernel_ms (optional): the device time of the build kernels of this chunk is ADDED to it
 cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int nkf, int kf_begin, const DevKf *h_kf,
-                             DevPack &pack, float adj_r2, cudaStream_t st, float *kernel_ms = nullptr);
+                             DevPack &pack, float adj_r2, cudaStream_t st, BuildScratch &scr, float *kernel_ms = nullptr);
 
 // plane index (knn3d.cu): k-NN + plane of every point of keyframes [kf_begin, kf_begin + nkf)
-cudaError_t build_plane_index(const DevPack &pk, const DevKf *h_kf, int kf_begin, int nkf, const DevParams &pr, cudaStream_t st);
+cudaError_t build_plane_index(const DevPack &pk, const DevKf *h_kf, int kf_begin, int nkf, const DevParams &pr, cudaStream_t st,
+                              BuildScratch &scr);
 
 // ---- K1 (assoc2d.cu) ------------------------------------------------------------
 size_t assoc2d_smem_bytes(int max_kp, int max_bm_words, int max_cells, int max_groups);

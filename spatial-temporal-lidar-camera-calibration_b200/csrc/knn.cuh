@@ -72,6 +72,12 @@ struct Sink1 {
     float df = 3.402823466e+38f;  // d rounded up to float32
     uint32_t oi = 0xffffffffu, pos = 0xffffffffu;
     __device__ __forceinline__ bool may_contain(float lb) const { return lb <= df; }
+    // start from a scan point expected to be close (all lanes read the same address): every box test then
+    // already sees a finite bound.  The point is an ordinary candidate of the (d2, index) minimum.
+    __device__ __forceinline__ void seed(const ScanView &S, uint32_t p, double qx, double qy, double qz) {
+        const double dd = dist3e(qx, qy, qz, (double)S.px[p], (double)S.py[p], (double)S.pz[p]);
+        if (dd == dd) { d = dd; df = __double2float_ru(dd); oi = S.orig[p]; pos = p; }
+    }
     __device__ __forceinline__ void visit(const ScanView &S, int leaf, double qx, double qy, double qz, int lane) {
         const int g = leaf * kLeaf + lane;
         const double dd = dist3e(qx, qy, qz, (double)S.px[g], (double)S.py[g], (double)S.pz[g]);  // NaN for pads
@@ -303,8 +309,10 @@ __device__ __forceinline__ void knn_around_point(const ScanView &S, uint32_t pos
 // query to the home box stays inside the covered range (all bounds rounded to the safe side); otherwise
 // the descent finishes the search with the bound already found (re-visiting a leaf cannot change a
 // (d2, index) minimum).
+// `hint` (optional, 0xffffffff = none) is a scan point of leaf `home` believed to be near the query: it seeds the bound.
 __device__ __forceinline__ void nn_near_leaf(const ScanView &S, float adj_r, int home, double qx, double qy, double qz, Sink1 &nn,
-                                             int lane) {
+                                             int lane, uint32_t hint = 0xffffffffu) {
+    if (hint != 0xffffffffu) nn.seed(S, hint, qx, qy, qz);
     const float cov = scan_adjacent(S, home, qx, qy, qz, nn, lane);
     if (S.stats && lane == 0) atomicAdd(S.stats + 4, 1ull);
     if (cov >= 0.f && nn.pos != 0xffffffffu) {

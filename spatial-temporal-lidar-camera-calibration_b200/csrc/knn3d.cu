@@ -70,7 +70,7 @@ k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
         double qx, qy, qz;
         map_point_lidar(pk, K, c, f, ks.x, qx, qy, qz);
         Sink1 nn;
-        nn_near_leaf(S, pr.adj_r, (int)(ks.y >> 5), qx, qy, qz, nn, lane);
+        nn_near_leaf(S, pr.adj_r, (int)(ks.y >> 5), qx, qy, qz, nn, lane, ks.y);  // seeded with the associated scan point
         if (lane == 0) wk.nn_pos[qbase + qi] = nn.pos;
         if (pr.use_plane && !pr.plane_index) {  // with the plane index the neighbourhood of nn is already fitted
             SinkK kn(pr.k, pr.radius2);
@@ -209,25 +209,22 @@ k_index_plane(const DevPack pk, const int kf_begin, const DevParams pr, const lo
 
 }  // namespace
 
-cudaError_t build_plane_index(const DevPack &pk, const DevKf *h_kf, int kf_begin, int nkf, const DevParams &pr, cudaStream_t st) {
+cudaError_t build_plane_index(const DevPack &pk, const DevKf *h_kf, int kf_begin, int nkf, const DevParams &pr, cudaStream_t st,
+                              BuildScratch &scr) {
     const long long first = h_kf[kf_begin].pt_off;
     const long long npts = h_kf[kf_begin + nkf - 1].pt_off + h_kf[kf_begin + nkf - 1].n_pad - first;
     if (npts <= 0) return cudaSuccess;
     int max_pts = 0;
     for (int f = 0; f < nkf; ++f) max_pts = max_pts > h_kf[kf_begin + f].n_pad ? max_pts : h_kf[kf_begin + f].n_pad;
-    uint32_t *nb = nullptr; int *m = nullptr; double *last = nullptr;
-    cudaError_t e = cudaMalloc(&nb, 4 * (size_t)npts * kMaxK);
-    if (e == cudaSuccess) e = cudaMalloc(&m, 4 * (size_t)npts);
-    if (e == cudaSuccess) e = cudaMalloc(&last, 8 * (size_t)npts);
-    if (e == cudaSuccess) {
-        const int bx = (max_pts + kWarps * 16 - 1) / (kWarps * 16);  // ~16 points per warp
-        k_index_knn<<<dim3(bx, nkf), kWarps * 32, 0, st>>>(pk, kf_begin, pr, first, nb, m, last);
-        k_index_plane<<<dim3((max_pts + kPlaneThreads * 4 - 1) / (kPlaneThreads * 4), nkf), kPlaneThreads, 0, st>>>(pk, kf_begin, pr, first, nb, m, last);
-        e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    }
-    cudaFree(nb); cudaFree(m); cudaFree(last);
-    return e;
+    cudaError_t e = scr.need(2, 4 * (size_t)npts * kMaxK);
+    if (e == cudaSuccess) e = scr.need(4, 4 * (size_t)npts);
+    if (e == cudaSuccess) e = scr.need(3, 8 * (size_t)npts);
+    if (e != cudaSuccess) return e;
+    uint32_t *nb = (uint32_t *)scr.buf[2]; int *m = (int *)scr.buf[4]; double *last = (double *)scr.buf[3];
+    const int bx = (max_pts + kWarps * 16 - 1) / (kWarps * 16);  // ~16 points per warp
+    k_index_knn<<<dim3(bx, nkf), kWarps * 32, 0, st>>>(pk, kf_begin, pr, first, nb, m, last);
+    k_index_plane<<<dim3((max_pts + kPlaneThreads * 4 - 1) / (kPlaneThreads * 4), nkf), kPlaneThreads, 0, st>>>(pk, kf_begin, pr, first, nb, m, last);
+    return cudaGetLastError();  // stream order protects the scratch: the next chunk's kernels run after these
 }
 
 cudaError_t launch_align3d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, int debug, cudaStream_t st) {

@@ -104,16 +104,25 @@ k_lm_plane_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
     if (!lm_frame_active(wk, pr, f, nq)) return;
     const DevKf K = pk.kf[f];
     const ScanView S = make_view(pk, K);
+    const bool from_index = pr.plane_index && !pr.use_gpr;  // then k_lm_knn_a did not run: the covisibility test is made here
+    const int C = pk.n_covis;
     for (int qi = j * blockDim.x + threadIdx.x; qi < nq; qi += kPlaneSub * blockDim.x) {
         const long long slot = K.mp_off + qi;
-        const int m = wk.nb_m[slot];
         lm.stage[slot] = 0;
-        if (m < 0) continue;
         const uint32_t ci = wk.q_corr[K.kp_off + qi];
         const uint32_t kp = wk.corr_kp[K.kp_off + ci], sp = wk.corr_sp[K.kp_off + ci];
+        int m = 0;
+        if (from_index) {
+            bool any = false;
+            for (int s = 0; s < C; ++s) any = any || (pk.covis_valid[f * C + s] && !isnan(pk.covis_uv[(K.kp_off + kp) * C + s].x));
+            if (!any) continue;  // iba_local.cpp:259
+        } else {
+            m = wk.nb_m[slot];
+            if (m < 0) continue;
+        }
         const double cx = (double)S.px[sp], cy = (double)S.py[sp], cz = (double)S.pz[sp];
-        const PlaneOut po = (pr.plane_index && !pr.use_gpr) ? plane_lookup(pk, K, sp)
-                                                             : plane_fit(NbCoords{wk.nbx + slot, wk.nbx_stride}, m, wk.nb_last[slot], cx, cy, cz, pr);
+        const PlaneOut po = from_index ? plane_lookup(pk, K, sp)
+                                       : plane_fit(NbCoords{wk.nbx + slot, wk.nbx_stride}, m, wk.nb_last[slot], cx, cy, cz, pr);
         if (!po.gates_ok) continue;  // m < min_pts || d2[m-1] < min_diff^2 (pointcloud.h:754)
         const long long cs = K.kp_off + ci;  // block slot = correspondence slot
         lm.slot_kf[cs] = f;
@@ -139,7 +148,7 @@ k_lm_plane_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
 // L3: map point -> LiDAR frame with the association extrinsic, 1-NN gate, neighbourhood of that point
 // (iba_local.cpp:283-295)
 __global__ void __launch_bounds__(kWarps * 32, STL_KNN_MINB)
-k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
+k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm, const uint32_t *__restrict__ nn_hint) {
     const int j = blockIdx.x % kAssocSub, f = blockIdx.x / kAssocSub;
     int nq;
     if (!lm_frame_active(wk, pr, f, nq)) return;
@@ -161,7 +170,11 @@ k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
         lm_map_point(pk, K, f, kp, Mx, My, Mz);
         xform(c0.Ri, c0.ti, dmul(Mx, c0.s), dmul(My, c0.s), dmul(Mz, c0.s), qx, qy, qz);  // initSE3.inverse() * (MapPoint * init_scale)
         Sink1 nn;
-        nn_near_leaf(S, pr.adj_r, (int)(sp >> 5), qx, qy, qz, nn, lane);
+        // seed: the 1-NN the evaluation at this same extrinsic found for (the float32-scaled twin of) this map
+        // point when it is at hand, else the associated scan point
+        uint32_t hint = nn_hint ? nn_hint[slot] : sp;
+        if (hint == 0xffffffffu) hint = sp;
+        nn_near_leaf(S, pr.adj_r, (int)(hint >> 5), qx, qy, qz, nn, lane, hint);
         if (nn.d > pr.max_3d_dist2) {  // iba_local.cpp:289
             if (lane == 0) lm.nnb_pos[slot] = 0xffffffffu;
             continue;
@@ -220,15 +233,8 @@ k_lm_plane_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
         g[6] = gates_ok ? n3[0] : 0.0; g[7] = gates_ok ? n3[1] : 0.0; g[8] = gates_ok ? n3[2] : 1.0;
         lm.type3d[cs] = state ? 2 : 1;  // Point2Plane_Factor : Point2Point_Factor (iba_local.cpp:300-309)
         lm.flag3d[cs] = 1;
+        if (!state) atomicAdd(lm.d_counts + 2, 1);  // point-to-point blocks (integer count: order does not matter)
     }
-}
-
-__global__ void k_count_types(const uint8_t *__restrict__ type3d, const int *__restrict__ idx3d, const int *__restrict__ n3d_dev, int *out) {
-    const int n3d = *n3d_dev;  // written by the select just before, on the same stream
-    int pt = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n3d; i += gridDim.x * blockDim.x) pt += type3d[idx3d[i]] == 1;
-    for (int o = 16; o; o >>= 1) pt += __shfl_down_sync(0xffffffffu, pt, o);
-    if ((threadIdx.x & 31) == 0 && pt) atomicAdd(out, pt);
 }
 
 // ------------------------------------------------------------------ K4b
@@ -647,7 +653,7 @@ void lm_free(LmState &lm) {
 // Enqueues BuildProblem on `st` and returns without waiting: the block counts stay on the device
 // (d_counts: plane, 3-D, point-to-point, GPR), where the linearisation kernels read them; a copy lands
 // in pinned host memory behind `counts_done` for callers that want the numbers (lm_block_counts).
-cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st) {
+cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st, const uint32_t *nn_hint) {
     cudaError_t e;
 #define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
     const long long ns = pk.n_kp_total > 0 ? pk.n_kp_total : 1;
@@ -679,9 +685,10 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
     }
     lm.ready = false;
     TRY(cudaMemsetAsync(lm.flags, 0, lm.flags_bytes, st));
-    k_lm_knn_a<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
+    if (!(pr.plane_index && !pr.use_gpr))  // with the plane index there is no neighbourhood to search at the scan point
+        k_lm_knn_a<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
     k_lm_plane_a<<<(unsigned)(pk.n_kf * kPlaneSub), 128, 0, st>>>(pk, wk, pr, lm);
-    k_lm_knn_b<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
+    k_lm_knn_b<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm, nn_hint);
     k_lm_plane_b<<<(unsigned)(pk.n_kf * kPlaneSub), 128, 0, st>>>(pk, wk, pr, lm);
     TRY(cudaGetLastError());
     cub::CountingInputIterator<int> it(0);
@@ -693,7 +700,6 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
         tb = lm.tmp_bytes;
         TRY(cub::DeviceSelect::Flagged(lm.d_tmp, tb, it, lm.flagG, lm.idxG, lm.d_counts + 3, (int)ns, st));
     }
-    k_count_types<<<64, 256, 0, st>>>(lm.type3d, lm.idx3d, lm.d_counts + 1, lm.d_counts + 2);
     TRY(cudaGetLastError());
     TRY(cudaMemcpyAsync(lm.h_counts, lm.d_counts, 16, cudaMemcpyDeviceToHost, st));
     TRY(cudaEventRecord(lm.counts_done, st));
@@ -736,12 +742,13 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
     TRY(cudaMemcpyAsync(lm.d_cand, hc, sizeof(LmCand) * B, cudaMemcpyHostToDevice, st));
     TRY(cudaEventRecord(lm.h2d_done, st));
     // grids are sized from the host-side upper bound of the block count (one block per map-point-carrying
-    // keypoint at most), or from the real counts when the host already has them; the kernels read the
-    // exact counts from the device
-    const long long work = lm.counts_valid ? (lm.n2d > lm.n3d ? lm.n2d : lm.n3d) : lm.max_blocks;
+    // keypoint at most) — never from the counts themselves, so that the chunking, and with it the order
+    // of the fp64 sums, is the same whether or not the host has looked at the counts; the kernels read
+    // the exact counts from the device
+    const long long work = lm.max_blocks;
     long long chunks_ll = (work + kLinThreads * 2 - 1) / (kLinThreads * 2);
     int chunks = (int)(chunks_ll < 1 ? 1 : (chunks_ll > 148 * 8 ? 148 * 8 : chunks_ll));
-    const long long gwork = !lm.use_gpr ? 0 : (lm.counts_valid ? lm.nG : lm.max_blocks);
+    const long long gwork = lm.use_gpr ? lm.max_blocks : 0;
     long long gchunks_ll = gwork > 0 ? (gwork + kGprWarps * 4 - 1) / (kGprWarps * 4) : 0;
     int gchunks = (int)(gchunks_ll > 148 * 8 ? 148 * 8 : gchunks_ll);
     const int stride = chunks + gchunks;
