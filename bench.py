@@ -348,7 +348,11 @@ def main():
     t_upload = time.time() - t0
     st0 = ctx.stage_stats()
     build_ms, pidx_ms = st0["build"][0], st0["plane_index"][0]
-    stream = torch.cuda.current_stream()
+    # a stream of our own: the handle of torch's default stream is 0, which the C-ABI reads as "the context's own
+    # stream" — events recorded on the legacy default stream would then not be ordered with the library's work
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     W = _abi.STL_STEP_NSUMS if mode != "eval" else _abi.STL_EVAL_NSUMS
     d_out = torch.zeros((max(args.steps, 1), B, W), dtype=torch.float64, device=dev)   # one record row per timed step
@@ -462,7 +466,12 @@ def main():
         k1_ms, k1_n = stats["assoc2d"]
         k1_avg = k1_ms / max(k1_n, 1)
         n_pts, n_kp = pack.n_points, pack.n_keypoints
-        k1_bytes = (12.0 * n_pts + 16.0 * n_kp) * B  # per launch: B candidates over this rank's keyframes
+        # algorithmic bytes of one K1 launch = one chunk of `per_launch` candidates over this rank's keyframes: the
+        # scan is read once per chunk (12 B / point; candidates 2.. of the chunk are served by L2), keypoints in
+        # and correspondences out per candidate (16 B / keypoint)
+        launches_per_step = max(1, round(k1_n / max(args.steps, 1)))
+        per_launch = B / launches_per_step
+        k1_bytes = 12.0 * n_pts + 16.0 * n_kp * per_launch
         achieved = k1_bytes / (k1_avg * 1e-3) / 1e9 if k1_avg > 0 else 0.0
         tot_stage = sum(v[0] for k, v in stats.items() if k not in ("build", "plane_index"))
         share = {k: round(v[0] / tot_stage, 4) for k, v in stats.items() if v[1] and k not in ("build", "plane_index")}
@@ -493,6 +502,7 @@ def main():
                 "kernel": "k_assoc2d (K1: transform + project + 2-D association)", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": k1_bytes, "avg_launch_ms": k1_avg, "launches": k1_n,
+                "candidates_per_launch": per_launch,
             },
             "roofline_k0": {
                 "kernel": "K0 index build (k_bbox, k_morton, radix sort, k_scatter, k_kd_refine, AABBs, k_leaf_adj), once per pack",
@@ -505,7 +515,7 @@ def main():
             "stage_ms_per_launch": {k: round(v[0] / v[1], 4) for k, v in stats.items() if v[1] and k not in ("build", "plane_index")},
             "knn": {"queries_per_eval": knn_q_eval, "queries_per_s_whole_step": knn_q_eval * value,
                     "k2_pairs_per_s": (q3 * B / (world if by_kf else 1) / (k2_ms / max(k2_n, 1) * 1e-3)) if k2_ms > 0 else None},
-            "k1_point_transforms_per_s": (float(n_pts) * B / (k1_avg * 1e-3)) if k1_avg > 0 else None,
+            "k1_point_transforms_per_s": (float(n_pts) * per_launch / (k1_avg * 1e-3)) if k1_avg > 0 else None,
             "assoc_reused": wc["assoc_reused"],
             "result_check": {"f_sums": [float(last[0, 0]), float(last[0, 1])], "frames_kept": float(last[0, 10]),
                              "lm_cost": float(last[0, 12]) if mode != "eval" else None},
@@ -527,7 +537,7 @@ def main():
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                line["roofline"]["traffic"] = tj["dram_bytes_per_launch"] * B * (pack.n_kf / float(tj.get("keyframes", pack.n_kf)))
+                line["roofline"]["traffic"] = tj["dram_bytes_per_launch"] * (pack.n_kf / float(tj.get("keyframes", pack.n_kf))) if per_launch == 1 else None
                 line["roofline"]["traffic_source"] = "static: " + tj.get("source", "profiles/k1_traffic.json") + " (ncu --set full, scaled to this launch's units)"
             except Exception:
                 pass

@@ -32,7 +32,7 @@ constexpr int kWarps = 8;
 constexpr int kAssocSub = 4;
 constexpr int kPlaneSub = 4;  // CTAs of 128 threads per keyframe in the thread-per-query plane kernels
 constexpr int kLinVals = 41;  // cost, g[7], H upper 28, n2d, npt, npl, nres, ngpr
-constexpr int kGprWarps = 3;
+constexpr int kGprWarps = 1;  // one warp per CTA: the dual kernel matrix of a block takes ~40 KB of shared memory
 constexpr int kLinThreads = 128;
 
 // ------------------------------------------------------------------ K4a (four small kernels)
@@ -425,60 +425,92 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
 
 // ------------------------------------------------------------------ K4b': IBA_GPRFactor blocks
 // IBACalib2.hpp:472-507 + TGPR::fit_predict (GPR.hpp:449-491): the neighbours are projected with the
-// CURRENT extrinsic, K = sigma^2 exp(-D/2l^2) + sigma_n I, alpha = K^-1 y (LLT), z = k*^T alpha, the
-// keypoint is back-projected at depth z and re-projected into the covisible keyframes.
-// One warp per block, lane j <-> neighbour j, matrices in shared memory.  The reference
-// differentiates through the Cholesky with Jets; here the same derivative is formed by the adjoint
-// identity  dz = dk*^T alpha + beta^T (dy - dK alpha),  beta = K^-1 k*  (no dual-number matrices).
+// CURRENT extrinsic, K = sigma^2 exp(-D/2l^2) + sigma_n I, alpha = K^-1 y (Eigen::LLT), z = k*^T alpha,
+// the keypoint is back-projected at depth z and re-projected into the covisible keyframes.
+//
+// K is conditioned like 1e12 (sigma_n = 1e-10), so HOW the derivative is formed decides its low digits.
+// The reference differentiates by running the whole algorithm on ceres::Jet numbers; this kernel does the
+// same, operation for operation: the kernel matrix, the unblocked lower Cholesky (Eigen's LLT for n < 32),
+// both triangular solves and the prediction are evaluated on D7 duals in the order of the reference's
+// loops (an adjoint formulation — one factorisation, no dual matrices — was measured 2e-6 off in J^T J,
+// above the 1e-6 bar).  What can still differ from a CPU evaluation is exp() (<= 1 ulp between libms).
+// One warp per block, lane i <-> row i; the dual matrix lives in shared memory, component-major, lower
+// triangle packed.
+constexpr int kGprTri = 32 * 33 / 2;
 struct GprSmem {
-    double K[32][33];
-    double xu[32], xv[32], y[32], alpha[32], beta[32], ks[32];
-    double dxu[7][32], dxv[7][32], dy[7][32];
+    double L[8][kGprTri];                      // K, then its Cholesky factor (lower triangle, packed by rows)
+    double xu[8][32], xv[8][32], y[8][32];     // neighbour pixels and depths (duals)
+    double al[8][32];                          // alpha
 };
 
-__device__ __forceinline__ double warp_sum(double v) {
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+__device__ __forceinline__ D7 ld7(const double (*m)[kGprTri], int idx) {
+    D7 r; r.a = m[0][idx];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) r.v[c] = m[1 + c][idx];
+    return r;
+}
+__device__ __forceinline__ void st7(double (*m)[kGprTri], int idx, const D7 &x) {
+    m[0][idx] = x.a;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) m[1 + c][idx] = x.v[c];
+}
+__device__ __forceinline__ D7 ld7v(const double (*m)[32], int i) {
+    D7 r; r.a = m[0][i];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) r.v[c] = m[1 + c][i];
+    return r;
+}
+__device__ __forceinline__ void st7v(double (*m)[32], int i, const D7 &x) {
+    m[0][i] = x.a;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) m[1 + c][i] = x.v[c];
+}
+__device__ __forceinline__ D7 d7_sqrt_dev(const D7 &f) {  // Jet sqrt: (sqrt a, f.v / (2 sqrt a))
+    D7 r; r.a = sqrt(f.a);
+    const double t = 1.0 / (2.0 * r.a);
+#pragma unroll
+    for (int c = 0; c < 7; ++c) r.v[c] = t * f.v[c];
+    return r;
+}
+__device__ __forceinline__ D7 d7_exp_dev(const D7 &f) {   // Jet exp: (e^a, e^a f.v)
+    D7 r; r.a = exp(f.a);
+#pragma unroll
+    for (int c = 0; c < 7; ++c) r.v[c] = r.a * f.v[c];
+    return r;
+}
+__device__ __forceinline__ D7 shfl7(const D7 &x, int src) {
+    D7 r; r.a = __shfl_sync(0xffffffffu, x.a, src);
+#pragma unroll
+    for (int c = 0; c < 7; ++c) r.v[c] = __shfl_sync(0xffffffffu, x.v[c], src);
+    return r;
 }
 
-// solves L L^T x = rhs in place (L = lower triangle of S.K incl. diagonal); lane i owns x[i]
-__device__ __forceinline__ double chol_solve(const GprSmem &S, double rhs, int n, int lane) {
-    double v = rhs;
-    for (int i = 0; i < n; ++i) {  // forward: L w = rhs
-        const double wi = __shfl_sync(0xffffffffu, v, i) / S.K[i][i];
-        if (lane == i) v = wi;
-        else if (lane > i && lane < n) v -= S.K[lane][i] * wi;
-    }
-    for (int i = n - 1; i >= 0; --i) {  // backward: L^T x = w
-        const double xi = __shfl_sync(0xffffffffu, v, i) / S.K[i][i];
-        if (lane == i) v = xi;
-        else if (lane < i) v -= S.K[i][lane] * xi;
-    }
-    return v;
-}
-
-// grid (chunks, B)
+// grid (chunks, B), one warp per CTA
 template <bool WB>
-__global__ void __launch_bounds__(kGprWarps * 32)
+__global__ void __launch_bounds__(32)
 k_linearize_gpr(const DevPack pk, const DevParams pr, const LmState lm, const LmCand *__restrict__ cands, double *__restrict__ partial,
                 int partial_stride, int partial_off, const BlockOut bo) {
-    __shared__ GprSmem SM[kGprWarps];
+    __shared__ GprSmem S;
     __shared__ LmCand c;
+    const int lane = threadIdx.x;
     {
         const double *src = reinterpret_cast<const double *>(cands + blockIdx.y);
         double *dst = reinterpret_cast<double *>(&c);
-        for (int i = threadIdx.x; i < (int)(sizeof(LmCand) / 8); i += blockDim.x) dst[i] = src[i];
+        for (int i = lane; i < (int)(sizeof(LmCand) / 8); i += 32) dst[i] = src[i];
     }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    GprSmem &S = SM[warp];
+    __syncwarp();
     Acc A;
 #pragma unroll
     for (int i = 0; i < kLinVals; ++i) A.v[i] = 0.0;
     const int C = pk.n_covis;
-    const double sigma2 = pr.gpr_sigma * pr.gpr_sigma, coef = -0.5 / (pr.gpr_l * pr.gpr_l);
+    // constants as the reference forms them on Jets with zero partials: sigma*sigma, T(-0.5)/(l*l) = -0.5 * (1/(l*l))
+    const double sigma2 = pr.gpr_sigma * pr.gpr_sigma;
+    const double inv_l2 = 1.0 / (pr.gpr_l * pr.gpr_l);
+    const double coef = -0.5 * inv_l2;
+    const D7 kdiag = d7_const(sigma2 * exp(coef * 0.0) + pr.gpr_noise);
     const int nG = lm.d_counts[3];
-    for (int it = blockIdx.x * kGprWarps + warp; it < nG; it += gridDim.x * kGprWarps) {
+    for (int it = blockIdx.x; it < nG; it += gridDim.x) {
         const int cs = lm.idxG[it];
         const int f = lm.slot_kf[cs];
         const uint32_t kp = lm.slot_kp[cs];
@@ -490,75 +522,76 @@ k_linearize_gpr(const DevPack pk, const DevParams pr, const LmState lm, const Lm
         const float2 kxy = pk.kp_xy[K.kp_off + kp];
         const double u0 = kxy.x, v0 = kxy.y;
         __syncwarp();
-        // 1. neighbour j -> camera frame with the candidate (duals), pixel coordinates and depth
+        // 1. neighbour j -> camera frame with the candidate, pixel coordinates X_j and depth y_j (IBACalib2.hpp:478-489)
+        D7 myu = d7_const(0.0), myv = d7_const(0.0);
         if (lane < n) {
             const uint32_t p = lm.gpr_nb[ms * kMaxK + lane];
             const double px = (double)pk.px[K.pt_off + p], py = (double)pk.py[K.pt_off + p], pz = (double)pk.pz[K.pt_off + p];
             D7 tf[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) tf[i] = ((c.R[i * 3] * px + c.R[i * 3 + 1] * py) + c.R[i * 3 + 2] * pz) + c.t[i];
-            const D7 xu = (tf[0] * fx) / tf[2] + cx, xv = (tf[1] * fy) / tf[2] + cy;
-            S.xu[lane] = xu.a; S.xv[lane] = xv.a; S.y[lane] = tf[2].a;
-#pragma unroll
-            for (int q = 0; q < 7; ++q) { S.dxu[q][lane] = xu.v[q]; S.dxv[q][lane] = xv.v[q]; S.dy[q][lane] = tf[2].v[q]; }
+            myu = (tf[0] * fx) / tf[2] + cx;
+            myv = (tf[1] * fy) / tf[2] + cy;
+            st7v(S.xu, lane, myu); st7v(S.xv, lane, myv); st7v(S.y, lane, tf[2]);
         }
         __syncwarp();
-        // 2. kernel matrix (both triangles; the strict upper one survives the factorisation)
-        const double mxu = lane < n ? S.xu[lane] : 0.0, mxv = lane < n ? S.xv[lane] : 0.0;
-        for (int r = 0; r < n; ++r) {
-            if (lane < n) {
-                const double dx = S.xu[r] - mxu, dy = S.xv[r] - mxv;
-                S.K[r][lane] = (r == lane) ? sigma2 + pr.gpr_noise : sigma2 * exp(coef * (dx * dx + dy * dy));
+        // 2. kernel matrix, lower triangle: K(i, j) = sigma2 * exp(coef * |X_j - X_i|^2) for j < i (self_pdist, GPR.hpp:41-54,
+        //    forms it at (ri = j, ci = i) as d = X[ri] - X[ci] and mirrors it); diagonal sigma2 * exp(0) + sigma_noise
+        if (lane < n) {
+            for (int j = 0; j < lane; ++j) {
+                const D7 dx = ld7v(S.xu, j) - myu, dy = ld7v(S.xv, j) - myv;
+                const D7 kv = d7_exp_dev((dx * dx + dy * dy) * coef) * sigma2;
+                st7(S.L, tri(lane, j), kv);
             }
+            st7(S.L, tri(lane, lane), kdiag);
         }
         __syncwarp();
-        // 3. left-looking Cholesky, lower triangle in place (Eigen::LLT unblocked order)
+        // 3. Eigen::LLT, unblocked (n < 32): for k: L_kk = sqrt(K_kk - sum_j L_kj^2); L_ik = (K_ik - sum_j L_ij L_kj) / L_kk
         for (int k = 0; k < n; ++k) {
-            double v = 0.0;
+            D7 v = d7_const(0.0);
             if (lane >= k && lane < n) {
-                v = S.K[lane][k];
-                for (int j = 0; j < k; ++j) v -= S.K[lane][j] * S.K[k][j];
+                v = ld7(S.L, tri(lane, k));
+                for (int j = 0; j < k; ++j) v = v - ld7(S.L, tri(lane, j)) * ld7(S.L, tri(k, j));
             }
-            const double d = sqrt(__shfl_sync(0xffffffffu, v, k));
-            if (lane == k) S.K[k][k] = d;
-            else if (lane > k && lane < n) S.K[lane][k] = v / d;
+            D7 xk = shfl7(v, k);
+            xk = d7_sqrt_dev(xk);
+            if (lane == k) st7(S.L, tri(k, k), xk);
+            else if (lane > k && lane < n) st7(S.L, tri(lane, k), v / xk);
             __syncwarp();
         }
-        // 4. alpha = K^-1 y, k*, beta = K^-1 k*, z
-        const double alpha = chol_solve(S, lane < n ? S.y[lane] : 0.0, n, lane);
-        double ks = 0.0;
-        if (lane < n) { const double dx = mxu - u0, dy = mxv - v0; ks = sigma2 * exp(coef * (dx * dx + dy * dy)); }
-        const double beta = chol_solve(S, ks, n, lane);
-        if (lane < n) { S.alpha[lane] = alpha; S.beta[lane] = beta; S.ks[lane] = ks; }
-        __syncwarp();
-        D7 z;
-        z.a = warp_sum(lane < n ? ks * alpha : 0.0);
-        // 5. derivatives by the adjoint identity
-        double w[7];
-#pragma unroll
-        for (int q = 0; q < 7; ++q) w[q] = 0.0;
-        if (lane < n) {
-            double acc[7];
-#pragma unroll
-            for (int q = 0; q < 7; ++q) acc[q] = 0.0;
-            for (int k = 0; k < n; ++k) {
-                if (k == lane) continue;
-                const double kv = lane < k ? S.K[lane][k] : S.K[k][lane];  // original kernel value (strict upper triangle)
-                const double ex = mxu - S.xu[k], ey = mxv - S.xv[k];
-                const double g = kv * coef * 2.0 * S.alpha[k];
-#pragma unroll
-                for (int q = 0; q < 7; ++q) acc[q] += g * (ex * (S.dxu[q][lane] - S.dxu[q][k]) + ey * (S.dxv[q][lane] - S.dxv[q][k]));
+        // 4. alpha = K^-1 y: forward substitution (row order), then backward (each row sums its terms in ascending column order)
+        {
+            D7 v = lane < n ? ld7v(S.y, lane) : d7_const(0.0);
+            for (int j = 0; j < n; ++j) {
+                D7 aj = v / ld7(S.L, tri(min(lane, n - 1), min(lane, n - 1)));  // meaningful on lane j only
+                aj = shfl7(aj, j);
+                if (lane == j) v = aj;
+                else if (lane > j && lane < n) v = v - ld7(S.L, tri(lane, j)) * aj;
             }
-            const double gs = ks * coef * 2.0 * alpha, ex0 = mxu - u0, ey0 = mxv - v0;
-#pragma unroll
-            for (int q = 0; q < 7; ++q)
-                w[q] = gs * (ex0 * S.dxu[q][lane] + ey0 * S.dxv[q][lane]) + beta * (S.dy[q][lane] - acc[q]);
+            if (lane < n) st7v(S.al, lane, v);
+            __syncwarp();
+            for (int i = n - 1; i >= 0; --i) {
+                if (lane == i) {
+                    D7 w = ld7v(S.al, i);
+                    for (int j = i + 1; j < n; ++j) w = w - ld7(S.L, tri(j, i)) * ld7v(S.al, j);
+                    st7v(S.al, i, w / ld7(S.L, tri(i, i)));
+                }
+                __syncwarp();
+            }
         }
-#pragma unroll
-        for (int q = 0; q < 7; ++q) z.v[q] = warp_sum(w[q]);
+        // 5. Kstar_j = sigma2 * exp((-0.5 * inv_l2) * |X_j - x*|^2) (rbf_kernel_2d, GPR.hpp:57-63), z = sum_j Kstar_j alpha_j in j order
+        D7 term = d7_const(0.0);
+        if (lane < n) {
+            const D7 dx = myu - u0, dy = myv - v0;
+            const D7 ks = d7_exp_dev((dx * dx + dy * dy) * (-0.5 * inv_l2)) * sigma2;
+            term = ks * ld7v(S.al, lane);
+        }
+        D7 z = d7_const(0.0);
+        for (int j = 0; j < n; ++j) z = z + shfl7(term, j);
         // 6. back-projection at depth z, covisible re-projection, Huber, normal equations (lane 0)
         if (lane == 0) {
-            const D7 P0[3] = {z * ((u0 - cx) / fx), z * ((v0 - cy) / fy), z};
+            const double ifx = 1.0 / fx, ify = 1.0 / fy;  // Jet division by a constant: multiply by 1/g
+            const D7 P0[3] = {(z * (u0 - cx)) * ifx, (z * (v0 - cy)) * ify, z};
             double sq = 0.0;
             int nres = 0;
             for (int s = 0; s < C; ++s) {
@@ -597,16 +630,13 @@ k_linearize_gpr(const DevPack pk, const DevParams pr, const LmState lm, const Lm
             if (WB) put_head(bo, gblk, 3, f, kp, nres);
         }
     }
-    // per-CTA partial: only lane 0 of every warp holds data
-    __shared__ double red[kGprWarps][kLinVals];
+    // per-CTA partial: lane 0 holds the sums
+    __shared__ double red[kLinVals];
     if (lane == 0)
-        for (int i = 0; i < kLinVals; ++i) red[warp][i] = A.v[i];
-    __syncthreads();
-    if (threadIdx.x < kLinVals) {
-        double x = 0.0;
-        for (int w2 = 0; w2 < kGprWarps; ++w2) x += red[w2][threadIdx.x];
-        partial[((long long)blockIdx.y * partial_stride + partial_off + blockIdx.x) * kLinVals + threadIdx.x] = x;
-    }
+        for (int i = 0; i < kLinVals; ++i) red[i] = A.v[i];
+    __syncwarp();
+    for (int i = lane; i < kLinVals; i += 32)
+        partial[((long long)blockIdx.y * partial_stride + partial_off + blockIdx.x) * kLinVals + i] = red[i];
 }
 
 // one CTA per candidate: sums the per-CTA partials in order and expands H to the full symmetric 7x7
@@ -749,7 +779,7 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
     long long chunks_ll = (work + kLinThreads * 2 - 1) / (kLinThreads * 2);
     int chunks = (int)(chunks_ll < 1 ? 1 : (chunks_ll > 148 * 8 ? 148 * 8 : chunks_ll));
     const long long gwork = lm.use_gpr ? lm.max_blocks : 0;
-    long long gchunks_ll = gwork > 0 ? (gwork + kGprWarps * 4 - 1) / (kGprWarps * 4) : 0;
+    long long gchunks_ll = gwork > 0 ? (gwork + 3) / 4 : 0;
     int gchunks = (int)(gchunks_ll > 148 * 8 ? 148 * 8 : gchunks_ll);
     const int stride = chunks + gchunks;
     const long long need = (long long)B * stride * kLinVals;
@@ -763,8 +793,8 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
     else k_linearize<false><<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, bo);
     TRY(cudaGetLastError());
     if (gchunks > 0) {
-        if (blocks) k_linearize_gpr<true><<<dim3(gchunks, B), kGprWarps * 32, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, chunks, bo);
-        else k_linearize_gpr<false><<<dim3(gchunks, B), kGprWarps * 32, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, chunks, bo);
+        if (blocks) k_linearize_gpr<true><<<dim3(gchunks, B), 32, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, chunks, bo);
+        else k_linearize_gpr<false><<<dim3(gchunks, B), 32, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, chunks, bo);
         TRY(cudaGetLastError());
     }
     k_lin_finish<<<B, 1024, 0, st>>>(lm.partial, stride, d_out, out_stride > 0 ? out_stride : STL_LIN_NSUMS);

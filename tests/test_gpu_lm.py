@@ -78,7 +78,9 @@ def test_lm_steps_reduce_the_cost_like_the_oracle(gpu_ctx, orc, small_candidates
 
 def test_gpr_factor_blocks(pkg, oracle_mod, small_pack, small_candidates):
     """use_gpr: non-planar neighbourhoods get an IBA_GPRFactor (the branch the reference keeps commented
-    out, iba_local.cpp:272-280); GPU derivative by the adjoint identity vs the oracle's Jet-Cholesky."""
+    out, iba_local.cpp:272-280).  The kernel runs the reference's algorithm on duals in the reference's own
+    operation order (Jets through the unblocked Cholesky), so cost, J^T r and J^T J meet the 1e-6 bar although the
+    kernel matrix is conditioned like 1e12; the printed figures are what is observed."""
     capi = importlib.import_module(PKG + ".capi")
     p = pkg.default_params(); p.use_gpr = 1
     pack = small_pack[0].shard(0, 3)
@@ -91,12 +93,14 @@ def test_gpr_factor_blocks(pkg, oracle_mod, small_pack, small_candidates):
         got = c.linearize(small_candidates[:3])
     assert np.array_equal(nb_g, nb_o) and nb_o[3] > 20
     assert np.array_equal(got[:, 57:], want[:, 57:])
-    # the kernel matrix (sigma^2 = 100, sigma_n = 1e-10, neighbours a few pixels apart) has a condition number
-    # around 1e12, so two correct evaluations agree to ~1e-8: the north-star tolerance (1e-6 relative) applies
-    assert np.allclose(got[:, 0], want[:, 0], rtol=1e-6, atol=0)
     sg = np.abs(want[:, 1:8]).max(axis=1, keepdims=True); sh = np.abs(want[:, 8:57]).max(axis=1, keepdims=True)
-    assert np.allclose(got[:, 1:8], want[:, 1:8], rtol=1e-5, atol=1e-6 * sg)
-    assert np.allclose(got[:, 8:57], want[:, 8:57], rtol=1e-5, atol=1e-6 * sh)
+    print("GPR parity: cost rel %.2e, J^T r %.2e, J^T J %.2e (relative to the largest entry); Frobenius J^T J %.2e" % (
+        np.abs(got[:, 0] / want[:, 0] - 1).max(), (np.abs(got[:, 1:8] - want[:, 1:8]) / sg).max(),
+        (np.abs(got[:, 8:57] - want[:, 8:57]) / sh).max(),
+        max(np.linalg.norm(got[i, 8:57] - want[i, 8:57]) / np.linalg.norm(want[i, 8:57]) for i in range(len(got)))))
+    assert np.allclose(got[:, 0], want[:, 0], rtol=1e-6, atol=0)
+    assert np.allclose(got[:, 1:8], want[:, 1:8], rtol=1e-6, atol=1e-6 * sg)
+    assert np.allclose(got[:, 8:57], want[:, 8:57], rtol=1e-6, atol=1e-6 * sh)
 
 
 @pytest.mark.parametrize("use_gpr", [0, 1])
