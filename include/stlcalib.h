@@ -99,6 +99,12 @@ typedef struct stl_params {
      * stl_associate / stl_linearize_* are refused with variant 1 (iba_local.cpp has no such variant);
      * plane_index works with both (the index is then fitted with the stable flavour's gates). */
     int32_t variant;              /* 0                                               */
+    /* use_gpr only: fit (sigma, l) of every GPR factor when it is created, as IBA_GPRFactor's constructor does
+     * with GPRParams.optimize (IBACalib2.hpp:441-461 -> GPR::fit, GPR.hpp:350-387; IBALocalParams.optimize_gpr).
+     * The fit runs on the host inside stl_associate (the reference keeps it on the CPU too); see stl_gpr_fit.
+     * 0 keeps gpr_sigma / gpr_l for all factors. */
+    int32_t gpr_optimize;         /* 0                                               */
+    int32_t gpr_grad_flavour;     /* 0 analytic gradient, 1 the expressions of GPR.hpp:166-171 as coded */
 } stl_params_t;
 
 /*
@@ -261,6 +267,24 @@ stl_status_t stl_linearize_batch_device(stl_ctx_t *ctx, const double *x, int32_t
  * order.  All buffers are host memory sized for `cap_blocks`; *n_blocks_out receives the count. */
 stl_status_t stl_eval_blocks(stl_ctx_t *ctx, const double *x, int32_t rmax, int64_t cap_blocks, int32_t *type, int32_t *kf,
                              int32_t *kp, int32_t *n_res, double *residuals, double *jacobians, int64_t *n_blocks_out);
+
+/* ---- GPR hyper-parameters (host; no context, no GPU) -------------------------------------------------
+ * The objective of GPR::fit — GPRHyperLoss::Evaluate (GPR.hpp:154-174): negative log marginal likelihood of the
+ * depths y[n] observed at pixels x[n][2] under K = sigma^2 exp(-D / 2 l^2) + sigma_noise I — and its gradient
+ * with respect to (sigma, l).  flavour 0: the derivative of that objective; flavour 1: the expressions of
+ * GPR.hpp:166-171,218-222 exactly as written (dK/dsigma = 2 sigma Kff with the full Kff, dK/dl = (Kff * Dist) / l^3
+ * as a matrix product).  Returns STL_ERR_INVALID if the Cholesky factorisation fails (Evaluate returns false). */
+stl_status_t stl_gpr_nlml(const double *x, const double *y, int32_t n, double sigma_noise, double sigma, double l, int32_t flavour,
+                          double *cost, double grad[2]);
+/* GPR::fit (GPR.hpp:350-387): at most max_iter (15 in the reference) quasi-Newton iterations on the objective above
+ * from (sigma0, l0).  out = {sigma, l, cost at the start, cost at the end, iterations, objective evaluations}.
+ * The reference drives the same objective with ceres::GradientProblemSolver (L-BFGS); its iterate path is not
+ * reproducible without Ceres — see csrc/gprfit.hpp. */
+stl_status_t stl_gpr_fit(const double *x, const double *y, int32_t n, double sigma_noise, double sigma0, double l0, int32_t max_iter,
+                         int32_t flavour, double out[6]);
+/* (sigma, l) of the GPR blocks of the last association, in block order ([n_blocks[3]][2]); the per-problem values
+ * unless params.gpr_optimize fitted them. */
+stl_status_t stl_gpr_hyper(stl_ctx_t *ctx, double *sigma_l, int64_t cap_blocks);
 
 /* Block counts {plane 2d, pt, pl, gpr 2d} of the last association of this context (waits for it). */
 stl_status_t stl_block_counts(stl_ctx_t *ctx, int64_t n_blocks[4]);

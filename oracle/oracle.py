@@ -48,6 +48,9 @@ _SYMS = {
     "orc_block_key": (None, [_vp, C.c_int64, _i32p]),
     "orc_block_eval": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp]),
     "orc_block_eval_plain": (C.c_int, [_vp, C.c_int64, _dp, _dp]),
+    "orc_gpr_hyper_loss": (C.c_int, [_dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp]),
+    "orc_set_gpr_hyper": (None, [_vp, _dp, C.c_int64]),
+    "orc_gpr_train": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp]),
     "orc_sim3exp": (None, [_dp, _dp, _dp, _dp]),
     "orc_se3log": (None, [_dp, _dp, _dp]),
     "orc_plane_fit": (None, [_dp, C.c_int, _dp, _dp]),
@@ -199,6 +202,17 @@ class Oracle:
         nr = self.lib.orc_block_eval(self.h, i, _d(x), _d(e), _d(J))
         return e[:nr], J[:nr]
 
+    def set_gpr_hyper(self, sigma_l):
+        a = np.ascontiguousarray(sigma_l, dtype=np.float64).reshape(-1, 2)
+        self.lib.orc_set_gpr_hyper(self.h, _d(a), a.shape[0])
+
+    def gpr_train(self, g: int, x0):
+        """Training pixels [n,2] and depths [n] of GPR block g at the association extrinsic x0."""
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        X, y = np.zeros((32, 2)), np.zeros(32)
+        n = self.lib.orc_gpr_train(self.h, g, _d(x0), _d(X), _d(y))
+        return X[:n].copy(), y[:n].copy()
+
     def linearize(self, x, nthreads: int = 1):
         """x: [B,7] -> [B,62] rows (cost, g[7], H[7,7], n_blocks_*, n_residuals).  nthreads = 1: one accumulator in
         block order (the goldens' order); otherwise the residual blocks of each x are evaluated by `nthreads`
@@ -237,3 +251,13 @@ def plane_fit(pts, kind="port"):
     reg = C.c_double(0)
     lib.orc_plane_fit(_d(pts), pts.shape[0], _d(n), C.byref(reg))
     return n, reg.value
+
+
+def gpr_hyper_loss(X, y, sigma, l, sigma_noise=1e-10, kind="port"):
+    """GPRHyperLoss::Evaluate as coded (GPR.hpp:154-174) -> (cost, grad[2]) or None when the Cholesky fails."""
+    lib = load(kind)
+    X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 2)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    cost, g = C.c_double(0), np.zeros(2)
+    ok = lib.orc_gpr_hyper_loss(_d(X), _d(y), len(y), sigma_noise, sigma, l, C.byref(cost), _d(g))
+    return (cost.value, g) if ok else None

@@ -548,6 +548,32 @@ class Oracle {
     }
 
     const std::vector<Block> &blocks() const { return blocks_; }
+    // per-factor hyper-parameters of the GPR blocks (block order), e.g. the ones a GPR::fit produced
+    void set_gpr_hyper(const double *sigma_l, size_t n) {
+        size_t g = 0;
+        for (Block &b : blocks_)
+            if (b.type == 3 && g < n) { b.sigma = sigma_l[g * 2]; b.l = sigma_l[g * 2 + 1]; ++g; }
+    }
+    // training data of GPR::fit for GPR block g at the association extrinsic x0 (IBACalib2.hpp:449-457)
+    int gpr_train(size_t g, const double x0[7], double *X /*[32][2]*/, double *y) const {
+        size_t k = 0;
+        for (const Block &b : blocks_) {
+            if (b.type != 3) continue;
+            if (k++ != g) continue;
+            double R[9], t[3], s;
+            Sim3Exp<double>(x0, R, t, s);
+            for (int j = 0; j < b.gm; ++j) {
+                double pt[3];
+                matvec3(R, b.gpts[j], pt);
+                for (int a = 0; a < 3; ++a) pt[a] += t[a];
+                X[j * 2] = b.fx * pt[0] / pt[2] + b.cx;
+                X[j * 2 + 1] = b.fy * pt[1] / pt[2] + b.cy;
+                y[j] = pt[2];
+            }
+            return b.gm;
+        }
+        return 0;
+    }
 
     // Residuals of one block as Duals (the functors' operator()).
     template <class T>

@@ -17,6 +17,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <vector>
 #include <cstdint>
 #include <limits>
 
@@ -328,6 +329,71 @@ inline void smallest_eigenvector(const double cov[6], double n[3]) {
 inline void normalize3(double v[3]) {
     const double z = dot3(v, v);
     if (z > 0) { const double nn = std::sqrt(z); v[0] /= nn; v[1] /= nn; v[2] /= nn; }
+}
+
+
+// ---------------------------------------------------------------- GPR hyper-parameter objective
+// GPRHyperLoss::Evaluate (include/GPR.hpp:154-174) restated matrix by matrix, INCLUDING its gradient expressions as
+// written: grad_kernel (GPR.hpp:218-222) returns {2 * sigma * Kff, Kff * Dist * inv_l3} where Kff is the full kernel
+// matrix (sigma^2 and the sigma_noise diagonal included) and `Kff * Dist` is Eigen's MATRIX product of two MatrixXd.
+// Returns false when the Cholesky factorisation fails (Evaluate returns false, GPR.hpp:159-160).
+inline bool GprHyperLoss(const double *X /*[n][2]*/, const double *y, int n, double sigma_noise, double sigma, double l, double *cost,
+                         double grad[2]) {
+    std::vector<double> Dist((size_t)n * n, 0.0), Kff((size_t)n * n), L((size_t)n * n, 0.0), Kinv((size_t)n * n), alpha(n);
+    for (int ri = 0; ri < n - 1; ++ri)  // self_pdist (GPR.hpp:41-54)
+        for (int ci = ri + 1; ci < n; ++ci) {
+            const double d0 = X[ri * 2] - X[ci * 2], d1 = X[ri * 2 + 1] - X[ci * 2 + 1];
+            Dist[(size_t)ri * n + ci] = d0 * d0 + d1 * d1;
+            Dist[(size_t)ci * n + ri] = Dist[(size_t)ri * n + ci];
+        }
+    for (size_t i = 0; i < (size_t)n * n; ++i) Kff[i] = sigma * sigma * std::exp(-0.5 / (l * l) * Dist[i]);  // computeCovariance (GPR.hpp:206-209)
+    for (int i = 0; i < n; ++i) Kff[(size_t)i * n + i] += sigma_noise;
+    for (int k = 0; k < n; ++k) {  // Eigen::LLT
+        double x = Kff[(size_t)k * n + k];
+        for (int j = 0; j < k; ++j) x -= L[(size_t)k * n + j] * L[(size_t)k * n + j];
+        if (!(x > 0)) return false;
+        x = std::sqrt(x);
+        L[(size_t)k * n + k] = x;
+        for (int i = k + 1; i < n; ++i) {
+            double v = Kff[(size_t)i * n + k];
+            for (int j = 0; j < k; ++j) v -= L[(size_t)i * n + j] * L[(size_t)k * n + j];
+            L[(size_t)i * n + k] = v / x;
+        }
+    }
+    auto llt_solve = [&](std::vector<double> &b) {
+        for (int i = 0; i < n; ++i) { double v = b[i]; for (int j = 0; j < i; ++j) v -= L[(size_t)i * n + j] * b[j]; b[i] = v / L[(size_t)i * n + i]; }
+        for (int i = n - 1; i >= 0; --i) { double v = b[i]; for (int j = i + 1; j < n; ++j) v -= L[(size_t)j * n + i] * b[j]; b[i] = v / L[(size_t)i * n + i]; }
+    };
+    for (int i = 0; i < n; ++i) alpha[i] = y[i];
+    llt_solve(alpha);
+    for (int c = 0; c < n; ++c) {  // Kinv: identity solved in place (GPR.hpp:197-200)
+        std::vector<double> e(n, 0.0);
+        e[c] = 1.0;
+        llt_solve(e);
+        for (int i = 0; i < n; ++i) Kinv[(size_t)i * n + c] = e[i];
+    }
+    double ya = 0, log_diag = 0;
+    for (int i = 0; i < n; ++i) { ya += y[i] * alpha[i]; log_diag += std::log(L[(size_t)i * n + i]); }
+    *cost = 0.5 * (ya + 2.0 * log_diag + n * std::log(2 * M_PI));  // GPR.hpp:163, LogDet :88-91
+    if (grad) {
+        const double inv_l3 = 1.0 / (l * l * l);
+        std::vector<double> inner((size_t)n * n), dKs((size_t)n * n), dKl((size_t)n * n, 0.0);
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) inner[(size_t)i * n + j] = alpha[i] * alpha[j] - Kinv[(size_t)i * n + j];
+        for (size_t i = 0; i < (size_t)n * n; ++i) dKs[i] = 2 * sigma * Kff[i];
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                double sacc = 0;
+                for (int k = 0; k < n; ++k) sacc += Kff[(size_t)i * n + k] * Dist[(size_t)k * n + j];
+                dKl[(size_t)i * n + j] = sacc * inv_l3;
+            }
+        double t0 = 0, t1 = 0;  // (inner * dK).trace()
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < n; ++k) { t0 += inner[(size_t)i * n + k] * dKs[(size_t)k * n + i]; t1 += inner[(size_t)i * n + k] * dKl[(size_t)k * n + i]; }
+        grad[0] = -0.5 * t0;
+        grad[1] = -0.5 * t1;
+    }
+    return true;
 }
 
 }  // namespace orc

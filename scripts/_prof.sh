@@ -1,3 +1,4 @@
+python -m pytest tests/test_gpr_fit.py -m gpu -x -q 2>&1 | tail -5
 STL_K1_CLK=1 python scripts/k1_clk.py 600 0.2 2>&1 | grep "K1 mean" | tail -2
 STL_DEBUG_STATS=1 python scripts/paths.py 300 0.2 2>&1 | grep "search paths" | tail -1
 for spec in "k1:k_assoc2d:2" "k2:k_nn_knn:2" "lmb:k_lm_knn_b:2" "lin:k_linearize:2"; do

@@ -54,6 +54,8 @@ class Params(C.Structure):
         ("gpr_sigma_noise", C.c_double),
         ("plane_index", C.c_int32),
         ("variant", C.c_int32),
+        ("gpr_optimize", C.c_int32),
+        ("gpr_grad_flavour", C.c_int32),
     ]
 
 
@@ -136,6 +138,9 @@ CALIB_SYMBOLS = {
     "stl_linearize_batch_device": (C.c_int, [_vp, _dp, C.c_int32, _vp, _vp]),
     "stl_eval_blocks": (C.c_int, [_vp, _dp, C.c_int32, C.c_int64, _i32p, _i32p, _i32p, _i32p, _dp, _dp, C.POINTER(C.c_int64)]),
     "stl_block_counts": (C.c_int, [_vp, _i64p]),
+    "stl_gpr_nlml": (C.c_int, [_dp, _dp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32, _dp, _dp]),
+    "stl_gpr_fit": (C.c_int, [_dp, _dp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, _dp]),
+    "stl_gpr_hyper": (C.c_int, [_vp, _dp, C.c_int64]),
     "stl_step_batch": (C.c_int, [_vp, _dp, C.c_int32, C.c_int32, C.POINTER(StepSums)]),
     "stl_step_batch_device": (C.c_int, [_vp, _dp, C.c_int32, C.c_int32, _vp, _vp]),
     "stl_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),

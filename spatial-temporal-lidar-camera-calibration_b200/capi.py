@@ -122,6 +122,13 @@ class Context:
                                                                 C.c_void_p(d_out_ptr), C.c_void_p(stream_ptr)))
         self.n_blocks = None
 
+    def gpr_hyper(self):
+        """(sigma, l) of the GPR blocks of the last association, block order -> [nG, 2]."""
+        nb = self.block_counts()
+        out = np.zeros((max(int(nb[3]), 1), 2))
+        _check(self.lib, self.h, self.lib.stl_gpr_hyper(self.h, out.ctypes.data_as(_dp), int(nb[3])))
+        return out[: int(nb[3])]
+
     # -- multi-GPU -------------------------------------------------------------
     def comm_unique_id(self) -> bytes:
         """ncclGetUniqueId (call on one rank, hand the bytes to the others)."""
@@ -236,3 +243,27 @@ class Context:
         _check(self.lib, self.h, self.lib.stl_work_counters(self.h, out.ctypes.data_as(_dp)))
         return dict(points=out[0], q2d=out[1], q3d_nn=out[2], q3d_knn=out[3], k1_bytes=out[4], launches=out[5], k1_overflow_units=out[6],
                     assoc_reused=out[7])
+
+
+def gpr_nlml(x, y, sigma, l, sigma_noise: float = 1e-10, flavour: int = 0):
+    """GPRHyperLoss::Evaluate (GPR.hpp:154-174) -> (cost, grad[2]); host only."""
+    lib = _abi.load_calib()
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 2)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    cost, g = C.c_double(0), np.zeros(2)
+    code = lib.stl_gpr_nlml(x.ctypes.data_as(_dp), y.ctypes.data_as(_dp), len(y), sigma_noise, sigma, l, flavour, C.byref(cost), g.ctypes.data_as(_dp))
+    if code != 0:
+        raise _abi.StlError(code, "Cholesky factorisation of the kernel matrix failed")
+    return cost.value, g
+
+
+def gpr_fit(x, y, sigma0: float = 10.0, l0: float = 10.0, sigma_noise: float = 1e-10, max_iter: int = 15, flavour: int = 0):
+    """GPR::fit (GPR.hpp:350-387) -> dict(sigma, l, cost0, cost, iterations, evaluations); host only."""
+    lib = _abi.load_calib()
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 2)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    out = np.zeros(6)
+    code = lib.stl_gpr_fit(x.ctypes.data_as(_dp), y.ctypes.data_as(_dp), len(y), sigma_noise, sigma0, l0, max_iter, flavour, out.ctypes.data_as(_dp))
+    if code != 0:
+        raise _abi.StlError(code, "the objective could not be evaluated at the starting point")
+    return dict(sigma=out[0], l=out[1], cost0=out[2], cost=out[3], iterations=int(out[4]), evaluations=int(out[5]))

@@ -15,6 +15,7 @@
 #include <nccl.h>
 
 #include "../../include/stlcalib.h"
+#include "gprfit.hpp"
 #include "hostmath.hpp"
 #include "kernels.h"
 #include "lm.h"
@@ -326,6 +327,11 @@ stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st) 
     { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint); }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "associate: %s", cudaGetErrorString(e));
     ctx->launches += (ctx->dpr.plane_index && !ctx->dpr.use_gpr) ? 3 : 4;  // the association kernels (cub select kernels not counted)
+    if (ctx->params.use_gpr && ctx->params.gpr_optimize) {  // GPR::fit per factor (IBACalib2.hpp:460-461), host side
+        e = lm_fit_gpr_hyper(pk, view, ctx->dpr, ctx->lm, st, ctx->params.gpr_grad_flavour);
+        if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "GPR hyper-parameter fit: %s", cudaGetErrorString(e));
+        ctx->launches += 2;
+    }
     ctx->dbg_b = -1;
     ctx->last_x.clear();
     return STL_OK;
@@ -365,6 +371,7 @@ void stl_default_params(stl_params_t *p) {
     p->num_min_corr = 30; p->norm_max_pts = 30; p->norm_min_pts = 5; p->use_plane = 1;
     p->use_gpr = 0; p->gpr_sigma = 10.0; p->gpr_l = 10.0; p->gpr_sigma_noise = 1e-10;
     p->plane_index = 1; p->variant = 0;
+    p->gpr_optimize = 0; p->gpr_grad_flavour = 0;
 }
 
 stl_status_t stl_create(const stl_params_t *params, int32_t device, stl_ctx_t **out) {
@@ -1023,6 +1030,35 @@ stl_status_t stl_work_counters(stl_ctx_t *ctx, double out[8]) {
     }
     ctx->counters[7] = (double)ctx->assoc_reused;
     memcpy(out, ctx->counters, sizeof(ctx->counters));
+    return STL_OK;
+}
+
+// ---- GPR hyper-parameters (host) -----------------------------------------------------------
+
+stl_status_t stl_gpr_nlml(const double *x, const double *y, int32_t n, double sigma_noise, double sigma, double l, int32_t flavour,
+                          double *cost, double grad[2]) {
+    if (!x || !y || n <= 0 || n > 4096) return STL_ERR_INVALID;
+    std::vector<double> D;
+    gpr_self_pdist(x, n, D);
+    return gpr_nlml(D, y, n, sigma_noise, sigma, l, flavour, cost, grad) ? STL_OK : STL_ERR_INVALID;
+}
+
+stl_status_t stl_gpr_fit(const double *x, const double *y, int32_t n, double sigma_noise, double sigma0, double l0, int32_t max_iter,
+                         int32_t flavour, double out[6]) {
+    if (!x || !y || !out || n <= 0 || n > 4096 || max_iter < 0) return STL_ERR_INVALID;
+    const GprFitResult r = gpr_fit(x, y, n, sigma_noise, sigma0, l0, max_iter, flavour);
+    out[0] = r.sigma; out[1] = r.l; out[2] = r.cost0; out[3] = r.cost; out[4] = r.iterations; out[5] = r.evaluations;
+    return r.ok ? STL_OK : STL_ERR_INVALID;
+}
+
+stl_status_t stl_gpr_hyper(stl_ctx_t *ctx, double *sigma_l, int64_t cap_blocks) {
+    if (!ctx || !sigma_l) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->lm.ready) return fail(ctx, STL_ERR_STATE, "stl_associate has not been called");
+    CK(cudaSetDevice(ctx->device));
+    CK(lm_block_counts(ctx->lm));
+    if (ctx->lm.nG > cap_blocks) return fail(ctx, STL_ERR_CAPACITY, "%d GPR blocks, room for %lld", ctx->lm.nG, (long long)cap_blocks);
+    CK(lm_get_gpr_hyper(ctx->dpr, ctx->lm, sigma_l, acquire_stream(ctx, nullptr)));
     return STL_OK;
 }
 

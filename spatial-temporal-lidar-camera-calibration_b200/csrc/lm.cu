@@ -19,6 +19,7 @@
 
 #include "../../include/stlcalib.h"
 #include "dual.cuh"
+#include "gprfit.hpp"
 #include "knn.cuh"
 #include "lm.h"
 
@@ -504,11 +505,6 @@ k_linearize_gpr(const DevPack pk, const DevParams pr, const LmState lm, const Lm
 #pragma unroll
     for (int i = 0; i < kLinVals; ++i) A.v[i] = 0.0;
     const int C = pk.n_covis;
-    // constants as the reference forms them on Jets with zero partials: sigma*sigma, T(-0.5)/(l*l) = -0.5 * (1/(l*l))
-    const double sigma2 = pr.gpr_sigma * pr.gpr_sigma;
-    const double inv_l2 = 1.0 / (pr.gpr_l * pr.gpr_l);
-    const double coef = -0.5 * inv_l2;
-    const D7 kdiag = d7_const(sigma2 * exp(coef * 0.0) + pr.gpr_noise);
     const int nG = lm.d_counts[3];
     for (int it = blockIdx.x; it < nG; it += gridDim.x) {
         const int cs = lm.idxG[it];
@@ -521,6 +517,13 @@ k_linearize_gpr(const DevPack pk, const DevParams pr, const LmState lm, const Lm
         const double fx = K.fx, fy = K.fy, cx = K.cx, cy = K.cy;
         const float2 kxy = pk.kp_xy[K.kp_off + kp];
         const double u0 = kxy.x, v0 = kxy.y;
+        // hyper-parameters of this factor (fitted per factor when params.gpr_optimize, IBACalib2.hpp:460-461); constants
+        // as the reference forms them on Jets with zero partials: sigma*sigma, T(-0.5)/(l*l) = -0.5 * (1/(l*l))
+        const double sigma = lm.gpr_hyper ? lm.gpr_hyper[ms * 2] : pr.gpr_sigma, ell = lm.gpr_hyper ? lm.gpr_hyper[ms * 2 + 1] : pr.gpr_l;
+        const double sigma2 = sigma * sigma;
+        const double inv_l2 = 1.0 / (ell * ell);
+        const double coef = -0.5 * inv_l2;
+        const D7 kdiag = d7_const(sigma2 * exp(coef * 0.0) + pr.gpr_noise);
         __syncwarp();
         // 1. neighbour j -> camera frame with the candidate, pixel coordinates X_j and depth y_j (IBACalib2.hpp:478-489)
         D7 myu = d7_const(0.0), myv = d7_const(0.0);
@@ -670,7 +673,7 @@ template <class T> void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
 
 void lm_free(LmState &lm) {
     dfree(lm.slot_kf); dfree(lm.slot_kp); dfree(lm.flags); dfree(lm.geo2d); dfree(lm.geo3d);
-    dfree(lm.idxG); dfree(lm.slot_mp); dfree(lm.gpr_nb); dfree(lm.gpr_m);
+    dfree(lm.idxG); dfree(lm.slot_mp); dfree(lm.gpr_nb); dfree(lm.gpr_m); dfree(lm.gpr_hyper);
     dfree(lm.stage); dfree(lm.plane_a); dfree(lm.nnb_pos); dfree(lm.nbb); dfree(lm.nbbx); dfree(lm.nbb_m); dfree(lm.nbb_last);
     dfree(lm.idx2d); dfree(lm.idx3d); dfree(lm.d_tmp); dfree(lm.partial); dfree(lm.d_cand);
     if (lm.h_cand) cudaFreeHost(lm.h_cand);
@@ -751,6 +754,110 @@ cudaError_t lm_block_counts(LmState &lm) {
     lm.n_blocks[0] = lm.n2d; lm.n_blocks[1] = npt; lm.n_blocks[2] = lm.n3d - npt; lm.n_blocks[3] = lm.nG;
     lm.counts_valid = true;
     return cudaSuccess;
+}
+
+namespace {
+// training data of GPR::fit for GPR block `it`: neighbour j -> (u, v, depth) with the association extrinsic
+// (IBACalib2.hpp:449-457: pt = R p + t; uv = fx pt0 / pt2 + cx, fy pt1 / pt2 + cy), fp64, one thread per neighbour
+__global__ void k_gpr_train(const DevPack pk, const DevWork wk, const LmState lm, double *__restrict__ out /*[nG][32][3]*/, int *__restrict__ out_n) {
+    const int it = blockIdx.x, lane = threadIdx.x;
+    if (it >= lm.d_counts[3]) return;
+    const int cs = lm.idxG[it];
+    const int f = lm.slot_kf[cs];
+    const long long ms = lm.slot_mp[cs];
+    const int n = lm.gpr_m[ms];
+    const DevKf &K = pk.kf[f];
+    const DevCand &c = wk.cand[0];
+    if (lane == 0) out_n[it] = n;
+    double u = 0, v = 0, z = 0;
+    if (lane < n) {
+        const uint32_t p = lm.gpr_nb[ms * kMaxK + lane];
+        double X, Y, Z;
+        xform(c.R, c.t, (double)pk.px[K.pt_off + p], (double)pk.py[K.pt_off + p], (double)pk.pz[K.pt_off + p], X, Y, Z);
+        u = (double)K.fx * X / Z + (double)K.cx;
+        v = (double)K.fy * Y / Z + (double)K.cy;
+        z = Z;
+    }
+    double *o = out + ((long long)it * kMaxK + lane) * 3;
+    o[0] = u; o[1] = v; o[2] = z;
+}
+__global__ void k_gpr_scatter_hyper(const LmState lm, const double *__restrict__ fitted /*[nG][2]*/, double *__restrict__ hyper) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= lm.d_counts[3]) return;
+    const long long ms = lm.slot_mp[lm.idxG[it]];
+    hyper[ms * 2] = fitted[it * 2];
+    hyper[ms * 2 + 1] = fitted[it * 2 + 1];
+}
+__global__ void k_gpr_gather_hyper(const LmState lm, const DevParams pr, double *__restrict__ out /*[nG][2]*/) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= lm.d_counts[3]) return;
+    const long long ms = lm.slot_mp[lm.idxG[it]];
+    out[it * 2] = lm.gpr_hyper ? lm.gpr_hyper[ms * 2] : pr.gpr_sigma;
+    out[it * 2 + 1] = lm.gpr_hyper ? lm.gpr_hyper[ms * 2 + 1] : pr.gpr_l;
+}
+}  // namespace
+
+cudaError_t lm_fit_gpr_hyper(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st, int flavour) {
+    cudaError_t e = lm_block_counts(lm);
+    if (e != cudaSuccess) return e;
+    const int nG = lm.nG;
+    const long long nm = pk.n_mp_total > 0 ? pk.n_mp_total : 1;
+    if (!lm.gpr_hyper) {
+        e = cudaMalloc(&lm.gpr_hyper, 16 * nm);
+        if (e != cudaSuccess) return e;
+    }
+    if (nG == 0) return cudaSuccess;
+    double *d_train = nullptr, *d_fit = nullptr;
+    int *d_n = nullptr;
+    std::vector<double> h_train((size_t)nG * kMaxK * 3), h_fit((size_t)nG * 2);
+    std::vector<int> h_n(nG);
+    e = cudaMalloc(&d_train, 8 * h_train.size());
+    if (e == cudaSuccess) e = cudaMalloc(&d_n, 4 * (size_t)nG);
+    if (e == cudaSuccess) e = cudaMalloc(&d_fit, 16 * (size_t)nG);
+    if (e == cudaSuccess) {
+        k_gpr_train<<<nG, kMaxK, 0, st>>>(pk, wk, lm, d_train, d_n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_train.data(), d_train, 8 * h_train.size(), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_n.data(), d_n, 4 * (size_t)nG, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) {
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int it = 0; it < nG; ++it) {
+            const int n = h_n[it];
+            double x[kMaxK * 2], y[kMaxK];
+            for (int j = 0; j < n; ++j) {
+                x[j * 2] = h_train[((size_t)it * kMaxK + j) * 3];
+                x[j * 2 + 1] = h_train[((size_t)it * kMaxK + j) * 3 + 1];
+                y[j] = h_train[((size_t)it * kMaxK + j) * 3 + 2];
+            }
+            const GprFitResult r = gpr_fit(x, y, n, pr.gpr_noise, pr.gpr_sigma, pr.gpr_l, 15, flavour);  // max_num_iterations = 15 (GPR.hpp:360)
+            h_fit[(size_t)it * 2] = r.sigma;
+            h_fit[(size_t)it * 2 + 1] = r.l;
+        }
+        e = cudaMemcpyAsync(d_fit, h_fit.data(), 16 * (size_t)nG, cudaMemcpyHostToDevice, st);
+    }
+    if (e == cudaSuccess) {
+        k_gpr_scatter_hyper<<<(nG + 127) / 128, 128, 0, st>>>(lm, d_fit, lm.gpr_hyper);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_train); cudaFree(d_n); cudaFree(d_fit);
+    return e;
+}
+
+cudaError_t lm_get_gpr_hyper(const DevParams &pr, LmState &lm, double *out, cudaStream_t st) {
+    cudaError_t e = lm_block_counts(lm);
+    if (e != cudaSuccess || lm.nG == 0) return e;
+    double *d = nullptr;
+    e = cudaMalloc(&d, 16 * (size_t)lm.nG);
+    if (e != cudaSuccess) return e;
+    k_gpr_gather_hyper<<<(lm.nG + 127) / 128, 128, 0, st>>>(lm, pr, d);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, 16 * (size_t)lm.nG, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    return e;
 }
 
 cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,

@@ -36,6 +36,7 @@ struct LmState {
     int *idxG = nullptr, *slot_mp = nullptr;
     uint32_t *gpr_nb = nullptr;   // [n_mp][32]
     int *gpr_m = nullptr;         // [n_mp]
+    double *gpr_hyper = nullptr;  // [n_mp][2] per-block (sigma, l) fitted at association time (null: the per-problem values)
     int nG = 0;
     int *d_counts = nullptr;      // [4] device: plane blocks, 3-D blocks, point-to-point among them, GPR blocks
     int *h_counts = nullptr;      // pinned copy, valid behind counts_done
@@ -73,5 +74,11 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
                          const BlockOut *blocks = nullptr, int out_stride = 0);
 // waits for the last association and mirrors its block counts into lm.n2d / n3d / nG / n_blocks
 cudaError_t lm_block_counts(LmState &lm);
+// GPR::fit for every GPR block of the last association (IBA_GPRFactor's constructor, IBACalib2.hpp:441-461): the
+// training pixels / depths are formed on the device with the association extrinsic (wk.cand[0]), the two-parameter
+// fit runs on the host (OpenMP over blocks), the result lands in lm.gpr_hyper.  Synchronous.
+cudaError_t lm_fit_gpr_hyper(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st, int flavour);
+// copies (sigma, l) of the GPR blocks, block order, to host memory out[nG][2]
+cudaError_t lm_get_gpr_hyper(const DevParams &pr, LmState &lm, double *out, cudaStream_t st);
 
 }  // namespace stl

@@ -161,4 +161,6 @@ def default_params() -> _abi.Params:
     p.gpr_sigma, p.gpr_l, p.gpr_sigma_noise = 10.0, 10.0, 1e-10
     p.plane_index = 1
     p.variant = 0
+    p.gpr_optimize = 0
+    p.gpr_grad_flavour = 0
     return p
