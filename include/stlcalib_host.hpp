@@ -76,6 +76,16 @@ class Context {
         check(stl_linearize_batch(ctx_, x, B, out.data()), "stl_linearize_batch");
         return out;
     }
+    // BAError sums + (BuildProblem at x[0]) + linearisation in one device round (one LM iteration, or a NOMAD poll on the
+    // frozen association): [B] records of {eval sums, linearisation}
+    std::vector<stl_step_sums_t> step(const double *x, int B, bool reassociate) {
+        std::vector<stl_step_sums_t> out((size_t)B);
+        check(stl_step_batch(ctx_, x, B, reassociate ? 1 : 0, out.data()), "stl_step_batch");
+        return out;
+    }
+    // keyframes sharded over several GPUs: this context holds shard `rank` of `n_ranks`; `id` comes from
+    // stl_comm_unique_id on one rank (handed over by the host program).  Afterwards every call returns the totals.
+    void comm_init(const uint8_t id[STL_COMM_ID_BYTES], int rank, int n_ranks) { check(stl_comm_init(ctx_, id, rank, n_ranks), "stl_comm_init"); }
     const stl_params_t &params() const { return params_; }
     stl_ctx_t *raw() { return ctx_; }
 
