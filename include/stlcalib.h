@@ -302,6 +302,42 @@ stl_status_t stl_step_batch(stl_ctx_t *ctx, const double *x, int32_t B, int32_t 
 /* Same; the [B][STL_STEP_NSUMS] record stays in DEVICE memory `d_out` on `stream`, no synchronisation. */
 stl_status_t stl_step_batch_device(stl_ctx_t *ctx, const double *x, int32_t B, int32_t reassociate, double *d_out, void *stream);
 
+/* ---- the two optimisation problems that precede the cost evaluation, on the same 7 parameters ----
+ * Hand-eye initialisation, HECalibRobustKernelg2o / HECalibLineProcessg2o (include/NLHECalib.hpp:118-278): one EdgeHE per
+ * motion pair (camera motion Ta, LiDAR motion Tb; :27-86) plus the EdgeRegulation on the translation parameters (:88-116).
+ * For B parameter vectors x the call returns, in stl_lin_sums_t: cost = sum rho(chi2) (g2o's robust chi2, no factor 1/2),
+ * g = J^T rho' Omega e (g2o's b is -g), H = J^T rho' Omega J, n_blocks_2d = edges, n_residuals.  chi2 (optional,
+ * [B][n]) receives every edge's e^T Omega e — HECalibLineProcessg2o re-weights its edges from them (:230-241). */
+typedef struct stl_he_edges {
+    int32_t n;
+    const double *Ta;      /* [n][12] camera motions, 3x4 row-major [R|t]                      */
+    const double *Tb;      /* [n][12] LiDAR motions                                              */
+    const double *info;    /* [n] information scale of each edge (information = info * I); NULL = 1 */
+    double huber_delta;    /* g2o::RobustKernelHuber delta (robust_kernel_size, :141-143); <= 0: none */
+    double regulation;     /* information scale of the regularisation edge (n * regulation_ratio, :148-150); 0: no such edge */
+} stl_he_edges_t;
+stl_status_t stl_he_linearize(stl_ctx_t *ctx, const stl_he_edges_t *edges, const double *x, int32_t B, stl_lin_sums_t *out, double *chi2);
+
+/* Calibration bundle adjustment, Optimizer::OptimizeExtrinsicGlobal / Local (src/orb_slam/src/Optimizer.cc:1399-1744):
+ * one calibEdge (:65-205) per (keyframe, observed map point): the map point (already in the frame of the first / oldest
+ * keyframe) is scaled, taken to the LiDAR frame with the inverse extrinsic, moved by the LiDAR pose of the keyframe,
+ * brought back with the extrinsic and projected; error = observation - projection, information = invSigma2 * I,
+ * Huber delta = sqrt(5.991).  `level` mirrors setLevel (1 = left out as an outlier, :1513-1524).  Same outputs as
+ * stl_he_linearize; chi2 is [B][n_edges] and is also filled for level-1 edges (the reference re-evaluates them, :1509). */
+typedef struct stl_calib_edges {
+    int32_t n_kf;
+    int64_t n_edges;
+    const int64_t *edge_offset; /* [n_kf+1] first edge of each keyframe                          */
+    const double *Tlw_quat;     /* [n_kf][6] rotation vector and translation of calibEdge::Tlw_quat */
+    const float *intrinsics;    /* [n_kf][4] fx, fy, cx, cy                                         */
+    const double *Xw;           /* [n_edges][3] calibEdge::Xw                                       */
+    const double *obs;          /* [n_edges][2] measurement (undistorted keypoint)                  */
+    const float *inv_sigma2;    /* [n_edges] mvInvLevelSigma2[octave]                               */
+    const uint8_t *level;       /* [n_edges] or NULL (all active)                                   */
+    double huber_delta;
+} stl_calib_edges_t;
+stl_status_t stl_calib_linearize(stl_ctx_t *ctx, const stl_calib_edges_t *edges, const double *x, int32_t B, stl_lin_sums_t *out, double *chi2);
+
 /* ---- multi-GPU: keyframes sharded over the GPUs of a node -----------------------------
  * One process (or thread) per GPU, each with its own context holding a contiguous block of keyframes
  * (stl_pack_t.n_kf = this rank's shard; covisible data is baked per keyframe, so there is no halo).

@@ -51,6 +51,11 @@ _SYMS = {
     "orc_gpr_hyper_loss": (C.c_int, [_dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double, _dp, _dp]),
     "orc_set_gpr_hyper": (None, [_vp, _dp, C.c_int64]),
     "orc_gpr_train": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp]),
+    "orc_he_linearize": (None, [C.POINTER(_abi.HeEdges), _dp, C.c_int, C.POINTER(_abi.LinSums), _dp]),
+    "orc_calib_linearize": (None, [C.POINTER(_abi.CalibEdges), _dp, C.c_int, C.POINTER(_abi.LinSums), _dp]),
+    "orc_he_edge": (None, [_dp, _dp, _dp, _dp, _dp]),
+    "orc_calib_edge_plain": (None, [_dp, _dp, _dp, _dp, _dp, _dp]),
+    "orc_rotvec": (None, [_dp, _dp]),
     "orc_sim3exp": (None, [_dp, _dp, _dp, _dp]),
     "orc_se3log": (None, [_dp, _dp, _dp]),
     "orc_plane_fit": (None, [_dp, C.c_int, _dp, _dp]),
@@ -261,3 +266,50 @@ def gpr_hyper_loss(X, y, sigma, l, sigma_noise=1e-10, kind="port"):
     cost, g = C.c_double(0), np.zeros(2)
     ok = lib.orc_gpr_hyper_loss(_d(X), _d(y), len(y), sigma_noise, sigma, l, C.byref(cost), _d(g))
     return (cost.value, g) if ok else None
+
+
+def he_linearize(edges, x, kind="port"):
+    """EdgeHE + EdgeRegulation problem (NLHECalib.hpp:27-116), g2o robust-kernel semantics -> ([B,62], chi2 [B,n])."""
+    lib = load(kind)
+    x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+    B = x.shape[0]
+    out = (_abi.LinSums * B)()
+    chi2 = np.zeros((B, max(edges.n, 1)))
+    c = edges.as_c()
+    lib.orc_he_linearize(C.byref(c), _d(x), B, out, _d(chi2))
+    return np.frombuffer(out, dtype=np.float64).reshape(B, _abi.STL_LIN_NSUMS).copy(), chi2[:, : edges.n]
+
+
+def calib_linearize(edges, x, kind="port"):
+    lib = load(kind)
+    x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+    B = x.shape[0]
+    out = (_abi.LinSums * B)()
+    chi2 = np.zeros((B, max(edges.n_edges, 1)))
+    c = edges.as_c()
+    lib.orc_calib_linearize(C.byref(c), _d(x), B, out, _d(chi2))
+    return np.frombuffer(out, dtype=np.float64).reshape(B, _abi.STL_LIN_NSUMS).copy(), chi2[:, : edges.n_edges]
+
+
+def he_edge(Ta, Tb, x, kind="port"):
+    lib = load(kind)
+    Ta, Tb, x = (np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (Ta, Tb, x))
+    e, J = np.zeros(3), np.zeros((3, 7))
+    lib.orc_he_edge(_d(Ta), _d(Tb), _d(x), _d(e), _d(J))
+    return e, J
+
+
+def calib_edge(x, Xw, Tlw_quat, intr, obs, kind="port"):
+    lib = load(kind)
+    a = [np.ascontiguousarray(v, dtype=np.float64).reshape(-1) for v in (x, Xw, Tlw_quat, intr, obs)]
+    err = np.zeros(2)
+    lib.orc_calib_edge_plain(*[_d(v) for v in a], _d(err))
+    return err
+
+
+def rotvec(R, kind="port"):
+    lib = load(kind)
+    R = np.ascontiguousarray(R, dtype=np.float64).reshape(9)
+    rv = np.zeros(3)
+    lib.orc_rotvec(_d(R), _d(rv))
+    return rv

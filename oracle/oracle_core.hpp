@@ -30,6 +30,7 @@
 
 #include "../include/stlcalib.h"
 #include "oracle_math.hpp"
+#include "oracle_calib.hpp"
 
 namespace orc {
 

@@ -102,6 +102,19 @@ class StepSums(C.Structure):
     _fields_ = [("eval", EvalSums), ("lin", LinSums)]
 
 
+class HeEdges(C.Structure):
+    """stl_he_edges_t (NLHECalib.hpp:27-116)."""
+    _fields_ = [("n", C.c_int32), ("Ta", C.POINTER(C.c_double)), ("Tb", C.POINTER(C.c_double)), ("info", C.POINTER(C.c_double)),
+                ("huber_delta", C.c_double), ("regulation", C.c_double)]
+
+
+class CalibEdges(C.Structure):
+    """stl_calib_edges_t (Optimizer.cc:65-205,1399-1744)."""
+    _fields_ = [("n_kf", C.c_int32), ("n_edges", C.c_int64), ("edge_offset", C.POINTER(C.c_int64)), ("Tlw_quat", C.POINTER(C.c_double)),
+                ("intrinsics", C.POINTER(C.c_float)), ("Xw", C.POINTER(C.c_double)), ("obs", C.POINTER(C.c_double)),
+                ("inv_sigma2", C.POINTER(C.c_float)), ("level", C.POINTER(C.c_uint8)), ("huber_delta", C.c_double)]
+
+
 class SynthCfg(C.Structure):
     _fields_ = [
         ("n_kf", C.c_int32), ("kf_begin", C.c_int32), ("n_kf_total", C.c_int32),
@@ -143,6 +156,8 @@ CALIB_SYMBOLS = {
     "stl_gpr_hyper": (C.c_int, [_vp, _dp, C.c_int64]),
     "stl_step_batch": (C.c_int, [_vp, _dp, C.c_int32, C.c_int32, C.POINTER(StepSums)]),
     "stl_step_batch_device": (C.c_int, [_vp, _dp, C.c_int32, C.c_int32, _vp, _vp]),
+    "stl_he_linearize": (C.c_int, [_vp, C.POINTER(HeEdges), _dp, C.c_int32, C.POINTER(LinSums), _dp]),
+    "stl_calib_linearize": (C.c_int, [_vp, C.POINTER(CalibEdges), _dp, C.c_int32, C.POINTER(LinSums), _dp]),
     "stl_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "stl_comm_init": (C.c_int, [_vp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]),
     "stl_comm_info": (C.c_int, [_vp, _i32p, _i32p]),

@@ -129,6 +129,29 @@ class Context:
         _check(self.lib, self.h, self.lib.stl_gpr_hyper(self.h, out.ctypes.data_as(_dp), int(nb[3])))
         return out[: int(nb[3])]
 
+    # -- the problems before the hot path (N4) --------------------------------------
+    def he_linearize(self, edges: "HandEyeEdges", x, want_chi2: bool = False):
+        """EdgeHE + EdgeRegulation (NLHECalib.hpp:27-116) at x [B,7] -> [B,62] (cost = sum rho(chi2), g, H) (, chi2 [B,n])."""
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        B = x.shape[0]
+        out = np.zeros((B, _abi.STL_LIN_NSUMS))
+        chi2 = np.zeros((B, max(edges.n, 1))) if want_chi2 else None
+        c = edges.as_c()
+        _check(self.lib, self.h, self.lib.stl_he_linearize(self.h, C.byref(c), x.ctypes.data_as(_dp), B, out.ctypes.data_as(C.POINTER(_abi.LinSums)),
+                                                           chi2.ctypes.data_as(_dp) if want_chi2 else None))
+        return (out, chi2[:, : edges.n]) if want_chi2 else out
+
+    def calib_linearize(self, edges: "CalibBAEdges", x, want_chi2: bool = False):
+        """calibEdge problem (Optimizer.cc:65-205,1399-1744) at x [B,7] -> [B,62] (, chi2 [B,n_edges])."""
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        B = x.shape[0]
+        out = np.zeros((B, _abi.STL_LIN_NSUMS))
+        chi2 = np.zeros((B, max(edges.n_edges, 1))) if want_chi2 else None
+        c = edges.as_c()
+        _check(self.lib, self.h, self.lib.stl_calib_linearize(self.h, C.byref(c), x.ctypes.data_as(_dp), B, out.ctypes.data_as(C.POINTER(_abi.LinSums)),
+                                                              chi2.ctypes.data_as(_dp) if want_chi2 else None))
+        return (out, chi2[:, : edges.n_edges]) if want_chi2 else out
+
     # -- multi-GPU -------------------------------------------------------------
     def comm_unique_id(self) -> bytes:
         """ncclGetUniqueId (call on one rank, hand the bytes to the others)."""
@@ -243,6 +266,46 @@ class Context:
         _check(self.lib, self.h, self.lib.stl_work_counters(self.h, out.ctypes.data_as(_dp)))
         return dict(points=out[0], q2d=out[1], q3d_nn=out[2], q3d_knn=out[3], k1_bytes=out[4], launches=out[5], k1_overflow_units=out[6],
                     assoc_reused=out[7])
+
+
+class HandEyeEdges:
+    """Host container of stl_he_edges_t: motion pairs (Ta camera, Tb LiDAR) as [n,12] row-major 3x4."""
+
+    def __init__(self, Ta, Tb, info=None, huber_delta: float = 0.0, regulation: float = 0.0):
+        self.Ta = np.ascontiguousarray(Ta, dtype=np.float64).reshape(-1, 12)
+        self.Tb = np.ascontiguousarray(Tb, dtype=np.float64).reshape(-1, 12)
+        self.n = len(self.Ta)
+        self.info = None if info is None else np.ascontiguousarray(info, dtype=np.float64)
+        self.huber_delta, self.regulation = float(huber_delta), float(regulation)
+
+    def as_c(self):
+        c = _abi.HeEdges(self.n, self.Ta.ctypes.data_as(_dp), self.Tb.ctypes.data_as(_dp),
+                         self.info.ctypes.data_as(_dp) if self.info is not None else None, self.huber_delta, self.regulation)
+        c._keep = self
+        return c
+
+
+class CalibBAEdges:
+    """Host container of stl_calib_edges_t."""
+
+    def __init__(self, edge_offset, Tlw_quat, intrinsics, Xw, obs, inv_sigma2, level=None, huber_delta: float = 5.991 ** 0.5):
+        self.edge_offset = np.ascontiguousarray(edge_offset, dtype=np.int64)
+        self.Tlw_quat = np.ascontiguousarray(Tlw_quat, dtype=np.float64).reshape(-1, 6)
+        self.intrinsics = np.ascontiguousarray(intrinsics, dtype=np.float32).reshape(-1, 4)
+        self.Xw = np.ascontiguousarray(Xw, dtype=np.float64).reshape(-1, 3)
+        self.obs = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1, 2)
+        self.inv_sigma2 = np.ascontiguousarray(inv_sigma2, dtype=np.float32)
+        self.level = None if level is None else np.ascontiguousarray(level, dtype=np.uint8)
+        self.n_kf, self.n_edges = len(self.Tlw_quat), len(self.Xw)
+        self.huber_delta = float(huber_delta)
+
+    def as_c(self):
+        c = _abi.CalibEdges(self.n_kf, self.n_edges, self.edge_offset.ctypes.data_as(_abi._i64p), self.Tlw_quat.ctypes.data_as(_dp),
+                            self.intrinsics.ctypes.data_as(C.POINTER(C.c_float)), self.Xw.ctypes.data_as(_dp), self.obs.ctypes.data_as(_dp),
+                            self.inv_sigma2.ctypes.data_as(C.POINTER(C.c_float)),
+                            self.level.ctypes.data_as(C.POINTER(C.c_uint8)) if self.level is not None else None, self.huber_delta)
+        c._keep = self
+        return c
 
 
 def gpr_nlml(x, y, sigma, l, sigma_noise: float = 1e-10, flavour: int = 0):

@@ -1062,6 +1062,31 @@ stl_status_t stl_gpr_hyper(stl_ctx_t *ctx, double *sigma_l, int64_t cap_blocks) 
     return STL_OK;
 }
 
+// ---- N4: hand-eye initialisation and calibration BA on the same parameter block ---------------------
+
+stl_status_t stl_he_linearize(stl_ctx_t *ctx, const stl_he_edges_t *edges, const double *x, int32_t B, stl_lin_sums_t *out, double *chi2) {
+    if (!ctx || !edges || !x || !out || B <= 0 || edges->n < 0) return STL_ERR_INVALID;
+    if (edges->n > 0 && (!edges->Ta || !edges->Tb)) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(he_linearize(*edges, x, B, reinterpret_cast<double *>(out), chi2, acquire_stream(ctx, nullptr)));
+    ctx->launches += 2;
+    return STL_OK;
+}
+
+stl_status_t stl_calib_linearize(stl_ctx_t *ctx, const stl_calib_edges_t *edges, const double *x, int32_t B, stl_lin_sums_t *out, double *chi2) {
+    if (!ctx || !edges || !x || !out || B <= 0 || edges->n_kf < 0 || edges->n_edges < 0) return STL_ERR_INVALID;
+    if (edges->n_edges > 0 && (!edges->edge_offset || !edges->Tlw_quat || !edges->intrinsics || !edges->Xw || !edges->obs || !edges->inv_sigma2))
+        return fail(ctx, STL_ERR_INVALID, "null member of stl_calib_edges_t");
+    if (edges->n_kf > 0 && (edges->edge_offset[0] != 0 || edges->edge_offset[edges->n_kf] != edges->n_edges))
+        return fail(ctx, STL_ERR_INVALID, "edge_offset must run from 0 to n_edges");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    CK(calib_linearize(*edges, x, B, reinterpret_cast<double *>(out), chi2, acquire_stream(ctx, nullptr)));
+    ctx->launches += 2;
+    return STL_OK;
+}
+
 // ---- multi-GPU ---------------------------------------------------------------------
 
 stl_status_t stl_comm_unique_id(uint8_t id[STL_COMM_ID_BYTES]) {

@@ -113,4 +113,12 @@ cudaError_t launch_knn3d(const DevPack &pk, int kf, const double *d_q, int nq, i
 // out: [B][out_stride] fp64 (first STL_EVAL_NSUMS of each row), written (not accumulated); out_stride 0 = STL_EVAL_NSUMS
 cudaError_t launch_reduce(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, double *d_out, cudaStream_t st, int out_stride = 0);
 
+// ---- N4 (calib.cu): hand-eye initialisation edges and calibration-BA edges; HOST in, HOST out, synchronous
+}  // namespace stl
+struct stl_he_edges;
+struct stl_calib_edges;
+namespace stl {
+cudaError_t he_linearize(const stl_he_edges &ed, const double *x, int B, double *h_out, double *h_chi2, cudaStream_t st);
+cudaError_t calib_linearize(const stl_calib_edges &ed, const double *x, int B, double *h_out, double *h_chi2, cudaStream_t st);
+
 }  // namespace stl

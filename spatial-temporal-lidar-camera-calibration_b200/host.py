@@ -107,3 +107,75 @@ class LMProblem:
         A = H + lam * np.diag(np.maximum(np.diag(H), 1e-12))
         dx = -np.linalg.solve(A, g)
         return np.asarray(x) + dx, cost
+
+
+# ------------------------------------------------------------------------------------------------
+# N4 — the steps before the cost evaluation, on the same 7 parameters
+class HandEyeInit:
+    """``HECalibRobustKernelg2o`` / ``HECalibLineProcessg2o`` (include/NLHECalib.hpp:118-278) with the edges evaluated
+    through an evaluator ``lin(edges, x) -> ([B,62], chi2 [B,n])`` — :meth:`capi.Context.he_linearize` on the GPU or the
+    oracle on the CPU.  The g2o optimiser itself (Dogleg / Levenberg with ``optimize(10)``) is third-party and not
+    available here: a damped Gauss-Newton loop on the returned (g, H) stands in for it, identically for both
+    evaluators, so the two final extrinsics can be compared."""
+
+    def __init__(self, lin):
+        self.lin = lin
+
+    def _solve(self, edges, x, iters=10):
+        lam = 1e-4
+        L, _ = self.lin(edges, x[None])
+        cost, g, H = L[0, 0], L[0, 1:8], L[0, 8:57].reshape(7, 7)
+        for _ in range(iters):
+            step = -np.linalg.solve(H + lam * np.diag(np.maximum(np.diag(H), 1e-12)), g)
+            L1, _ = self.lin(edges, (x + step)[None])
+            if L1[0, 0] < cost:
+                x = x + step
+                cost, g, H = L1[0, 0], L1[0, 1:8], L1[0, 8:57].reshape(7, 7)
+                lam = max(lam / 3.0, 1e-12)
+            else:
+                lam *= 4.0
+        return x, cost
+
+    def robust_kernel(self, edges, x0, iters=10):
+        """Huber kernel on every motion edge + the regularisation edge (NLHECalib.hpp:118-158)."""
+        return self._solve(edges, np.asarray(x0, dtype=np.float64).copy(), iters)
+
+    def line_process(self, edges, x0, mu0=64.0, divid_factor=1.4, min_mu=1e-1, ex_max_iter=20, regulation_ratio=0.005):
+        """Graduated re-weighting w = mu / (mu + chi2), information = w^2 I (NLHECalib.hpp:224-246)."""
+        import copy
+        ed = copy.copy(edges)
+        ed.huber_delta = 0.0
+        ed.info = None
+        x, cost = self._solve(ed, np.asarray(x0, dtype=np.float64).copy())
+        mu = mu0
+        for _ in range(ex_max_iter):
+            ed.info = None
+            _, chi2 = self.lin(ed, x[None])       # chi2 with identity information
+            w2 = (mu / (mu + chi2[0])) ** 2
+            ed.info = np.ascontiguousarray(w2)
+            if edges.regulation > 0:
+                ed.regulation = float(w2.sum() * regulation_ratio)
+            x, cost = self._solve(ed, x)
+            mu /= divid_factor
+            if mu < min_mu:
+                break
+        return x, cost
+
+
+def calib_ba(lin, edges, x0, rounds=4, iters=10, chi2_max=5.991):
+    """``Optimizer::OptimizeExtrinsicGlobal`` (Optimizer.cc:1583-1744): four rounds of ten iterations from the SAME start,
+    edges re-classified as outliers (level 1) by chi2 > 5.991 after every round, the robust kernel dropped after the
+    third.  ``lin(edges, x) -> ([B,62], chi2)``.  Returns (x, inliers)."""
+    import copy
+    ed = copy.copy(edges)
+    ed.level = np.zeros(edges.n_edges, np.uint8)
+    x0 = np.asarray(x0, dtype=np.float64)
+    x = x0.copy()
+    he = HandEyeInit(lin)
+    for it in range(rounds):
+        x, _ = he._solve(ed, x0.copy(), iters)       # v->setEstimate(p_tcl) at the start of every round
+        _, chi2 = lin(ed, x[None])
+        ed.level = (chi2[0] > chi2_max).astype(np.uint8)
+        if it == 2:
+            ed.huber_delta = 0.0                        # e->setRobustKernel(0)
+    return x, int((ed.level == 0).sum())
