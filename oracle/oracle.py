@@ -56,6 +56,10 @@ _SYMS = {
     "orc_he_edge": (None, [_dp, _dp, _dp, _dp, _dp]),
     "orc_calib_edge_plain": (None, [_dp, _dp, _dp, _dp, _dp, _dp]),
     "orc_rotvec": (None, [_dp, _dp]),
+    "orc_covariance": (None, [_dp, _u32p, C.c_int, _dp]),
+    "orc_smallest_eigvec": (None, [_dp, _dp]),
+    "orc_sim3exp_dual": (None, [_dp, _dp]),
+    "orc_se3exp": (None, [_dp, _dp, _dp]),
     "orc_sim3exp": (None, [_dp, _dp, _dp, _dp]),
     "orc_se3log": (None, [_dp, _dp, _dp]),
     "orc_plane_fit": (None, [_dp, C.c_int, _dp, _dp]),
@@ -90,6 +94,26 @@ def load(kind: str = "port"):
             fn.restype, fn.argtypes = res, args
         _libs[kind] = lib
     return _libs[kind]
+
+
+REFMATH_PATH = os.path.join(_HERE, "_ref", "liboracle_refmath.so")
+
+
+def load_refmath():
+    """The reference's own arithmetic lines compiled verbatim (oracle/Makefile `refmath`); None if not built."""
+    if not os.path.exists(REFMATH_PATH):
+        return None
+    if "refmath" not in _libs:
+        lib = C.CDLL(REFMATH_PATH)
+        lib.refm_covariance.argtypes = [_dp, C.c_int, _u32p, C.c_int, _dp]
+        lib.refm_fast_eigen.argtypes = [_dp, _dp, _dp]
+        lib.refm_sim3exp.argtypes = [_dp, _dp, _dp, _dp]
+        lib.refm_sim3exp_dual.argtypes = [_dp, _dp]
+        lib.refm_se3exp.argtypes = [_dp, _dp, _dp]
+        for f in (lib.refm_covariance, lib.refm_fast_eigen, lib.refm_sim3exp, lib.refm_sim3exp_dual, lib.refm_se3exp):
+            f.restype = None
+        _libs["refmath"] = lib
+    return _libs["refmath"]
 
 
 def have_ref() -> bool:
