@@ -121,7 +121,7 @@ void free_work(stl_ctx *c) {
     DevWork &w = c->wk;
     dfree(w.cand); dfree(w.corr_kp); dfree(w.corr_pt); dfree(w.corr_sp); dfree(w.q_corr); dfree(w.q_kpsp); dfree(w.n_corr); dfree(w.n_q);
     dfree(w.k1_match);
-    dfree(w.frame); dfree(w.align); dfree(w.nn_pos); dfree(w.nb); dfree(w.nbx); dfree(w.nb_m); dfree(w.nb_last); dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn); dfree(w.dbg_stats);
+    dfree(w.frame); dfree(w.align); dfree(w.nn_pos); dfree(w.nn_g2); dfree(w.nb); dfree(w.nbx); dfree(w.nb_m); dfree(w.nb_last); dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn); dfree(w.dbg_stats);
     dfree(w.overflow); dfree(w.k1_clk);
     w = DevWork();
     c->wk_cap = 0;
@@ -208,7 +208,7 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
             A_(w.n_corr, 4 * nf); A_(w.n_q, 4 * nf);
             A_(w.k1_match, sizeof(ulonglong2) * 8192 * nf);
             A_(w.frame, sizeof(FrameRec) * nf); A_(w.align, sizeof(AlignRec) * nf * w.sub);
-            A_(w.nn_pos, 4 * nm); A_(w.nb, 4 * nm * kMaxK); A_(w.nbx, sizeof(float4) * nm * kMaxK); A_(w.nb_m, 4 * nm); A_(w.nb_last, 8 * nm);
+            A_(w.nn_pos, 4 * nm); A_(w.nn_g2, 4 * nm); A_(w.nb, 4 * nm * kMaxK); A_(w.nbx, sizeof(float4) * nm * kMaxK); A_(w.nb_m, 4 * nm); A_(w.nb_last, 8 * nm);
             w.nbx_stride = (long long)nm;
             if (getenv("STL_K1_CLK")) { A_(w.k1_clk, 64 * nf); e = cudaMemsetAsync(w.k1_clk, 0, 64 * nf, ctx->last_stream); if (e != cudaSuccess) return e; }
             A_(w.overflow, 4);
@@ -303,12 +303,13 @@ stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st) 
     if (getenv("STL_NO_ASSOC_REUSE")) slot = -1;
     DevWork view = ctx->wk;
     const uint32_t *nn_hint = nullptr;
+    const float *nn_g2 = nullptr;
     if (slot >= 0) {
         const long long nk = pk.n_kp_total, F = pk.n_kf;
         view.cand += slot;
         view.corr_kp += slot * nk; view.corr_pt += slot * nk; view.corr_sp += slot * nk; view.q_corr += slot * nk; view.q_kpsp += slot * nk;
         view.n_corr += slot * F; view.n_q += slot * F;
-        if (ctx->wk_has_nn) nn_hint = ctx->wk.nn_pos + slot * pk.n_mp_total;  // K2a's 1-NN of the same map points at this x
+        if (ctx->wk_has_nn) { nn_hint = ctx->wk.nn_pos + slot * pk.n_mp_total; nn_g2 = ctx->wk.nn_g2 + slot * pk.n_mp_total; }  // K2a's 1-NN of the same map points at this x
         ctx->assoc_reused += 1;
     } else {
         DevCand *hc = ctx->h_cand;
@@ -324,7 +325,7 @@ stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st) 
         ctx->wk_has_nn = false;
     }
     cudaError_t e;
-    { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint); }
+    { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint, getenv("STL_NO_NN_CERT") ? nullptr : nn_g2); }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "associate: %s", cudaGetErrorString(e));
     ctx->launches += (ctx->dpr.plane_index && !ctx->dpr.use_gpr) ? 3 : 4;  // the association kernels (cub select kernels not counted)
     if (ctx->params.use_gpr && ctx->params.gpr_optimize) {  // GPR::fit per factor (IBACalib2.hpp:460-461), host side

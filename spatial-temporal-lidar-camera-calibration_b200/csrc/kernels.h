@@ -50,6 +50,7 @@ struct DevWork {
     AlignRec *align = nullptr;    // [Bc][n_kf][sub]
     // neighbour lists of the 3-D queries, slot = b * n_mp_total + mp_off[f] + qi
     uint32_t *nn_pos = nullptr;   // [Bc][n_mp_total] sorted position of the 1-NN
+    float *nn_g2 = nullptr;       // [Bc][n_mp_total] lower bound of the squared distance to any OTHER scan point (Sink1::g2)
     uint32_t *nb = nullptr;       // [Bc][n_mp_total][32] sorted positions of the k-NN, distance order
     float4 *nbx = nullptr;        // [32][Bc * n_mp_total] their coordinates, transposed (plane kernels read them coalesced)
     long long nbx_stride = 0;

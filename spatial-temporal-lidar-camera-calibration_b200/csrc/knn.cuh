@@ -13,6 +13,7 @@
 // by original index.  Latency-bound on L2-resident data.
 #pragma once
 #include <cfloat>
+#include <cmath>
 
 #include "common.cuh"
 #include "geom.cuh"
@@ -67,11 +68,25 @@ __device__ __forceinline__ float box_lbf(const QueryF &q, float4 lo, float4 hi) 
 
 // ---- result sinks ---------------------------------------------------------------
 // 1-NN: (d2, orig) lexicographic minimum.  All members are warp-uniform.
+// Besides the minimum the sink keeps g2, a float32 LOWER bound of the squared distance from the query to every scan point
+// other than the current best that has been looked at or ruled out so far (visited points: their own distance, shrunk by
+// 2^-22; unopened boxes: the box bound, see note_pruned / note_bound).  After an exhaustive search g2 bounds the distance
+// to the second-nearest point from below; a nearby query (the LM path's twin of an evaluation query) can then be answered
+// without a search whenever the gap exceeds the displacement (lm.cu, k_lm_knn_b).
 struct Sink1 {
     double d = DBL_MAX;
     float df = 3.402823466e+38f;  // d rounded up to float32
+    float g2 = HUGE_VALF;  // +inf
     uint32_t oi = 0xffffffffu, pos = 0xffffffffu;
     __device__ __forceinline__ bool may_contain(float lb) const { return lb <= df; }
+    __device__ __forceinline__ static float below(double dd) { return __fmul_rd(__double2float_rd(dd), 0.99999976f); }
+    // boxes that were tested and never opened: lane-wise bound `lb`, counted where `pruned`
+    __device__ __forceinline__ void note_pruned(float lb, bool pruned) {
+        const unsigned k = __reduce_min_sync(kFull, pruned ? __float_as_uint(lb) : 0x7f800000u);
+        g2 = fminf(g2, __uint_as_float(k));
+    }
+    // a bound that holds for every point not covered otherwise (warp-uniform argument)
+    __device__ __forceinline__ void note_bound(float b) { g2 = fminf(g2, b); }
     // start from a scan point expected to be close (all lanes read the same address): every box test then
     // already sees a finite bound.  The point is an ordinary candidate of the (d2, index) minimum.
     __device__ __forceinline__ void seed(const ScanView &S, uint32_t p, double qx, double qy, double qz) {
@@ -81,8 +96,12 @@ struct Sink1 {
     __device__ __forceinline__ void visit(const ScanView &S, int leaf, double qx, double qy, double qz, int lane) {
         const int g = leaf * kLeaf + lane;
         const double dd = dist3e(qx, qy, qz, (double)S.px[g], (double)S.py[g], (double)S.pz[g]);  // NaN for pads
+        const float lowf = dd == dd ? below(dd) : __int_as_float(0x7f800000);
         const bool q = dd <= d;
-        if (!__any_sync(kFull, q)) return;
+        if (!__any_sync(kFull, q)) {  // nothing here beats the best: every point of the leaf except the best itself is an "other" point
+            note_pruned(lowf, (uint32_t)g != pos);
+            return;
+        }
         const uint32_t o = q ? S.orig[g] : 0xffffffffu;
         unsigned hi = q ? (unsigned)__double2hiint(dd) : 0xffffffffu;
         const unsigned mhi = __reduce_min_sync(kFull, hi);
@@ -93,8 +112,12 @@ struct Sink1 {
         const double cd = __hiloint2double((int)mhi, (int)mlo);
         if (cd < d || (cd == d && mo < oi)) {
             const int src = __ffs(__ballot_sync(kFull, tie && o == mo)) - 1;
+            if (pos != 0xffffffffu) g2 = fminf(g2, below(d));  // the previous best is an "other" point from now on
+            note_pruned(lowf, lane != src);                     // ... and so is everything in this leaf but the winner
             d = cd; oi = mo; pos = (uint32_t)(leaf * kLeaf + src);
             df = __double2float_ru(cd);
+        } else {
+            note_pruned(lowf, (uint32_t)g != pos);
         }
     }
 };
@@ -115,6 +138,8 @@ struct SinkK {
         return d < r2 && (count < k || d < wd || (d == wd && i < wi));
     }
     __device__ __forceinline__ bool may_contain(float lb) const { return lb <= r2f && (count < k || lb <= wdf); }
+    __device__ __forceinline__ void note_pruned(float, bool) {}
+    __device__ __forceinline__ void note_bound(float) {}
     __device__ __forceinline__ void visit(const ScanView &S, int leaf, double qx, double qy, double qz, int lane) {
         const int g = leaf * kLeaf + lane;
         const double dd = dist3e(qx, qy, qz, (double)S.px[g], (double)S.py[g], (double)S.pz[g]);
@@ -252,8 +277,11 @@ __device__ __forceinline__ void traverse(const ScanView &S, double qx, double qy
                 done0 |= 1u << s0;
                 sink.visit(S, (s2 * 32 + s1) * 32 + s0, qx, qy, qz, lane);
             }
+            sink.note_pruned(lb0, !((done0 >> lane) & 1u));
         }
+        sink.note_pruned(lb1, !((done1 >> lane) & 1u));
     }
+    sink.note_pruned(lb2, !((done2 >> lane) & 1u));
 }
 
 // Queries of a CTA are handed out through a shared-memory ticket: a warp that drew short traversals
@@ -288,6 +316,7 @@ __device__ __forceinline__ float scan_adjacent(const ScanView &S, int home, doub
         done |= 1u << s;
         sink.visit(S, (int)__shfl_sync(kFull, id, s), qx, qy, qz, lane);
     }
+    sink.note_pruned(lb, !((done >> lane) & 1u));  // listed boxes that were never opened (unlisted slots carry +inf)
     return cov;
 }
 
@@ -326,6 +355,10 @@ __device__ __forceinline__ void nn_near_leaf(const ScanView &S, float adj_r, int
         const float reach = __fadd_ru(__fsqrt_ru(nn.df), delta);
         if (cov > 3.0e38f ? reach <= adj_r : reach < __fsqrt_rd(cov)) {
             if (S.stats && lane == 0) atomicAdd(S.stats + 5, 1ull);
+            // leaves the row does not list lie farther than the covered range from the home box, hence from the query by
+            // at least that minus the distance of the query to the home box
+            const float u = __fsub_rd(cov > 3.0e38f ? adj_r : __fsqrt_rd(cov), delta);
+            nn.note_bound(u > 0.f ? __fmul_rd(u, u) : 0.f);
             return;
         }
         // second chance through the leaf of the point just found (p1, at distance rho): every point as
@@ -336,8 +369,11 @@ __device__ __forceinline__ void nn_near_leaf(const ScanView &S, float adj_r, int
             const float cov1 = S.adj_cov[l1];
             const float two_rho = __fmul_ru(2.f, __fsqrt_ru(nn.df));
             if (cov1 >= 0.f && (cov1 > 3.0e38f ? two_rho <= adj_r : two_rho < __fsqrt_rd(cov1))) {
+                const float rho_up = __fsqrt_ru(nn.df);  // distance from the query to p1, which lies in leaf l1
                 scan_adjacent(S, l1, qx, qy, qz, nn, lane);
                 if (S.stats && lane == 0) atomicAdd(S.stats + 5, 1ull);
+                const float u = __fsub_rd(cov1 > 3.0e38f ? adj_r : __fsqrt_rd(cov1), rho_up);  // leaves not listed in l1's row
+                nn.note_bound(u > 0.f ? __fmul_rd(u, u) : 0.f);
                 return;
             }
         }

@@ -71,7 +71,7 @@ k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
         map_point_lidar(pk, K, c, f, ks.x, qx, qy, qz);
         Sink1 nn;
         nn_near_leaf(S, pr.adj_r, (int)(ks.y >> 5), qx, qy, qz, nn, lane, ks.y);  // seeded with the associated scan point
-        if (lane == 0) wk.nn_pos[qbase + qi] = nn.pos;
+        if (lane == 0) { wk.nn_pos[qbase + qi] = nn.pos; wk.nn_g2[qbase + qi] = nn.g2; }
         if (pr.use_plane && !pr.plane_index) {  // with the plane index the neighbourhood of nn is already fitted
             SinkK kn(pr.k, pr.radius2);
             knn_around_point(S, nn.pos, kn, lane);

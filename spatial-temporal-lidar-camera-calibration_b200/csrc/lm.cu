@@ -147,54 +147,96 @@ k_lm_plane_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
 }
 
 // L3: map point -> LiDAR frame with the association extrinsic, 1-NN gate, neighbourhood of that point
-// (iba_local.cpp:283-295)
+// (iba_local.cpp:283-295).
+// A warp draws 32 queries at a time, one per lane.  When the evaluation at this same extrinsic has just answered the 1-NN
+// of the map point's float32-scaled twin q (K2a: position h, and g2 = a lower bound of the squared distance from q to every
+// OTHER scan point), the LM query q' — the same map point scaled in fp64, a few micrometres from q — needs no search if
+//     sqrt(g2) - |q - q'|  >  |q' - h|                                  (triangle inequality, margins below):
+// every other point is then strictly farther from q' than h, so h is exactly what the KD-tree search returns.  Lanes
+// whose query is not settled that way (no evaluation at hand, near-equidistant neighbours) take turns on the warp-wide
+// exact search, seeded with h or with the associated scan point.
 __global__ void __launch_bounds__(kWarps * 32, STL_KNN_MINB)
-k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm, const uint32_t *__restrict__ nn_hint) {
+k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm, const uint32_t *__restrict__ nn_hint,
+           const float *__restrict__ nn_g2) {
     const int j = blockIdx.x % kAssocSub, f = blockIdx.x / kAssocSub;
     int nq;
     if (!lm_frame_active(wk, pr, f, nq)) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const DevKf K = pk.kf[f];
     const DevCand &c0 = wk.cand[0];
     const ScanView S = make_view(pk, K);
+    const float *Tcw = pk.Tcw + (long long)f * 12;
     __shared__ int ticket;
     if (threadIdx.x == 0) ticket = 0;
     __syncthreads();
     for (;;) {
-        const int qi = next_ticket(&ticket, lane) * kAssocSub + j;
-        if (qi >= nq) break;
+        const int base = next_ticket(&ticket, lane) * 32;
+        if ((long long)base * kAssocSub + j >= nq) break;
+        const int qi = (base + lane) * kAssocSub + j;
         const long long slot = K.mp_off + qi;
-        if (lm.stage[slot] != 1) continue;
-        const uint2 ks = wk.q_kpsp[K.kp_off + qi];
-        const uint32_t kp = ks.x, sp = ks.y;
-        double Mx, My, Mz, qx, qy, qz;
-        lm_map_point(pk, K, f, kp, Mx, My, Mz);
-        xform(c0.Ri, c0.ti, dmul(Mx, c0.s), dmul(My, c0.s), dmul(Mz, c0.s), qx, qy, qz);  // initSE3.inverse() * (MapPoint * init_scale)
-        Sink1 nn;
-        // seed: the 1-NN the evaluation at this same extrinsic found for (the float32-scaled twin of) this map
-        // point when it is at hand, else the associated scan point
-        uint32_t hint = nn_hint ? nn_hint[slot] : sp;
-        if (hint == 0xffffffffu) hint = sp;
-        nn_near_leaf(S, pr.adj_r, (int)(hint >> 5), qx, qy, qz, nn, lane, hint);
-        if (nn.d > pr.max_3d_dist2) {  // iba_local.cpp:289
-            if (lane == 0) lm.nnb_pos[slot] = 0xffffffffu;
-            continue;
+        const bool valid = qi < nq && lm.stage[slot] == 1;
+        uint32_t sp = 0, hint = 0xffffffffu, nn_pos = 0xffffffffu;
+        double qx = 0, qy = 0, qz = 0, nn_d = DBL_MAX;
+        bool settled = false;
+        if (valid) {
+            const uint2 ks = wk.q_kpsp[K.kp_off + qi];
+            const uint32_t kp = ks.x;
+            sp = ks.y;
+            double Mx, My, Mz;
+            lm_map_point(pk, K, f, kp, Mx, My, Mz);
+            xform(c0.Ri, c0.ti, dmul(Mx, c0.s), dmul(My, c0.s), dmul(Mz, c0.s), qx, qy, qz);  // initSE3.inverse() * (MapPoint * init_scale)
+            hint = nn_hint ? nn_hint[slot] : sp;
+            if (hint == 0xffffffffu) hint = sp;
+            if (nn_hint && nn_g2 && nn_hint[slot] != 0xffffffffu) {
+                // the evaluation's query for this map point (iba_global.cpp:231-234: GetWorldPos() * scale in float32)
+                const float *mp = pk.kp_mp + (K.kp_off + kp) * 3;
+                const double wx = (double)__fmul_rn(mp[0], c0.sf), wy = (double)__fmul_rn(mp[1], c0.sf), wz = (double)__fmul_rn(mp[2], c0.sf);
+                const double ex = dadd(dot3e((double)Tcw[0], (double)Tcw[1], (double)Tcw[2], wx, wy, wz), dmul((double)Tcw[3], c0.s));
+                const double ey = dadd(dot3e((double)Tcw[4], (double)Tcw[5], (double)Tcw[6], wx, wy, wz), dmul((double)Tcw[7], c0.s));
+                const double ez = dadd(dot3e((double)Tcw[8], (double)Tcw[9], (double)Tcw[10], wx, wy, wz), dmul((double)Tcw[11], c0.s));
+                double ox, oy, oz;
+                xform(c0.Ri, c0.ti, ex, ey, ez, ox, oy, oz);
+                const double move = sqrt(dist3e(ox, oy, oz, qx, qy, qz)) * (1.0 + 1e-9) + 1e-12;  // |q - q'|, rounded up
+                const double dh = dist3e(qx, qy, qz, (double)S.px[hint], (double)S.py[hint], (double)S.pz[hint]);
+                const double reach = (double)__fsqrt_rd(nn_g2[slot]) - move;                      // every other point is at least this far from q'
+                if (reach > 0.0 && reach * reach > dh * (1.0 + 1e-6) + 1e-18) { settled = true; nn_pos = hint; nn_d = dh; }
+            }
         }
-        if (lane == 0) lm.nnb_pos[slot] = nn.pos;
-        if (nn.pos == sp) {  // very often the associated scan point itself: its plane is already known
-            if (lane == 0) lm.nbb_m[slot] = -2;
-            continue;
+        // exact searches for the lanes that are not settled, one query at a time on the whole warp
+        unsigned todo = __ballot_sync(kFull, valid && !settled);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const double sx = __shfl_sync(kFull, qx, src), sy = __shfl_sync(kFull, qy, src), sz = __shfl_sync(kFull, qz, src);
+            const uint32_t sh = __shfl_sync(kFull, hint, src);
+            Sink1 nn;
+            nn_near_leaf(S, pr.adj_r, (int)(sh >> 5), sx, sy, sz, nn, lane, sh);
+            if (lane == src) { nn_pos = nn.pos; nn_d = nn.d; }
         }
-        if (pr.plane_index) {  // looked up by k_lm_plane_b
-            if (lane == 0) lm.nbb_m[slot] = -3;
-            continue;
+        bool want_knn = false;
+        if (valid) {
+            if (nn_d > pr.max_3d_dist2) {  // iba_local.cpp:289
+                lm.nnb_pos[slot] = 0xffffffffu;
+            } else {
+                lm.nnb_pos[slot] = nn_pos;
+                if (nn_pos == sp) lm.nbb_m[slot] = -2;          // very often the associated scan point itself: its plane is already known
+                else if (pr.plane_index) lm.nbb_m[slot] = -3;   // looked up by k_lm_plane_b
+                else want_knn = true;
+            }
         }
-        SinkK kn(pr.k, pr.radius2);
-        knn_around_point(S, nn.pos, kn, lane);
-        lm.nbb[slot * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
-        store_nb_coords(lm.nbbx, lm.nbbx_stride, slot, S, lane, kn.count, kn.kpos);
-        const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
-        if (lane == 0) { lm.nbb_m[slot] = kn.count; lm.nbb_last[slot] = last; }
+        unsigned kn_todo = __ballot_sync(kFull, want_knn);
+        while (kn_todo) {
+            const int src = __ffs(kn_todo) - 1;
+            kn_todo &= kn_todo - 1;
+            const uint32_t p = __shfl_sync(kFull, nn_pos, src);
+            const long long sl = K.mp_off + ((long long)(base + src) * kAssocSub + j);
+            SinkK kn(pr.k, pr.radius2);
+            knn_around_point(S, p, kn, lane);
+            lm.nbb[sl * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
+            store_nb_coords(lm.nbbx, lm.nbbx_stride, sl, S, lane, kn.count, kn.kpos);
+            const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
+            if (lane == 0) { lm.nbb_m[sl] = kn.count; lm.nbb_last[sl] = last; }
+        }
     }
 }
 
@@ -686,7 +728,8 @@ void lm_free(LmState &lm) {
 // Enqueues BuildProblem on `st` and returns without waiting: the block counts stay on the device
 // (d_counts: plane, 3-D, point-to-point, GPR), where the linearisation kernels read them; a copy lands
 // in pinned host memory behind `counts_done` for callers that want the numbers (lm_block_counts).
-cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st, const uint32_t *nn_hint) {
+cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st, const uint32_t *nn_hint,
+                         const float *nn_g2) {
     cudaError_t e;
 #define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
     const long long ns = pk.n_kp_total > 0 ? pk.n_kp_total : 1;
@@ -721,7 +764,7 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
     if (!(pr.plane_index && !pr.use_gpr))  // with the plane index there is no neighbourhood to search at the scan point
         k_lm_knn_a<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
     k_lm_plane_a<<<(unsigned)(pk.n_kf * kPlaneSub), 128, 0, st>>>(pk, wk, pr, lm);
-    k_lm_knn_b<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm, nn_hint);
+    k_lm_knn_b<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm, nn_hint, nn_g2);
     k_lm_plane_b<<<(unsigned)(pk.n_kf * kPlaneSub), 128, 0, st>>>(pk, wk, pr, lm);
     TRY(cudaGetLastError());
     cub::CountingInputIterator<int> it(0);

@@ -57,9 +57,10 @@ struct LmState {
 
 void lm_free(LmState &lm);
 // wk must hold the K1 result (correspondences) of the association extrinsic at candidate slot 0.
-// nn_hint (optional): per map-point slot, the 1-NN position an evaluation at the SAME extrinsic found (seeds the 3-D search)
+// nn_hint / nn_g2 (optional): per map-point slot, the 1-NN position an evaluation at the SAME extrinsic found and its
+// lower bound of the squared distance to any other scan point (Sink1::g2): seeds, or settles, the 3-D search
 cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st,
-                         const uint32_t *nn_hint = nullptr);
+                         const uint32_t *nn_hint = nullptr, const float *nn_g2 = nullptr);
 // x: HOST [B][7]; d_out: DEVICE [B][STL_LIN_NSUMS]
 // optional per-block output of a linearisation (device pointers; B must be 1)
 struct BlockOut {

@@ -547,6 +547,13 @@ def test_step_batch_equals_separate_calls(pkg, small_pack, small_candidates, mon
         c.upload(pack)
         assert np.array_equal(c.step(X, reassociate=True), S)
         assert c.work_counters()["assoc_reused"] == 0
+    monkeypatch.delenv("STL_NO_ASSOC_REUSE")
+    # the association settles most 1-NN searches of the map points from the evaluation's own result (second-nearest bound):
+    # switching that off (every query searched) must not change a bit
+    monkeypatch.setenv("STL_NO_NN_CERT", "1")
+    with capi.Context() as c:
+        c.upload(pack)
+        assert np.array_equal(c.step(X, reassociate=True), S)
 
 
 def test_rejected_pack_keeps_the_previous_state(pkg, small_pack, small_candidates):
