@@ -27,8 +27,8 @@ namespace stl {
 namespace {
 
 constexpr int kWarps = 8;
-#ifndef STL_KNN_MINB
-#define STL_KNN_MINB 8  // resident CTAs per SM the traversal kernels are compiled for (32 registers, full occupancy; measured best of 4..8)
+#ifndef STL_LM_MINB
+#define STL_LM_MINB 6  // resident CTAs per SM of the association's traversal kernels (40 registers): 8 / 6 / 5 measured 0.216 / 0.198 / 0.195 ms for the stage
 #endif
 constexpr int kAssocSub = 4;
 constexpr int kPlaneSub = 4;  // CTAs of 128 threads per keyframe in the thread-per-query plane kernels
@@ -59,7 +59,7 @@ __device__ __forceinline__ void lm_map_point(const DevPack &pk, const DevKf &K, 
 // The reference searches for every correspondence and only afterwards drops those without a map
 // point (:213) or without a covisible observation (:259); neither test depends on the search, so
 // they come first here.
-__global__ void __launch_bounds__(kWarps * 32, STL_KNN_MINB)
+__global__ void __launch_bounds__(kWarps * 32, STL_LM_MINB)
 k_lm_knn_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
     const int j = blockIdx.x % kAssocSub, f = blockIdx.x / kAssocSub;
     int nq;
@@ -155,7 +155,7 @@ k_lm_plane_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
 // every other point is then strictly farther from q' than h, so h is exactly what the KD-tree search returns.  Lanes
 // whose query is not settled that way (no evaluation at hand, near-equidistant neighbours) take turns on the warp-wide
 // exact search, seeded with h or with the associated scan point.
-__global__ void __launch_bounds__(kWarps * 32, STL_KNN_MINB)
+__global__ void __launch_bounds__(kWarps * 32, STL_LM_MINB)
 k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm, const uint32_t *__restrict__ nn_hint,
            const float *__restrict__ nn_g2) {
     const int j = blockIdx.x % kAssocSub, f = blockIdx.x / kAssocSub;
