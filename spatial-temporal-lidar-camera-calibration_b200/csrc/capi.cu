@@ -38,7 +38,8 @@ struct stl_ctx {
     DevPack pk;
     std::vector<DevKf> h_kf;
     int max_kp = 0, max_bm_words = 0;
-    size_t k1_smem = 0;
+    size_t k1_smem = 0, k1_split_smem = 0;
+    bool k1_mono = true;   // the one-kernel K1 (assoc2d.cu); STL_K1_SPLIT=1 selects the three-kernel form (assoc2d_split.cu)
     long long n_pts_total = 0;
     // workspace
     DevWork wk;
@@ -120,7 +121,7 @@ void free_pack(stl_ctx *c) {
 void free_work(stl_ctx *c) {
     DevWork &w = c->wk;
     dfree(w.cand); dfree(w.corr_kp); dfree(w.corr_pt); dfree(w.corr_sp); dfree(w.q_corr); dfree(w.q_kpsp); dfree(w.n_corr); dfree(w.n_q);
-    dfree(w.k1_match);
+    dfree(w.k1_match); dfree(w.k1_surv); dfree(w.k1_cnt); dfree(w.k1_best_d2); dfree(w.k1_best_key);
     dfree(w.frame); dfree(w.align); dfree(w.nn_pos); dfree(w.nn_g2); dfree(w.nb); dfree(w.nbx); dfree(w.nb_m); dfree(w.nb_last); dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn); dfree(w.dbg_stats);
     dfree(w.overflow); dfree(w.k1_clk);
     w = DevWork();
@@ -191,7 +192,7 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
     if (ctx->wk_cap == 0) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        const size_t per_cand = (size_t)pk.n_kp_total * 24 + (size_t)pk.n_mp_total * (20 * kMaxK + 16) + (size_t)pk.n_kf * (sizeof(FrameRec) + 4 * sizeof(AlignRec) + 8 + sizeof(ulonglong2) * 8192) + sizeof(DevCand);
+        const size_t per_cand = (size_t)pk.n_kp_total * 24 + (size_t)pk.n_mp_total * (20 * kMaxK + 16) + (size_t)pk.n_kf * (sizeof(FrameRec) + 4 * sizeof(AlignRec) + 24 + sizeof(ulonglong2) * kK1MatchCap + 4 * kK1SurvCap) + (size_t)pk.n_kp_total * 16 + sizeof(DevCand);
         size_t budget = std::min<size_t>((size_t)12 << 30, free_b / 4);
         int cap = (int)std::max<size_t>(1, std::min<size_t>(budget / std::max<size_t>(per_cand, 1), 256));
         if (const char *e = getenv("STL_MAX_CHUNK")) cap = std::max(1, std::min(cap, atoi(e)));  // tests: force the multi-chunk path
@@ -206,7 +207,8 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
             A_(w.cand, sizeof(DevCand) * cap);
             A_(w.corr_kp, 4 * nk); A_(w.corr_pt, 4 * nk); A_(w.corr_sp, 4 * nk); A_(w.q_corr, 4 * nk); A_(w.q_kpsp, 8 * nk);
             A_(w.n_corr, 4 * nf); A_(w.n_q, 4 * nf);
-            A_(w.k1_match, sizeof(ulonglong2) * 8192 * nf);
+            A_(w.k1_match, sizeof(ulonglong2) * kK1MatchCap * nf);
+            A_(w.k1_surv, 4 * (size_t)kK1SurvCap * nf); A_(w.k1_cnt, 16 * nf); A_(w.k1_best_d2, 8 * nk); A_(w.k1_best_key, 8 * nk);
             A_(w.frame, sizeof(FrameRec) * nf); A_(w.align, sizeof(AlignRec) * nf * w.sub);
             A_(w.nn_pos, 4 * nm); A_(w.nn_g2, 4 * nm); A_(w.nb, 4 * nm * kMaxK); A_(w.nbx, sizeof(float4) * nm * kMaxK); A_(w.nb_m, 4 * nm); A_(w.nb_last, 8 * nm);
             w.nbx_stride = (long long)nm;
@@ -267,7 +269,10 @@ stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, c
     for (int c0 = 0; c0 < B; c0 += Bc) {
         const int nb = std::min(Bc, B - c0);
         CK(cudaMemcpyAsync(ctx->wk.cand, ctx->h_cand + c0, sizeof(DevCand) * nb, cudaMemcpyHostToDevice, st));
-        { StageTimer t(ctx, STL_STAGE_ASSOC2D, st); CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_smem, st)); }
+        { StageTimer t(ctx, STL_STAGE_ASSOC2D, st);
+          if (ctx->k1_mono) CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_smem, st));
+          else CK(launch_assoc2d_split(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_split_smem, 0, st)); }
+        ctx->launches += ctx->k1_mono ? 0 : 2;
         { StageTimer t(ctx, STL_STAGE_KNN3D, st); CK(launch_align3d(ctx->pk, ctx->wk, ctx->dpr, nb, debug ? 1 : 0, st)); }
         { StageTimer t(ctx, STL_STAGE_REDUCE, st); CK(launch_reduce(ctx->pk, ctx->wk, ctx->dpr, nb, d_out + (size_t)c0 * out_stride, st, out_stride)); }
         ctx->launches += 4;  // K1, K2a, K2b, K3
@@ -319,8 +324,10 @@ stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st) 
         CK(cudaMemcpyAsync(ctx->wk.cand, hc, sizeof(DevCand), cudaMemcpyHostToDevice, st));
         CK(cudaEventRecord(ctx->h2d_done, st));
         // 2-D association at x0 (FindProjectCorrespondences, iba_local.cpp:191): K1 without the cost terms
-        { StageTimer t(ctx, STL_STAGE_ASSOC2D, st); CK(launch_assoc2d(pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, st, 0)); }
-        ctx->launches += 1;
+        { StageTimer t(ctx, STL_STAGE_ASSOC2D, st);
+          if (ctx->k1_mono) CK(launch_assoc2d(pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, st, 0));
+          else CK(launch_assoc2d_split(pk, ctx->wk, ctx->dpr, 1, ctx->k1_split_smem, 0, st, 0)); }
+        ctx->launches += ctx->k1_mono ? 1 : 3;
         ctx->wk_x.assign(x0, x0 + 7);
         ctx->wk_has_nn = false;
     }
@@ -490,6 +497,9 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     if (k1_smem_new > (size_t)smem_optin)
         return fail(ctx, STL_ERR_CAPACITY, "K1 needs %zu B of shared memory (%d keypoints); device limit %d", k1_smem_new, max_kp, smem_optin);
     CK(assoc2d_configure(k1_smem_new));
+    const size_t k1_split_new = assoc2d_split_smem_bytes(max_bm, max_groups);
+    if (k1_split_new > (size_t)smem_optin) return fail(ctx, STL_ERR_CAPACITY, "K1a needs %zu B of shared memory; device limit %d", k1_split_new, smem_optin);
+    CK(assoc2d_split_configure(k1_split_new));
 
     // ---- from here on the previous state is gone
     free_work(ctx);
@@ -497,7 +507,8 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     lm_free(ctx->lm);
     ctx->h_kf.swap(hk_new);
     std::vector<DevKf> &hk2 = ctx->h_kf;
-    ctx->max_kp = max_kp; ctx->max_bm_words = max_bm; ctx->k1_smem = k1_smem_new;
+    ctx->max_kp = max_kp; ctx->max_bm_words = max_bm; ctx->k1_smem = k1_smem_new; ctx->k1_split_smem = k1_split_new;
+    ctx->k1_mono = getenv("STL_K1_SPLIT") == nullptr;
     cudaStream_t st = acquire_stream(ctx, nullptr);
     struct Scope {  // events and the raw-scan scratch are released on every exit path
         cudaEvent_t ev0 = nullptr, ev1 = nullptr; float *d_raw = nullptr; BuildScratch scr;

@@ -64,6 +64,11 @@ struct DevWork {
     uint32_t *dbg_knn = nullptr;  // [n_kp_total][32]
     unsigned long long *dbg_stats = nullptr;  // [8] traversal statistics (debug runs)
     ulonglong2 *k1_match = nullptr;  // [Bc][n_kf][8192] (d2 bits, keypoint<<32 | position) recorded by K1's exact pass
+    // three-kernel K1 (assoc2d_split.cu)
+    uint32_t *k1_surv = nullptr;              // [Bc][n_kf][kK1SurvCap] sorted positions that passed the pre-cull
+    int *k1_cnt = nullptr;                    // [Bc][n_kf][4] survivors, matches, overflow flag, pad
+    unsigned long long *k1_best_d2 = nullptr; // [Bc][n_kp_total] bits of the smallest squared pixel distance per keypoint
+    unsigned long long *k1_best_key = nullptr;// [Bc][n_kp_total] (original index << 32 | position) of the point that owns it
     long long *k1_clk = nullptr;  // optional [units][8] phase clocks of K1 (diagnostic, STL_K1_CLK=1)
     int *overflow = nullptr;      // K1 survivor-list overflow counter (diagnostic)
 };
@@ -97,12 +102,19 @@ cudaError_t build_scan_index(const float *d_raw, const long long *h_raw_off, int
 cudaError_t build_plane_index(const DevPack &pk, const DevKf *h_kf, int kf_begin, int nkf, const DevParams &pr, cudaStream_t st,
                               BuildScratch &scr);
 
-// ---- K1 (assoc2d.cu) ------------------------------------------------------------
+constexpr int kK1SurvCap = 4096;   // survivors of the float32 pre-cull a (candidate, keyframe) unit may list
+constexpr int kK1MatchCap = 8192;  // (keypoint, point) matches a unit may record between the exact pass and the tie pass
+
+// ---- K1 (assoc2d.cu: one kernel; assoc2d_split.cu: stream / exact / correspondence kernels, the default) ----------
 size_t assoc2d_smem_bytes(int max_kp, int max_bm_words, int max_cells, int max_groups);
 cudaError_t assoc2d_configure(size_t smem);
 // with_terms = 0: correspondences only (the association pass of the LM path needs neither the covisible
 // re-projection term nor the hand-eye term)
 cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, cudaStream_t st, int with_terms = 1);
+size_t assoc2d_split_smem_bytes(int max_bm_words, int max_groups);
+cudaError_t assoc2d_split_configure(size_t smem);
+cudaError_t launch_assoc2d_split(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, int max_pts, cudaStream_t st,
+                                 int with_terms = 1);
 
 // ---- K2 (knn3d.cu) ---------------------------------------------------------------
 // K2a (traversal: 1-NN + k-NN, warp per query) then K2b (plane fit + distance, thread per query)
