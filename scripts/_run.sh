@@ -1,10 +1,6 @@
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,smsp__inst_executed.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:"k_stream|k_exact|k_corr" -s 6 -c 6 --csv --log-file gpurun_out/r02g_k1split.csv python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-extras > /dev/null 2>&1
-python - <<'PY'
-import csv
-rows=[r for r in csv.reader(l for l in open('gpurun_out/r02g_k1split.csv') if l.startswith('"'))]
-h=rows[0]; ik=h.index('Kernel Name'); im=h.index('Metric Name'); iv=h.index('Metric Value'); iid=h.index('ID')
-cur={}
-for r in rows[1:]:
-    cur.setdefault((r[iid], r[ik][:40]),{})[r[im]]=r[iv]
-for k,v in cur.items(): print(k, v)
-PY
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for e in "STL_SUB=4" "STL_SUB=8" "STL_SUB=16"; do env $e python bench.py --config c2 --nkf 188 --steps 60 --warmup 5 --no-cpu-baseline --no-extras 2>/dev/null | python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('$e', round(d['value'],1), round(d['ms_per_step'],4), d['stage_ms_per_launch'])"; done

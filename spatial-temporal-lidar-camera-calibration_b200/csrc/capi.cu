@@ -198,7 +198,12 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
         if (const char *e = getenv("STL_MAX_CHUNK")) cap = std::max(1, std::min(cap, atoi(e)));  // tests: force the multi-chunk path
         DevWork &w = ctx->wk;
         w.Bc = cap;
-        w.sub = getenv("STL_SUB") ? std::max(1, std::min(16, atoi(getenv("STL_SUB")))) : 4;
+        // CTAs per (candidate, keyframe) of the query kernels: a function of the keyframe count ONLY (never of the batch size:
+        // the sub-block partials are summed in sub order, and a batch must give the bits its candidates give one by one)
+        // (4 / 8 / 16 measured on a 188-keyframe shard: 0.319 / 0.316 / 0.329 ms per step — the small-shard kernels are bound
+        // by the latency of their longest query, not by the number of CTAs)
+        w.sub = 4;
+        if (getenv("STL_SUB")) w.sub = std::max(1, std::min(16, atoi(getenv("STL_SUB"))));
         const size_t nk = (size_t)std::max<long long>(pk.n_kp_total, 1) * cap, nf = (size_t)pk.n_kf * cap;
         const size_t nm = (size_t)std::max<long long>(pk.n_mp_total, 1) * cap;
         auto alloc_all = [&]() -> cudaError_t {

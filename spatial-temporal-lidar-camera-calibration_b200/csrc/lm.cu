@@ -30,8 +30,8 @@ constexpr int kWarps = 8;
 #ifndef STL_LM_MINB
 #define STL_LM_MINB 6  // resident CTAs per SM of the association's traversal kernels (40 registers): 8 / 6 / 5 measured 0.216 / 0.198 / 0.195 ms for the stage
 #endif
-constexpr int kAssocSub = 4;
-constexpr int kPlaneSub = 4;  // CTAs of 128 threads per keyframe in the thread-per-query plane kernels
+// CTAs per keyframe of the association kernels: LmState::sub, chosen from the keyframe count of the pack (4 at the KITTI-00
+// shape; more for a small keyframe shard of a multi-GPU run, whose few keyframes would otherwise leave most SMs idle)
 constexpr int kLinVals = 41;  // cost, g[7], H upper 28, n2d, npt, npl, nres, ngpr
 constexpr int kGprWarps = 1;  // one warp per CTA: the dual kernel matrix of a block takes ~40 KB of shared memory
 constexpr int kLinThreads = 128;
@@ -61,7 +61,7 @@ __device__ __forceinline__ void lm_map_point(const DevPack &pk, const DevKf &K, 
 // they come first here.
 __global__ void __launch_bounds__(kWarps * 32, STL_LM_MINB)
 k_lm_knn_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
-    const int j = blockIdx.x % kAssocSub, f = blockIdx.x / kAssocSub;
+    const int j = blockIdx.x % lm.sub, f = blockIdx.x / lm.sub;
     int nq;
     if (!lm_frame_active(wk, pr, f, nq)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -72,7 +72,7 @@ k_lm_knn_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
     if (threadIdx.x == 0) ticket = 0;
     __syncthreads();
     for (;;) {
-        const int qi = next_ticket(&ticket, lane) * kAssocSub + j;
+        const int qi = next_ticket(&ticket, lane) * lm.sub + j;
         if (qi >= nq) break;
         const uint2 ks = wk.q_kpsp[K.kp_off + qi];
         const uint32_t kp = ks.x, sp = ks.y;
@@ -100,14 +100,14 @@ k_lm_knn_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
 // L2: plane at the scan point (iba_local.cpp:218-231) -> 3-D/2-D block; decides whether the 3-D search runs
 __global__ void __launch_bounds__(128)
 k_lm_plane_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
-    const int j = blockIdx.x % kPlaneSub, f = blockIdx.x / kPlaneSub;
+    const int j = blockIdx.x % lm.sub, f = blockIdx.x / lm.sub;
     int nq;
     if (!lm_frame_active(wk, pr, f, nq)) return;
     const DevKf K = pk.kf[f];
     const ScanView S = make_view(pk, K);
     const bool from_index = pr.plane_index && !pr.use_gpr;  // then k_lm_knn_a did not run: the covisibility test is made here
     const int C = pk.n_covis;
-    for (int qi = j * blockDim.x + threadIdx.x; qi < nq; qi += kPlaneSub * blockDim.x) {
+    for (int qi = j * blockDim.x + threadIdx.x; qi < nq; qi += lm.sub * blockDim.x) {
         const long long slot = K.mp_off + qi;
         lm.stage[slot] = 0;
         const uint32_t ci = wk.q_corr[K.kp_off + qi];
@@ -158,7 +158,7 @@ k_lm_plane_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
 __global__ void __launch_bounds__(kWarps * 32, STL_LM_MINB)
 k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm, const uint32_t *__restrict__ nn_hint,
            const float *__restrict__ nn_g2) {
-    const int j = blockIdx.x % kAssocSub, f = blockIdx.x / kAssocSub;
+    const int j = blockIdx.x % lm.sub, f = blockIdx.x / lm.sub;
     int nq;
     if (!lm_frame_active(wk, pr, f, nq)) return;
     const int lane = threadIdx.x & 31;
@@ -171,8 +171,8 @@ k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm, c
     __syncthreads();
     for (;;) {
         const int base = next_ticket(&ticket, lane) * 32;
-        if ((long long)base * kAssocSub + j >= nq) break;
-        const int qi = (base + lane) * kAssocSub + j;
+        if ((long long)base * lm.sub + j >= nq) break;
+        const int qi = (base + lane) * lm.sub + j;
         const long long slot = K.mp_off + qi;
         const bool valid = qi < nq && lm.stage[slot] == 1;
         uint32_t sp = 0, hint = 0xffffffffu, nn_pos = 0xffffffffu;
@@ -229,7 +229,7 @@ k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm, c
             const int src = __ffs(kn_todo) - 1;
             kn_todo &= kn_todo - 1;
             const uint32_t p = __shfl_sync(kFull, nn_pos, src);
-            const long long sl = K.mp_off + ((long long)(base + src) * kAssocSub + j);
+            const long long sl = K.mp_off + ((long long)(base + src) * lm.sub + j);
             SinkK kn(pr.k, pr.radius2);
             knn_around_point(S, p, kn, lane);
             lm.nbb[sl * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
@@ -243,12 +243,12 @@ k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm, c
 // L4: ComputeLocalNormalSingleThre at the map point's neighbour (pointcloud.h:699-717,651-666) -> 3-D/3-D block
 __global__ void __launch_bounds__(128)
 k_lm_plane_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
-    const int j = blockIdx.x % kPlaneSub, f = blockIdx.x / kPlaneSub;
+    const int j = blockIdx.x % lm.sub, f = blockIdx.x / lm.sub;
     int nq;
     if (!lm_frame_active(wk, pr, f, nq)) return;
     const DevKf K = pk.kf[f];
     const ScanView S = make_view(pk, K);
-    for (int qi = j * blockDim.x + threadIdx.x; qi < nq; qi += kPlaneSub * blockDim.x) {
+    for (int qi = j * blockDim.x + threadIdx.x; qi < nq; qi += lm.sub * blockDim.x) {
         const long long slot = K.mp_off + qi;
         if (lm.stage[slot] != 1) continue;
         const uint32_t np = lm.nnb_pos[slot];
@@ -760,12 +760,13 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
         lm.max_blocks = nm;
     }
     lm.ready = false;
+    lm.sub = wk.sub;
     TRY(cudaMemsetAsync(lm.flags, 0, lm.flags_bytes, st));
     if (!(pr.plane_index && !pr.use_gpr))  // with the plane index there is no neighbourhood to search at the scan point
-        k_lm_knn_a<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
-    k_lm_plane_a<<<(unsigned)(pk.n_kf * kPlaneSub), 128, 0, st>>>(pk, wk, pr, lm);
-    k_lm_knn_b<<<(unsigned)(pk.n_kf * kAssocSub), kWarps * 32, 0, st>>>(pk, wk, pr, lm, nn_hint, nn_g2);
-    k_lm_plane_b<<<(unsigned)(pk.n_kf * kPlaneSub), 128, 0, st>>>(pk, wk, pr, lm);
+        k_lm_knn_a<<<(unsigned)(pk.n_kf * lm.sub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
+    k_lm_plane_a<<<(unsigned)(pk.n_kf * lm.sub), 128, 0, st>>>(pk, wk, pr, lm);
+    k_lm_knn_b<<<(unsigned)(pk.n_kf * lm.sub), kWarps * 32, 0, st>>>(pk, wk, pr, lm, nn_hint, nn_g2);
+    k_lm_plane_b<<<(unsigned)(pk.n_kf * lm.sub), 128, 0, st>>>(pk, wk, pr, lm);
     TRY(cudaGetLastError());
     cub::CountingInputIterator<int> it(0);
     size_t tb = lm.tmp_bytes;

@@ -12,6 +12,7 @@ struct LmState {
     bool ready = false;
     long long n_blocks[4] = {0, 0, 0, 0};  // plane (3-D/2-D), point-to-point, point-to-plane, GPR (3-D/2-D)
     long long n_slots = 0;
+    int sub = 4;                  // CTAs per keyframe of the association kernels (= DevWork::sub)
     int *slot_kf = nullptr;       // [n_slots]
     uint32_t *slot_kp = nullptr;  // [n_slots]
     uint8_t *flags = nullptr;     // one allocation: flag2d | type3d | flag3d | flagG | d_counts (cleared by one memset)
