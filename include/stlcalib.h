@@ -354,6 +354,11 @@ stl_status_t stl_comm_unique_id(uint8_t id[STL_COMM_ID_BYTES]);
 stl_status_t stl_comm_init(stl_ctx_t *ctx, const uint8_t id[STL_COMM_ID_BYTES], int32_t rank, int32_t n_ranks);
 /* rank / size of the attached communicator (0 / 1 when none). */
 stl_status_t stl_comm_info(stl_ctx_t *ctx, int32_t *rank, int32_t *n_ranks);
+/* How the records are exchanged: out[0] = 1 when every rank could map every other rank's receive buffer (cudaIpc peer
+ * memory over NVLink): the kernel that finishes a record then also sums it over the ranks, in rank order, with no separate
+ * collective launch (csrc/p2p.cuh); 0 = ncclAllReduce after the last kernel (also used for batches over 256 candidates;
+ * STL_NO_P2P=1 forces it).  out[1] = exchanges done through peer memory so far, out[2] = through NCCL. */
+stl_status_t stl_comm_stats(stl_ctx_t *ctx, int64_t out[3]);
 
 /* ---- debug getters (parity tests only) --------------------------------- */
 

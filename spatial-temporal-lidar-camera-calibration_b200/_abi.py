@@ -161,6 +161,7 @@ CALIB_SYMBOLS = {
     "stl_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "stl_comm_init": (C.c_int, [_vp, C.POINTER(C.c_uint8), C.c_int32, C.c_int32]),
     "stl_comm_info": (C.c_int, [_vp, _i32p, _i32p]),
+    "stl_comm_stats": (C.c_int, [_vp, _i64p]),
     "stl_debug_corrset": (C.c_int, [_vp, C.c_int32, C.c_int32, _u32p, _u32p, C.c_int32, _i32p]),
     "stl_debug_align": (C.c_int, [_vp, C.c_int32, C.c_int32, _u32p, _u32p, _i32p, _i32p, _dp, _u32p,
                                   C.c_int32, _i32p]),

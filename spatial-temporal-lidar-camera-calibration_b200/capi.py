@@ -165,6 +165,12 @@ class Context:
         buf = (C.c_uint8 * _abi.STL_COMM_ID_BYTES).from_buffer_copy(uid)
         _check(self.lib, self.h, self.lib.stl_comm_init(self.h, buf, rank, n_ranks))
 
+    def comm_stats(self):
+        """dict(p2p: records exchanged inside the finishing kernel over peer memory?, p2p_exchanges, nccl_exchanges)."""
+        out = np.zeros(3, np.int64)
+        _check(self.lib, self.h, self.lib.stl_comm_stats(self.h, out.ctypes.data_as(_abi._i64p)))
+        return dict(p2p=bool(out[0]), p2p_exchanges=int(out[1]), nccl_exchanges=int(out[2]))
+
     def comm_info(self):
         r, n = C.c_int32(0), C.c_int32(1)
         _check(self.lib, self.h, self.lib.stl_comm_info(self.h, C.byref(r), C.byref(n)))

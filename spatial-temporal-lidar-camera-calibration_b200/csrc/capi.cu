@@ -60,6 +60,13 @@ struct stl_ctx {
     // multi-GPU: keyframes sharded over the ranks of this communicator (owned)
     ncclComm_t comm = nullptr;
     int comm_rank = 0, comm_size = 1;
+    // the record exchange inside the last kernel of a call, over cudaIpc-mapped peer memory (p2p.cuh)
+    bool p2p_on = false;
+    unsigned p2p_seq = 0;
+    P2pView p2p;  // data / flag pointers of every rank, rank, n, err
+    double *p2p_data = nullptr;
+    unsigned *p2p_flag = nullptr;
+    long long p2p_exchanges = 0, nccl_exchanges = 0;
     // LM path
     LmState lm;
     double *d_lin = nullptr;
@@ -184,6 +191,18 @@ void drain_events(stl_ctx *c) {
     c->evs.clear();
 }
 
+// The exchange folded into the kernel that finishes the record (p2p.cuh): a view for ONE exchange of B candidates, or a
+// disabled view (n = 0) when the peer path cannot take it — the caller then runs allreduce_record (NCCL) instead.
+P2pView p2p_view(stl_ctx *ctx, int B, int off, int width) {
+    P2pView v;
+    if (!ctx->p2p_on || B > kP2pMaxB || width > kP2pWidth) return v;
+    v = ctx->p2p;
+    v.seq = ++ctx->p2p_seq;
+    v.off = off; v.width = width;
+    ctx->p2p_exchanges += 1;
+    return v;
+}
+
 // Workspace of one candidate chunk.  Allocation is all-or-nothing: a failure midway frees what was
 // obtained and leaves wk_cap == 0, so the next call starts over instead of using half a workspace.
 // The counters are cleared on the stream the context last used (any later stream waits for it).
@@ -264,7 +283,10 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
 }
 
 // Enqueues the evaluation of B candidates; d_out [B][STL_EVAL_NSUMS] device.
-stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, cudaStream_t st, bool debug, int out_stride = STL_EVAL_NSUMS) {
+// exchange: the record of this call is complete after K3 (stl_eval_batch): K3 sums it over the ranks, chunk by chunk, when
+// the peer path is up; *exchanged tells the caller whether that happened (else it runs the NCCL all-reduce)
+stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, cudaStream_t st, bool debug, int out_stride = STL_EVAL_NSUMS,
+                          bool exchange = false, bool *exchanged = nullptr) {
     stl_status_t s = ensure_work(ctx, B, debug);
     if (s != STL_OK) return s;
     if (!ctx->h2d_done) CK(cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming));
@@ -279,7 +301,12 @@ stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, c
           else CK(launch_assoc2d_split(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_split_smem, 0, st)); }
         ctx->launches += ctx->k1_mono ? 0 : 2;
         { StageTimer t(ctx, STL_STAGE_KNN3D, st); CK(launch_align3d(ctx->pk, ctx->wk, ctx->dpr, nb, debug ? 1 : 0, st)); }
-        { StageTimer t(ctx, STL_STAGE_REDUCE, st); CK(launch_reduce(ctx->pk, ctx->wk, ctx->dpr, nb, d_out + (size_t)c0 * out_stride, st, out_stride)); }
+        {
+            StageTimer t(ctx, STL_STAGE_REDUCE, st);
+            const P2pView pv = exchange ? p2p_view(ctx, nb, 0, STL_EVAL_NSUMS) : P2pView();
+            if (exchanged) *exchanged = pv.n > 1;
+            CK(launch_reduce(ctx->pk, ctx->wk, ctx->dpr, nb, d_out + (size_t)c0 * out_stride, st, out_stride, &pv));
+        }
         ctx->launches += 4;  // K1, K2a, K2b, K3
         ctx->wk_x.assign(x + (size_t)c0 * 7, x + (size_t)(c0 + nb) * 7);
         ctx->wk_has_nn = true;  // K2a runs for every query of a kept frame and writes its nn_pos
@@ -298,6 +325,7 @@ stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, c
 stl_status_t allreduce_record(stl_ctx *ctx, double *d_buf, size_t count, cudaStream_t st) {
     if (!ctx->comm || ctx->comm_size <= 1) return STL_OK;
     StageTimer t(ctx, STL_STAGE_ALLREDUCE, st);
+    ctx->nccl_exchanges += 1;
     const ncclResult_t r = ncclAllReduce(d_buf, d_buf, count, ncclDouble, ncclSum, ctx->comm, st);
     if (r != ncclSuccess) return fail(ctx, STL_ERR_CUDA, "ncclAllReduce: %s", ncclGetErrorString(r));
     return STL_OK;
@@ -414,6 +442,11 @@ void stl_destroy(stl_ctx_t *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    for (int q = 0; q < kP2pMaxRanks; ++q) {
+        if (q != c->comm_rank && c->p2p.data[q]) cudaIpcCloseMemHandle(c->p2p.data[q]);
+        if (q != c->comm_rank && c->p2p.flag[q]) cudaIpcCloseMemHandle(c->p2p.flag[q]);
+    }
+    dfree(c->p2p_data); dfree(c->p2p_flag); dfree(c->p2p.err);
     if (c->comm) { ncclCommDestroy(c->comm); c->comm = nullptr; }
     drain_events(c);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -697,8 +730,9 @@ stl_status_t stl_eval_batch_device(stl_ctx_t *ctx, const double *x, int32_t B, d
     if (!ctx->has_pack) return fail(ctx, STL_ERR_STATE, "stl_upload_pack has not been called");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = acquire_stream(ctx, stream);
-    stl_status_t s = enqueue_eval(ctx, x, B, d_sums, st, false);
-    if (s != STL_OK) return s;
+    bool done = false;
+    stl_status_t s = enqueue_eval(ctx, x, B, d_sums, st, false, STL_EVAL_NSUMS, true, &done);
+    if (s != STL_OK || done) return s;
     return allreduce_record(ctx, d_sums, (size_t)B * STL_EVAL_NSUMS, st);
 }
 
@@ -710,9 +744,10 @@ stl_status_t stl_eval_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl_eval
     stl_status_t s = ensure_work(ctx, B, false);
     if (s != STL_OK) return s;
     cudaStream_t st = acquire_stream(ctx, nullptr);
-    s = enqueue_eval(ctx, x, B, ctx->d_sums, st, false);
+    bool done = false;
+    s = enqueue_eval(ctx, x, B, ctx->d_sums, st, false, STL_EVAL_NSUMS, true, &done);
     if (s != STL_OK) return s;
-    s = allreduce_record(ctx, ctx->d_sums, (size_t)B * STL_EVAL_NSUMS, st);
+    if (!done) s = allreduce_record(ctx, ctx->d_sums, (size_t)B * STL_EVAL_NSUMS, st);
     if (s != STL_OK) return s;
     CK(cudaMemcpyAsync(ctx->h_sums, ctx->d_sums, sizeof(double) * STL_EVAL_NSUMS * B, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -873,10 +908,15 @@ stl_status_t stl_block_counts(stl_ctx_t *ctx, int64_t n_blocks[4]) {
     return STL_OK;
 }
 
-static stl_status_t lin_enqueue(stl_ctx *ctx, const double *x, int B, double *d_out, cudaStream_t st, int out_stride = STL_LIN_NSUMS) {
+// exch_off / exch_width: the record k_lin_finish completes starts exch_off doubles from its own output row and is exch_width
+// long (0: no exchange); *exchanged as in enqueue_eval
+static stl_status_t lin_enqueue(stl_ctx *ctx, const double *x, int B, double *d_out, cudaStream_t st, int out_stride = STL_LIN_NSUMS,
+                                int exch_off = 0, int exch_width = 0, bool *exchanged = nullptr) {
     if (!ctx->lm.ready) return fail(ctx, STL_ERR_STATE, "stl_associate has not been called");
     cudaError_t e;
-    { StageTimer t(ctx, STL_STAGE_LINEARIZE, st); e = lm_linearize(ctx->pk, ctx->dpr, ctx->lm, x, B, d_out, st, nullptr, out_stride); }
+    const P2pView pv = exch_width > 0 ? p2p_view(ctx, B, exch_off, exch_width) : P2pView();
+    if (exchanged) *exchanged = pv.n > 1;
+    { StageTimer t(ctx, STL_STAGE_LINEARIZE, st); e = lm_linearize(ctx->pk, ctx->dpr, ctx->lm, x, B, d_out, st, nullptr, out_stride, &pv); }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "linearize: %s", cudaGetErrorString(e));
     ctx->launches += 2 + (ctx->lm.use_gpr ? 1 : 0);  // k_linearize, (k_linearize_gpr,) k_lin_finish
     return STL_OK;
@@ -902,10 +942,11 @@ static stl_status_t step_enqueue(stl_ctx *ctx, const double *x, int B, int reass
         s = enqueue_associate(ctx, x, st);
         if (s != STL_OK) return s;
     }
-    s = lin_enqueue(ctx, x, B, d_out + STL_EVAL_NSUMS, st, STL_STEP_NSUMS);
+    bool done = false;
+    s = lin_enqueue(ctx, x, B, d_out + STL_EVAL_NSUMS, st, STL_STEP_NSUMS, -STL_EVAL_NSUMS, STL_STEP_NSUMS, &done);
     if (s != STL_OK) return s;
     ctx->last_x.assign(x, x + (size_t)B * 7);  // the evaluation part stays inspectable through the debug getters
-    return allreduce_record(ctx, d_out, (size_t)B * STL_STEP_NSUMS, st);
+    return done ? STL_OK : allreduce_record(ctx, d_out, (size_t)B * STL_STEP_NSUMS, st);
 }
 
 stl_status_t stl_step_batch_device(stl_ctx_t *ctx, const double *x, int32_t B, int32_t reassociate, double *d_out, void *stream) {
@@ -941,8 +982,9 @@ stl_status_t stl_linearize_batch_device(stl_ctx_t *ctx, const double *x, int32_t
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = acquire_stream(ctx, stream);
-    stl_status_t s = lin_enqueue(ctx, x, B, d_out, st);
-    if (s != STL_OK) return s;
+    bool done = false;
+    stl_status_t s = lin_enqueue(ctx, x, B, d_out, st, STL_LIN_NSUMS, 0, STL_LIN_NSUMS, &done);
+    if (s != STL_OK || done) return s;
     return allreduce_record(ctx, d_out, (size_t)B * STL_LIN_NSUMS, st);
 }
 
@@ -953,9 +995,10 @@ stl_status_t stl_linearize_batch(stl_ctx_t *ctx, const double *x, int32_t B, stl
     stl_status_t s = ensure_lin(ctx, B, STL_LIN_NSUMS);
     if (s != STL_OK) return s;
     cudaStream_t st = acquire_stream(ctx, nullptr);
-    s = lin_enqueue(ctx, x, B, ctx->d_lin, st);
+    bool done = false;
+    s = lin_enqueue(ctx, x, B, ctx->d_lin, st, STL_LIN_NSUMS, 0, STL_LIN_NSUMS, &done);
     if (s != STL_OK) return s;
-    s = allreduce_record(ctx, ctx->d_lin, (size_t)B * STL_LIN_NSUMS, st);
+    if (!done) s = allreduce_record(ctx, ctx->d_lin, (size_t)B * STL_LIN_NSUMS, st);
     if (s != STL_OK) return s;
     CK(cudaMemcpyAsync(ctx->h_lin, ctx->d_lin, sizeof(double) * STL_LIN_NSUMS * B, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1126,6 +1169,50 @@ stl_status_t stl_comm_init(stl_ctx_t *ctx, const uint8_t id[STL_COMM_ID_BYTES], 
     const ncclResult_t r = ncclCommInitRank(&ctx->comm, n_ranks, u, rank);
     if (r != ncclSuccess) { ctx->comm = nullptr; return fail(ctx, STL_ERR_CUDA, "ncclCommInitRank: %s", ncclGetErrorString(r)); }
     ctx->comm_rank = rank; ctx->comm_size = n_ranks;
+    // peer-memory exchange (p2p.cuh): every rank maps every other rank's receive buffer; enabled only if ALL ranks succeed
+    int ok = 0;
+    if (!getenv("STL_NO_P2P") && n_ranks > 1 && n_ranks <= kP2pMaxRanks) {
+        const size_t db = sizeof(double) * 2 * n_ranks * kP2pMaxB * kP2pWidth, fb = sizeof(unsigned) * 2 * n_ranks * kP2pMaxB;
+        cudaIpcMemHandle_t mine[2], *all = new cudaIpcMemHandle_t[2 * n_ranks];
+        char *d_send = nullptr, *d_recv = nullptr;
+        cudaStream_t st = acquire_stream(ctx, nullptr);
+        bool good = cudaMalloc(&ctx->p2p_data, db) == cudaSuccess && cudaMalloc(&ctx->p2p_flag, fb) == cudaSuccess &&
+                    cudaMalloc(&ctx->p2p.err, sizeof(int)) == cudaSuccess && cudaMemset(ctx->p2p_data, 0, db) == cudaSuccess &&
+                    cudaMemset(ctx->p2p_flag, 0, fb) == cudaSuccess && cudaMemset(ctx->p2p.err, 0, sizeof(int)) == cudaSuccess &&
+                    cudaIpcGetMemHandle(&mine[0], ctx->p2p_data) == cudaSuccess && cudaIpcGetMemHandle(&mine[1], ctx->p2p_flag) == cudaSuccess &&
+                    cudaMalloc(&d_send, sizeof(mine)) == cudaSuccess && cudaMalloc(&d_recv, sizeof(mine) * n_ranks) == cudaSuccess &&
+                    cudaMemcpy(d_send, mine, sizeof(mine), cudaMemcpyHostToDevice) == cudaSuccess;
+        // the handles travel through the communicator itself; the collective is issued even on a rank whose setup failed
+        if (!good) { cudaGetLastError(); if (!d_send) cudaMalloc(&d_send, sizeof(mine)); if (!d_recv) cudaMalloc(&d_recv, sizeof(mine) * n_ranks); }
+        if (d_send && d_recv && ncclAllGather(d_send, d_recv, sizeof(mine), ncclChar, ctx->comm, st) == ncclSuccess && cudaStreamSynchronize(st) == cudaSuccess &&
+            cudaMemcpy(all, d_recv, sizeof(mine) * n_ranks, cudaMemcpyDeviceToHost) == cudaSuccess && good) {
+            ok = 1;
+            for (int q = 0; q < n_ranks && ok; ++q) {
+                if (q == rank) { ctx->p2p.data[q] = ctx->p2p_data; ctx->p2p.flag[q] = ctx->p2p_flag; continue; }
+                void *pd = nullptr, *pf = nullptr;
+                if (cudaIpcOpenMemHandle(&pd, all[2 * q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                    cudaIpcOpenMemHandle(&pf, all[2 * q + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+                ctx->p2p.data[q] = (double *)pd; ctx->p2p.flag[q] = (unsigned *)pf;
+            }
+        }
+        // agreement: one rank without the mapping and all fall back to NCCL
+        int *d_ok = nullptr;
+        if (cudaMalloc(&d_ok, sizeof(int)) == cudaSuccess && cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
+            ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, ctx->comm, st) == ncclSuccess && cudaStreamSynchronize(st) == cudaSuccess)
+            cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost);
+        else ok = 0;
+        cudaFree(d_ok); cudaFree(d_send); cudaFree(d_recv);
+        delete[] all;
+        ctx->p2p.n = n_ranks; ctx->p2p.rank = rank;
+        ctx->p2p_on = ok == 1;
+    }
+    return STL_OK;
+}
+
+stl_status_t stl_comm_stats(stl_ctx_t *ctx, int64_t out[3]) {
+    if (!ctx || !out) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    out[0] = ctx->p2p_on ? 1 : 0; out[1] = ctx->p2p_exchanges; out[2] = ctx->nccl_exchanges;
     return STL_OK;
 }
 

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace stl {
 
@@ -124,7 +125,9 @@ cudaError_t launch_knn3d(const DevPack &pk, int kf, const double *d_q, int nq, i
 
 // ---- K3 (reduce.cu) ----------------------------------------------------------------
 // out: [B][out_stride] fp64 (first STL_EVAL_NSUMS of each row), written (not accumulated); out_stride 0 = STL_EVAL_NSUMS
-cudaError_t launch_reduce(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, double *d_out, cudaStream_t st, int out_stride = 0);
+// p2p (optional): the kernel also exchanges and sums each candidate's record over the ranks (p2p.cuh)
+cudaError_t launch_reduce(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, double *d_out, cudaStream_t st, int out_stride = 0,
+                          const P2pView *p2p = nullptr);
 
 // ---- N4 (calib.cu): hand-eye initialisation edges and calibration-BA edges; HOST in, HOST out, synchronous
 }  // namespace stl

@@ -688,7 +688,7 @@ k_linearize_gpr(const DevPack pk, const DevParams pr, const LmState lm, const Lm
 // one CTA of 1024 threads per candidate: warp w sums values w, w+32 over the chunks (lane-strided partial
 // sums, then a shuffle tree: a fixed order, so the result is reproducible)
 __global__ void __launch_bounds__(1024)
-k_lin_finish(const double *__restrict__ partial, int nchunks, double *__restrict__ out, int out_stride) {
+k_lin_finish(const double *__restrict__ partial, int nchunks, double *__restrict__ out, int out_stride, const P2pView P) {
     __shared__ double tot[kLinVals];
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int v = warp; v < kLinVals; v += 32) {
@@ -707,6 +707,7 @@ k_lin_finish(const double *__restrict__ partial, int nchunks, double *__restrict
             for (int c = a; c < 7; ++c) { o[8 + a * 7 + c] = tot[h]; o[8 + c * 7 + a] = tot[h]; ++h; }
         o[57] = tot[36]; o[58] = tot[37]; o[59] = tot[38]; o[60] = tot[39]; o[61] = tot[40];
     }
+    if (P.n > 1) p2p_allreduce_record(P, b, out + (long long)b * out_stride + P.off);  // keyframes sharded over GPUs: sum the shards here
 }
 
 template <class T> void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
@@ -905,7 +906,7 @@ cudaError_t lm_get_gpr_hyper(const DevParams &pr, LmState &lm, double *out, cuda
 }
 
 cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
-                         const BlockOut *blocks, int out_stride) {
+                         const BlockOut *blocks, int out_stride, const P2pView *p2p) {
     cudaError_t e;
 #define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
     if (B > lm.cand_cap) {
@@ -948,7 +949,7 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
         else k_linearize_gpr<false><<<dim3(gchunks, B), 32, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, chunks, bo);
         TRY(cudaGetLastError());
     }
-    k_lin_finish<<<B, 1024, 0, st>>>(lm.partial, stride, d_out, out_stride > 0 ? out_stride : STL_LIN_NSUMS);
+    k_lin_finish<<<B, 1024, 0, st>>>(lm.partial, stride, d_out, out_stride > 0 ? out_stride : STL_LIN_NSUMS, p2p ? *p2p : P2pView());
     TRY(cudaGetLastError());
 #undef TRY
     return cudaSuccess;

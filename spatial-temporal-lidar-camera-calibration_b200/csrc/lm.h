@@ -73,7 +73,7 @@ struct BlockOut {
 
 // out_stride: doubles between the records of consecutive candidates in d_out (0 = STL_LIN_NSUMS)
 cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
-                         const BlockOut *blocks = nullptr, int out_stride = 0);
+                         const BlockOut *blocks = nullptr, int out_stride = 0, const P2pView *p2p = nullptr);
 // waits for the last association and mirrors its block counts into lm.n2d / n3d / nG / n_blocks
 cudaError_t lm_block_counts(LmState &lm);
 // GPR::fit for every GPR block of the last association (IBA_GPRFactor's constructor, IBACalib2.hpp:441-461): the

@@ -4,13 +4,14 @@
 // result is bit-reproducible run to run.  One CTA per candidate.
 #include "../../include/stlcalib.h"
 #include "kernels.h"
+#include "p2p.cuh"
 
 namespace stl {
 namespace {
 
 constexpr int kT = 256;
 
-__global__ void __launch_bounds__(kT) k_reduce(const DevPack pk, const DevWork wk, const DevParams pr, double *__restrict__ out, const int out_stride) {
+__global__ void __launch_bounds__(kT) k_reduce(const DevPack pk, const DevWork wk, const DevParams pr, double *__restrict__ out, const int out_stride, const P2pView P) {
     const int b = blockIdx.x;
     const int F = pk.n_kf, sub = wk.sub;
     double v[STL_EVAL_NSUMS];
@@ -42,13 +43,15 @@ __global__ void __launch_bounds__(kT) k_reduce(const DevPack pk, const DevWork w
         for (int w = 0; w < kT / 32; ++w) x += red[threadIdx.x][w];
         out[(long long)b * out_stride + threadIdx.x] = x;
     }
+    if (P.n > 1) p2p_allreduce_record(P, b, out + (long long)b * out_stride + P.off);  // keyframes sharded over GPUs: sum the shards here
 }
 
 }  // namespace
 
-cudaError_t launch_reduce(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, double *d_out, cudaStream_t st, int out_stride) {
+cudaError_t launch_reduce(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, double *d_out, cudaStream_t st, int out_stride,
+                          const P2pView *p2p) {
     if (B <= 0) return cudaSuccess;
-    k_reduce<<<B, kT, 0, st>>>(pk, wk, pr, d_out, out_stride > 0 ? out_stride : STL_EVAL_NSUMS);
+    k_reduce<<<B, kT, 0, st>>>(pk, wk, pr, d_out, out_stride > 0 ? out_stride : STL_EVAL_NSUMS, p2p ? *p2p : P2pView());
     return cudaGetLastError();
 }
 

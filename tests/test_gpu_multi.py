@@ -43,18 +43,22 @@ _WORKER = textwrap.dedent("""
         st = c.step(X, reassociate=True)
         nb = c.block_counts()
         lin = c.linearize(X[:2])
-        np.savez(outf, ev=ev, st=st, nb=nb, lin=lin)
+        cs = c.comm_stats()
+        np.savez(outf, ev=ev, st=st, nb=nb, lin=lin, p2p=np.array([cs["p2p"], cs["p2p_exchanges"], cs["nccl_exchanges"]]))
 """)
 
 
 @pytest.mark.skipif(not has_cuda() or _n_gpus() < 2, reason="needs two GPUs")
-def test_keyframe_shards_allreduced_by_the_library(tmp_path, synth):
+@pytest.mark.parametrize("exchange", ["peer-memory", "nccl"])
+def test_keyframe_shards_allreduced_by_the_library(tmp_path, synth, exchange):
     import importlib
     capi = importlib.import_module(PKG + ".capi")
     script = tmp_path / "worker.py"
     script.write_text(_WORKER.format(root=ROOT, pkg=PKG))
     idf = str(tmp_path / "nccl_id.bin")
     env = dict(os.environ, OMP_NUM_THREADS="4")
+    if exchange == "nccl":
+        env["STL_NO_P2P"] = "1"
     procs = [subprocess.Popen([sys.executable, str(script), str(r), "2", idf, str(tmp_path / f"out{r}.npz")],
                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env) for r in range(2)]
     outs = [p.communicate(timeout=600) for p in procs]
@@ -62,6 +66,10 @@ def test_keyframe_shards_allreduced_by_the_library(tmp_path, synth):
     r0, r1 = (np.load(str(tmp_path / f"out{r}.npz")) for r in range(2))
     for key in ("ev", "st", "lin"):
         assert np.array_equal(r0[key], r1[key]), key                    # every rank holds the same totals
+    if exchange == "nccl":
+        assert r0["p2p"][0] == 0 and r0["p2p"][1] == 0 and r0["p2p"][2] >= 3
+    else:   # the finishing kernels exchanged the records themselves: no collective launch at all
+        assert r0["p2p"][0] == 1 and r0["p2p"][1] >= 3 and r0["p2p"][2] == 0, r0["p2p"]
     pack, x_gt, _ = synth.generate(n_kf=6, seed=1000)
     X = synth.candidates(x_gt, 5, 0.4)
     with capi.Context(device=0) as c:
