@@ -390,6 +390,11 @@ stl_status_t stl_debug_frame(stl_ctx_t *ctx, int32_t b, int32_t kf, double out[1
 stl_status_t stl_knn3d(stl_ctx_t *ctx, int32_t kf, const double *q, int32_t nq, int32_t k,
                        double radius2, uint32_t *out_idx, double *out_d2, int32_t *out_count);
 
+/* The two transcendental calls of the plane fit (std::acos, std::cos in FastEigen3x3_EV, pointcloud.h:404-407) as the
+ * device evaluates them — correctly rounded, csrc/crmath.cuh — element-wise on x[n] (acos on x clamped to [-1, 1]).
+ * For the parity test against the host libm. */
+stl_status_t stl_debug_trig(stl_ctx_t *ctx, const double *x, int32_t n, double *acos_out, double *cos_out);
+
 /* ---- measurement -------------------------------------------------------- */
 
 #define STL_STAGE_ASSOC2D 0  /* K1 transform + project + 2-D association      */

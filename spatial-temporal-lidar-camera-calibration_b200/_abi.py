@@ -166,6 +166,7 @@ CALIB_SYMBOLS = {
     "stl_debug_align": (C.c_int, [_vp, C.c_int32, C.c_int32, _u32p, _u32p, _i32p, _i32p, _dp, _u32p,
                                   C.c_int32, _i32p]),
     "stl_debug_frame": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp]),
+    "stl_debug_trig": (C.c_int, [_vp, _dp, C.c_int32, _dp, _dp]),
     "stl_knn3d": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32, C.c_int32, C.c_double, _u32p, _dp, _i32p]),
     "stl_set_stream": (C.c_int, [_vp, _vp]),
     "stl_set_profiling": (C.c_int, [_vp, C.c_int32]),

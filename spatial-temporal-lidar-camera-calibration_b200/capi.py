@@ -242,6 +242,13 @@ class Context:
                  "sum_3d3d", "valid_3d3d", "cnt_3d3d", "valid_pl", "valid_pt")
         return dict(zip(names, out))
 
+    def debug_trig(self, x):
+        """The device's acos (of x clamped to [-1, 1]) and cos, as the plane fit evaluates them."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        a, c = np.zeros_like(x), np.zeros_like(x)
+        _check(self.lib, self.h, self.lib.stl_debug_trig(self.h, x.ctypes.data_as(_dp), len(x), a.ctypes.data_as(_dp), c.ctypes.data_as(_dp)))
+        return a, c
+
     def knn3d(self, kf: int, q, k: int, radius2: float = 0.0):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, 3)
         nq = q.shape[0]

@@ -875,6 +875,24 @@ stl_status_t stl_knn3d(stl_ctx_t *ctx, int32_t kf, const double *q, int32_t nq, 
     return STL_OK;
 }
 
+stl_status_t stl_debug_trig(stl_ctx_t *ctx, const double *x, int32_t n, double *acos_out, double *cos_out) {
+    if (!ctx || !x || !acos_out || !cos_out || n < 0) return STL_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) return STL_OK;
+    double *d = nullptr;
+    CK(cudaMalloc(&d, 24 * (size_t)n));
+    cudaStream_t st = acquire_stream(ctx, nullptr);
+    cudaError_t e = cudaMemcpyAsync(d, x, 8 * (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = launch_debug_trig(d, n, d + n, d + 2 * (size_t)n, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(acos_out, d + n, 8 * (size_t)n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cos_out, d + 2 * (size_t)n, 8 * (size_t)n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "debug_trig: %s", cudaGetErrorString(e));
+    return STL_OK;
+}
+
 // ---- LM path -------------------------------------------------------------------
 
 stl_status_t stl_associate(stl_ctx_t *ctx, const double *x0, int64_t n_blocks[4]) {

@@ -8,6 +8,7 @@
 //    3x3 Symmetric Matrices"; acos/cos are CUDA's, not bit-identical to glibc: normals
 //    agree to ~1e-15, gates are tolerance-aware in the tests.)
 #pragma once
+#include "crmath.cuh"
 #include "common.cuh"
 
 namespace stl {
@@ -81,8 +82,9 @@ __device__ inline V3 smallest_eigvec(const double *cov) {
         const double c02 = A[1] * A[4] - b11 * A[2];
         const double det = (b00 * c00 - A[1] * c01 + A[2] * c02) / (p * p * p);
         const double hd = fmin(fmax(det * 0.5, -1.0), 1.0);
-        const double ang = acos(hd) / 3.0;
-        const double beta2 = cos(ang) * 2, beta0 = cos(ang + 2.09439510239319549) * 2, beta1 = -(beta0 + beta2);
+        // std::acos / std::cos of the reference, correctly rounded (crmath.cuh): plane normals bit-identical to a glibc evaluation
+        const double ang = acos_cr(hd) / 3.0;
+        const double beta2 = cos_cr(ang) * 2, beta0 = cos_cr(ang + 2.09439510239319549) * 2, beta1 = -(beta0 + beta2);
         const double e0 = q + p * beta0, e1 = q + p * beta1, e2 = q + p * beta2;
         if (hd >= 0) {
             const V3 v2 = eigvec_first(A, e2);

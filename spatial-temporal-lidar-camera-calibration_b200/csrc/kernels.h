@@ -123,6 +123,9 @@ cudaError_t launch_align3d(const DevPack &pk, const DevWork &wk, const DevParams
 cudaError_t launch_knn3d(const DevPack &pk, int kf, const double *d_q, int nq, int k, double radius2, uint32_t *d_idx, double *d_d2,
                          int *d_cnt, cudaStream_t st);
 
+// the eigen-solver's correctly rounded acos / cos (crmath.cuh), element-wise: for the parity test against glibc
+cudaError_t launch_debug_trig(const double *d_x, int n, double *d_acos, double *d_cos, cudaStream_t st);
+
 // ---- K3 (reduce.cu) ----------------------------------------------------------------
 // out: [B][out_stride] fp64 (first STL_EVAL_NSUMS of each row), written (not accumulated); out_stride 0 = STL_EVAL_NSUMS
 // p2p (optional): the kernel also exchanges and sums each candidate's record over the ranks (p2p.cuh)

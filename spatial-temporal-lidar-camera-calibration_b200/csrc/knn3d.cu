@@ -227,6 +227,21 @@ cudaError_t build_plane_index(const DevPack &pk, const DevKf *h_kf, int kf_begin
     return cudaGetLastError();  // stream order protects the scratch: the next chunk's kernels run after these
 }
 
+namespace {
+__global__ void k_debug_trig(const double *__restrict__ x, int n, double *__restrict__ ac, double *__restrict__ co) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ac[i] = acos_cr(fmin(fmax(x[i], -1.0), 1.0));
+    co[i] = cos_cr(x[i]);
+}
+}  // namespace
+
+cudaError_t launch_debug_trig(const double *d_x, int n, double *d_acos, double *d_cos, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_debug_trig<<<(n + 255) / 256, 256, 0, st>>>(d_x, n, d_acos, d_cos);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_align3d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, int debug, cudaStream_t st) {
     if (B <= 0 || pk.n_kf <= 0) return cudaSuccess;
     k_nn_knn<<<(unsigned)(pk.n_kf * B * wk.sub), kWarps * 32, 0, st>>>(pk, wk, pr, B);

@@ -568,3 +568,34 @@ def test_rejected_pack_keeps_the_previous_state(pkg, small_pack, small_candidate
         with pytest.raises(pkg._abi.StlError):
             c.upload(bad)
         assert np.array_equal(c.eval_sums(small_candidates[:1]), want)
+
+
+def test_plane_fit_trigonometry_is_correctly_rounded(pkg):
+    """acos / cos of the eigen-solver (pointcloud.h:404-407): the device evaluates them in double-double and rounds once, so
+    they equal the correctly rounded value — checked against 50-digit arithmetic — and therefore glibc's wherever glibc
+    rounds correctly (counted: all but a percent or so), which makes the plane normals bit-identical to a CPU evaluation."""
+    import mpmath as mp
+    capi = importlib.import_module(PKG + ".capi")
+    rng = np.random.default_rng(9)
+    xa = np.concatenate([rng.uniform(-1, 1, 200000), 1 - 10.0 ** rng.uniform(-12, -1, 20000), -1 + 10.0 ** rng.uniform(-12, -1, 20000), [0.0, 0.5, -0.5]])
+    xc = np.concatenate([rng.uniform(0, np.pi, 200000), rng.uniform(0, np.pi / 3, 20000) + 2.09439510239319549, 10.0 ** rng.uniform(-9, 0, 20000), [0.0, np.pi / 2, np.pi]])
+    with capi.Context() as c:
+        a_dev, _ = c.debug_trig(xa)
+        _, c_dev = c.debug_trig(xc)
+    a_host, c_host = np.arccos(xa), np.cos(xc)
+    ulp_a = np.abs(a_dev - a_host) / np.spacing(np.abs(a_host))
+    ulp_c = np.abs(c_dev - c_host) / np.spacing(np.maximum(np.abs(c_host), 1e-300))
+    assert ulp_a.max() <= 1.0 and ulp_c.max() <= 1.0
+    # where they differ from glibc, the device value is the correctly rounded one (glibc's acos / cos are allowed 1 ulp)
+    mp.mp.prec = 200
+    for x, dv, hv, f in [(xa, a_dev, a_host, mp.acos), (xc, c_dev, c_host, mp.cos)]:
+        bad = np.flatnonzero(dv != hv)
+        for i in bad[:: max(1, len(bad) // 300)]:
+            t = f(mp.mpf(float(x[i])))
+            assert abs(mp.mpf(float(dv[i])) - t) <= abs(mp.mpf(float(hv[i])) - t), (x[i], dv[i], hv[i])
+        ok = np.flatnonzero(dv == hv)
+        for i in ok[:: max(1, len(ok) // 300)]:   # ... and where they agree, both are
+            t = f(mp.mpf(float(x[i])))
+            assert abs(mp.mpf(float(dv[i])) - t) <= mp.mpf(float(np.spacing(abs(dv[i])))) / 2 * (1 + mp.mpf(10) ** -20), (x[i], dv[i])
+    print("acos: %.2f %% of %d arguments bit-equal to glibc; cos: %.2f %% of %d" % (100 * (ulp_a == 0).mean(), len(xa), 100 * (ulp_c == 0).mean(), len(xc)))
+    assert (ulp_a == 0).mean() > 0.85 and (ulp_c == 0).mean() > 0.85
