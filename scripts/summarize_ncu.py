@@ -42,7 +42,7 @@ def launches():
     is_build = lambda k: any(k.startswith(b) or b in k for b in build)
     step_tot = sum(sum(v) for k, v in per.items() if not is_build(k)) or 1.0
     with open(os.path.join(P, f"{tag}_launches.txt"), "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  (python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-plane-index --no-poll-batch)\n")
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none  (python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras)\n")
         f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
         f.write("# share = of everything the process launched; step% = of the kernels of the timed step (index build excluded)\n")
         f.write(f"{'kernel':34s} {'launches':>8s} {'avg_us':>10s} {'total_us':>11s} {'share':>7s} {'step%':>7s}\n")
@@ -86,3 +86,7 @@ if d1:
 full("k2_full", f"{tag}_k2_knn.txt")
 full("k2b_full", f"{tag}_k2_plane.txt")
 full("lm_full", f"{tag}_lm_knn.txt")
+full("lin_full", f"{tag}_linearize.txt")
+full("k0_full", f"{tag}_k0_kd_refine.txt")
+full("kidx_full", f"{tag}_k0_index_knn.txt")
+full("k1poll_full", f"{tag}_k1_poll256.txt")
