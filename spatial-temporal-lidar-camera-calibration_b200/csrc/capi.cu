@@ -37,7 +37,7 @@ struct stl_ctx {
     float adj_r2 = 0.f;  // squared radius of the leaf adjacency lists, rounded up (0: none)
     DevPack pk;
     std::vector<DevKf> h_kf;
-    int max_kp = 0, max_bm_words = 0;
+    int max_kp = 0, max_bm_words = 0, max_tab = 0, n_sm = 0;
     size_t k1_smem = 0, k1_split_smem = 0;
     bool k1_mono = true;   // the one-kernel K1 (assoc2d.cu); STL_K1_SPLIT=1 selects the three-kernel form (assoc2d_split.cu)
     long long n_pts_total = 0;
@@ -120,7 +120,7 @@ void free_pack(stl_ctx *c) {
     DevPack &p = c->pk;
     dfree(p.kf); dfree(p.px); dfree(p.py); dfree(p.pz); dfree(p.orig); dfree(p.node_lo); dfree(p.node_hi); dfree(p.adj); dfree(p.adj_cov);
     dfree(p.pl_rec); dfree(p.pl_m);
-    dfree(p.bitmap); dfree(p.grid_start); dfree(p.grid_kp); dfree(p.kp_xy); dfree(p.kp_xyd); dfree(p.kp_mp); dfree(p.Tcw);
+    dfree(p.k1tab); dfree(p.bitmap); dfree(p.grid_start); dfree(p.grid_kp); dfree(p.kp_xy); dfree(p.kp_xyd); dfree(p.kp_mp); dfree(p.Tcw);
     dfree(p.relpose); dfree(p.covis_valid); dfree(p.covis_uv); dfree(p.he_Tc); dfree(p.he_Tl);
     p = DevPack();
     c->has_pack = false;
@@ -128,7 +128,7 @@ void free_pack(stl_ctx *c) {
 void free_work(stl_ctx *c) {
     DevWork &w = c->wk;
     dfree(w.cand); dfree(w.corr_kp); dfree(w.corr_pt); dfree(w.corr_sp); dfree(w.q_corr); dfree(w.q_kpsp); dfree(w.n_corr); dfree(w.n_q);
-    dfree(w.k1_match); dfree(w.k1_surv); dfree(w.k1_cnt); dfree(w.k1_best_d2); dfree(w.k1_best_key);
+    dfree(w.k1_ticket); dfree(w.k1_rec); dfree(w.k1_match); dfree(w.k1_surv); dfree(w.k1_cnt); dfree(w.k1_best_d2); dfree(w.k1_best_key);
     dfree(w.frame); dfree(w.align); dfree(w.nn_pos); dfree(w.nn_g2); dfree(w.nb); dfree(w.nbx); dfree(w.nb_m); dfree(w.nb_last); dfree(w.dbg_nn); dfree(w.dbg_m); dfree(w.dbg_plane); dfree(w.dbg_dist); dfree(w.dbg_knn); dfree(w.dbg_stats);
     dfree(w.overflow); dfree(w.k1_clk);
     w = DevWork();
@@ -211,7 +211,7 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
     if (ctx->wk_cap == 0) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        const size_t per_cand = (size_t)pk.n_kp_total * 24 + (size_t)pk.n_mp_total * (20 * kMaxK + 16) + (size_t)pk.n_kf * (sizeof(FrameRec) + 4 * sizeof(AlignRec) + 24 + sizeof(ulonglong2) * kK1MatchCap + 4 * kK1SurvCap) + (size_t)pk.n_kp_total * 16 + sizeof(DevCand);
+        const size_t per_cand = (size_t)pk.n_kp_total * 24 + (size_t)pk.n_mp_total * (20 * kMaxK + 16) + (size_t)pk.n_kf * (sizeof(FrameRec) + 4 * sizeof(AlignRec) + 24 + (ctx->k1_mono ? 0 : sizeof(ulonglong2) * kK1MatchCap + 4 * kK1SurvCap)) + (size_t)pk.n_kp_total * 16 + sizeof(DevCand);
         size_t budget = std::min<size_t>((size_t)12 << 30, free_b / 4);
         int cap = (int)std::max<size_t>(1, std::min<size_t>(budget / std::max<size_t>(per_cand, 1), 256));
         if (const char *e = getenv("STL_MAX_CHUNK")) cap = std::max(1, std::min(cap, atoi(e)));  // tests: force the multi-chunk path
@@ -231,8 +231,16 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
             A_(w.cand, sizeof(DevCand) * cap);
             A_(w.corr_kp, 4 * nk); A_(w.corr_pt, 4 * nk); A_(w.corr_sp, 4 * nk); A_(w.q_corr, 4 * nk); A_(w.q_kpsp, 8 * nk);
             A_(w.n_corr, 4 * nf); A_(w.n_q, 4 * nf);
-            A_(w.k1_match, sizeof(ulonglong2) * kK1MatchCap * nf);
-            A_(w.k1_surv, 4 * (size_t)kK1SurvCap * nf); A_(w.k1_cnt, 16 * nf); A_(w.k1_best_d2, 8 * nk); A_(w.k1_best_key, 8 * nk);
+            if (ctx->k1_mono) {  // persistent K1: scratch per resident CTA, not per unit
+                w.k1_slots = 2 * std::max(ctx->n_sm, 1);
+                A_(w.k1_match, sizeof(ulonglong2) * kK1MatchCap * (size_t)w.k1_slots);
+                A_(w.k1_rec, sizeof(float4) * kK1SurvCap * (size_t)w.k1_slots);
+                A_(w.k1_ticket, 8);
+                e = cudaMemsetAsync(w.k1_ticket, 0, 8, ctx->last_stream); if (e != cudaSuccess) return e;
+            } else {
+                A_(w.k1_match, sizeof(ulonglong2) * kK1MatchCap * nf);
+                A_(w.k1_surv, 4 * (size_t)kK1SurvCap * nf); A_(w.k1_cnt, 16 * nf); A_(w.k1_best_d2, 8 * nk); A_(w.k1_best_key, 8 * nk);
+            }
             A_(w.frame, sizeof(FrameRec) * nf); A_(w.align, sizeof(AlignRec) * nf * w.sub);
             A_(w.nn_pos, 4 * nm); A_(w.nn_g2, 4 * nm); A_(w.nb, 4 * nm * kMaxK); A_(w.nbx, sizeof(float4) * nm * kMaxK); A_(w.nb_m, 4 * nm); A_(w.nb_last, 8 * nm);
             w.nbx_stride = (long long)nm;
@@ -297,7 +305,7 @@ stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, c
         const int nb = std::min(Bc, B - c0);
         CK(cudaMemcpyAsync(ctx->wk.cand, ctx->h_cand + c0, sizeof(DevCand) * nb, cudaMemcpyHostToDevice, st));
         { StageTimer t(ctx, STL_STAGE_ASSOC2D, st);
-          if (ctx->k1_mono) CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_smem, st));
+          if (ctx->k1_mono) CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_smem, ctx->max_kp, ctx->max_tab, st));
           else CK(launch_assoc2d_split(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_split_smem, 0, st)); }
         ctx->launches += ctx->k1_mono ? 0 : 2;
         { StageTimer t(ctx, STL_STAGE_KNN3D, st); CK(launch_align3d(ctx->pk, ctx->wk, ctx->dpr, nb, debug ? 1 : 0, st)); }
@@ -358,7 +366,7 @@ stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st) 
         CK(cudaEventRecord(ctx->h2d_done, st));
         // 2-D association at x0 (FindProjectCorrespondences, iba_local.cpp:191): K1 without the cost terms
         { StageTimer t(ctx, STL_STAGE_ASSOC2D, st);
-          if (ctx->k1_mono) CK(launch_assoc2d(pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, st, 0));
+          if (ctx->k1_mono) CK(launch_assoc2d(pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, ctx->max_kp, ctx->max_tab, st, 0));
           else CK(launch_assoc2d_split(pk, ctx->wk, ctx->dpr, 1, ctx->k1_split_smem, 0, st, 0)); }
         ctx->launches += ctx->k1_mono ? 1 : 3;
         ctx->wk_x.assign(x0, x0 + 7);
@@ -489,8 +497,8 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     std::vector<DevKf> hk_new;
     std::vector<DevKf> &hk = hk_new;
     hk.assign(F, DevKf());
-    long long pt = 0, nodes = 0, bmw = 0, gcells = 0, mp_total = 0;
-    int max_kp = 0, max_bm = 0;
+    long long pt = 0, nodes = 0, bmw = 0, gcells = 0, mp_total = 0, tab_total = 0;
+    int max_kp = 0, max_bm = 0, max_tab = 0;
     for (int f = 0; f < F; ++f) {
         DevKf &K = hk[f];
         const long long n = p->scan_offset[f + 1] - p->scan_offset[f];
@@ -516,6 +524,11 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
         K.gw = std::max(1, (K.W + kGridCell - 1) / kGridCell);
         K.gh = std::max(1, (K.H + kGridCell - 1) / kGridCell);
         K.grid_off = gcells; gcells += (long long)K.gw * K.gh + 1;
+        {
+            const K1Tab tl = k1tab_layout(K.n_kp, K.bm_wpr * K.bm_rows, K.gw * K.gh);
+            K.tab_off = tab_total; K.tab_bytes = tl.bytes; tab_total += tl.bytes;
+            max_tab = std::max(max_tab, tl.bytes);
+        }
         K.he_valid = p->he_valid[f] ? 1 : 0;
         K.mp_off = mp_total;
         K.n_mp = 0;
@@ -529,7 +542,7 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     int max_cells = 0, max_groups = 0;
     for (int f = 0; f < F; ++f) { max_cells = std::max(max_cells, hk[f].gw * hk[f].gh); max_groups = std::max(max_groups, hk[f].n_pad / 128); }
     if (max_kp > 65535) return fail(ctx, STL_ERR_CAPACITY, "more than 65535 keypoints in a keyframe");
-    const size_t k1_smem_new = assoc2d_smem_bytes(max_kp, max_bm, max_cells, max_groups);
+    const size_t k1_smem_new = assoc2d_smem_bytes(max_kp, max_tab, max_groups);
     int smem_optin = 0;
     CK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     if (k1_smem_new > (size_t)smem_optin)
@@ -545,7 +558,9 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     lm_free(ctx->lm);
     ctx->h_kf.swap(hk_new);
     std::vector<DevKf> &hk2 = ctx->h_kf;
-    ctx->max_kp = max_kp; ctx->max_bm_words = max_bm; ctx->k1_smem = k1_smem_new; ctx->k1_split_smem = k1_split_new;
+    ctx->max_kp = max_kp; ctx->max_bm_words = max_bm; ctx->max_tab = max_tab;
+    CK(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+    ctx->k1_smem = k1_smem_new; ctx->k1_split_smem = k1_split_new;
     ctx->k1_mono = getenv("STL_K1_SPLIT") == nullptr;
     cudaStream_t st = acquire_stream(ctx, nullptr);
     struct Scope {  // events and the raw-scan scratch are released on every exit path
@@ -618,6 +633,26 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
         for (int k = 0; k < K.n_kp; ++k) gk[cur[cell[k]]++] = (uint32_t)k;
     }
 
+    // ---- K1 table blobs: the same tables, per keyframe, contiguous in the order K1 keeps them in shared memory
+    std::vector<uint8_t> k1tab((size_t)std::max<long long>(tab_total, 16), 0);
+#pragma omp parallel for schedule(static)
+    for (int f = 0; f < F; ++f) {
+        const DevKf &K = hk2[f];
+        const int ncell = K.gw * K.gh, bmwords = K.bm_wpr * K.bm_rows;
+        const K1Tab tl = k1tab_layout(K.n_kp, bmwords, ncell);
+        uint8_t *dst = k1tab.data() + K.tab_off;
+        memcpy(dst, kp_host + K.kp_off * 2, 8 * (size_t)K.n_kp);
+        memcpy(dst + tl.off_bm, bitmap.data() + K.bm_off, 4 * (size_t)bmwords);
+        uint16_t *gs16 = reinterpret_cast<uint16_t *>(dst + tl.off_gs), *gk16 = reinterpret_cast<uint16_t *>(dst + tl.off_gk);
+        uint32_t *mpm = reinterpret_cast<uint32_t *>(dst + tl.off_mp);
+        for (int i = 0; i <= ncell; ++i) gs16[i] = (uint16_t)gstart[K.grid_off + i];
+        for (int k = 0; k < K.n_kp; ++k) {
+            gk16[k] = (uint16_t)gkp[K.kp_off + k];
+            const float m0 = p->kp_mappoint[(K.kp_off + k) * 3];
+            if (m0 == m0) mpm[k >> 5] |= 1u << (k & 31);
+        }
+    }
+
     // ---- device allocation + small uploads
     DevPack &pk = ctx->pk;
     pk.n_kf = F; pk.n_covis = C; pk.n_pad_total = pt; pk.n_nodes_total = nodes; pk.n_kp_total = NK; pk.n_mp_total = mp_total;
@@ -627,6 +662,8 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     CK(cudaMalloc(&pk.px, 4 * npt)); CK(cudaMalloc(&pk.py, 4 * npt)); CK(cudaMalloc(&pk.pz, 4 * npt)); CK(cudaMalloc(&pk.orig, 4 * npt));
     CK(cudaMalloc(&pk.node_lo, sizeof(float4) * nodes)); CK(cudaMalloc(&pk.node_hi, sizeof(float4) * nodes));
     if (ctx->adj_r2 > 0.f) { CK(cudaMalloc(&pk.adj, sizeof(uint16_t) * 32 * (size_t)nodes)); CK(cudaMalloc(&pk.adj_cov, sizeof(float) * (size_t)nodes)); }
+    CK(cudaMalloc(&pk.k1tab, k1tab.size()));
+    CK(cudaMemcpyAsync(pk.k1tab, k1tab.data(), k1tab.size(), cudaMemcpyHostToDevice, st));
     CK(cudaMalloc(&pk.bitmap, 4 * (size_t)bmw)); CK(cudaMalloc(&pk.grid_start, 4 * (size_t)gcells)); CK(cudaMalloc(&pk.grid_kp, 4 * nkk));
     CK(cudaMalloc(&pk.kp_xy, sizeof(float2) * nkk)); CK(cudaMalloc(&pk.kp_mp, 12 * nkk));
     CK(cudaMalloc(&pk.Tcw, 48 * (size_t)F)); CK(cudaMalloc(&pk.relpose, 48 * (size_t)std::max(F * C, 1)));
@@ -840,7 +877,7 @@ stl_status_t stl_debug_frame(stl_ctx_t *ctx, int32_t b, int32_t kf, double out[1
         cudaMemcpy(h.data(), ctx->wk.k1_clk, 64 * (size_t)ctx->pk.n_kf, cudaMemcpyDeviceToHost);
         double a[8] = {0};
         for (int f = 0; f < ctx->pk.n_kf; ++f) for (int i = 0; i < 8; ++i) a[i] += (double)h[(size_t)f * 8 + i] / ctx->pk.n_kf;
-        fprintf(stderr, "[stl] K1 mean clocks/unit: prologue %.0f | stream %.0f | exact-1 %.0f | exact-2 %.0f | compact %.0f | covis %.0f | epilogue %.0f | tie-pass(thread 0) %.0f\n", a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+        fprintf(stderr, "[stl] K1 mean clocks/unit: prologue %.0f | cells + table wait %.0f | stream %.0f | exact-1 %.0f | tie pass %.0f | corrset + covisible term %.0f | reduction %.0f | epilogue %.0f\n", a[7], a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
     }
     if (getenv("STL_DEBUG_STATS")) {
         unsigned long long st[8];

@@ -29,8 +29,9 @@ struct DevKf {
     long long bm_off;
     long long grid_off;
     long long mp_off;  // first slot of this keyframe in the map-point-indexed query lists
+    long long tab_off; // byte offset of this keyframe's K1 table blob in DevPack::k1tab (16-byte aligned)
     int n_mp;          // keypoints that carry a map point (upper bound of the 3-D queries)
-    int pad0_;
+    int tab_bytes;     // size of the blob (multiple of 16)
     int n_pts, n_pad;
     int n0, n1, n2;
     int n_kp;
@@ -42,6 +43,21 @@ struct DevKf {
     float pmax;  // max |coordinate| of the scan (fast-path error bound)
     float pad_;
 };
+
+// K1 table blob of one keyframe: everything the association kernel stages in shared memory, contiguous and 16-byte
+// granular so that ONE bulk copy (cp.async.bulk, completion on an mbarrier) brings it in:
+//   [float2 kp[n_kp]] [uint32 bitmap[bm_words]] [uint16 grid_start[ncell + 1]] [uint16 grid_kp[n_kp]] [uint32 has_mp[(n_kp + 31) / 32]]
+struct K1Tab { int off_bm, off_gs, off_gk, off_mp, bytes; };
+__host__ __device__ inline int k1_a16(int x) { return (x + 15) & ~15; }
+__host__ __device__ inline K1Tab k1tab_layout(int n_kp, int bm_words, int ncell) {
+    K1Tab t;
+    t.off_bm = k1_a16(8 * n_kp);
+    t.off_gs = t.off_bm + k1_a16(4 * bm_words);
+    t.off_gk = t.off_gs + k1_a16(2 * (ncell + 1));
+    t.off_mp = t.off_gk + k1_a16(2 * n_kp);
+    t.bytes = t.off_mp + k1_a16(4 * ((n_kp + 31) / 32));
+    return t;
+}
 
 struct DevCand {
     double R[9], t[3];    // Tcl  (Sim3Exp, computed on the host in libm)

@@ -21,6 +21,7 @@ struct DevPack {
     float *adj_cov = nullptr;        // [n_nodes_total] squared distance the row covers (+inf: all of adj_r; -1: no row)
     PlaneRec *pl_rec = nullptr;      // [n_pad_total] plane index (null unless params.plane_index)
     int *pl_m = nullptr;             // [n_pad_total] neighbours kept; negative (-(m+1)) when the gates failed
+    uint8_t *k1tab = nullptr;        // per-keyframe K1 table blobs (common.cuh: K1Tab), DevKf::tab_off / tab_bytes
     uint32_t *bitmap = nullptr;
     uint32_t *grid_start = nullptr;  // per keyframe gw*gh+1 entries
     uint32_t *grid_kp = nullptr;     // [n_kp_total] keypoint ids sorted by cell (local ids)
@@ -64,7 +65,12 @@ struct DevWork {
     double *dbg_dist = nullptr;
     uint32_t *dbg_knn = nullptr;  // [n_kp_total][32]
     unsigned long long *dbg_stats = nullptr;  // [8] traversal statistics (debug runs)
-    ulonglong2 *k1_match = nullptr;  // [Bc][n_kf][8192] (d2 bits, keypoint<<32 | position) recorded by K1's exact pass
+    // K1 (assoc2d.cu) is persistent: k1_slots CTAs draw (candidate, keyframe) units from k1_ticket; the survivor records and
+    // the match list are scratch of the CTA (slot = blockIdx.x), small enough to stay in L2
+    int k1_slots = 0;
+    int *k1_ticket = nullptr;        // [2] next chunk of units, CTAs that have left (the last one re-arms both)
+    float4 *k1_rec = nullptr;        // [k1_slots][kK1SurvCap] (x, y, z, sorted position) of the points that passed the pre-cull
+    ulonglong2 *k1_match = nullptr;  // [k1_slots][8192] (one-kernel K1) or [Bc][n_kf][8192] (three-kernel K1): matches of the exact pass
     // three-kernel K1 (assoc2d_split.cu)
     uint32_t *k1_surv = nullptr;              // [Bc][n_kf][kK1SurvCap] sorted positions that passed the pre-cull
     int *k1_cnt = nullptr;                    // [Bc][n_kf][4] survivors, matches, overflow flag, pad
@@ -107,11 +113,12 @@ constexpr int kK1SurvCap = 4096;   // survivors of the float32 pre-cull a (candi
 constexpr int kK1MatchCap = 8192;  // (keypoint, point) matches a unit may record between the exact pass and the tie pass
 
 // ---- K1 (assoc2d.cu: one kernel; assoc2d_split.cu: stream / exact / correspondence kernels, the default) ----------
-size_t assoc2d_smem_bytes(int max_kp, int max_bm_words, int max_cells, int max_groups);
+size_t assoc2d_smem_bytes(int max_kp, int max_tab_bytes, int max_groups);
 cudaError_t assoc2d_configure(size_t smem);
 // with_terms = 0: correspondences only (the association pass of the LM path needs neither the covisible
 // re-projection term nor the hand-eye term)
-cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, cudaStream_t st, int with_terms = 1);
+cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, int max_kp, int max_tab_bytes,
+                           cudaStream_t st, int with_terms = 1);
 size_t assoc2d_split_smem_bytes(int max_bm_words, int max_groups);
 cudaError_t assoc2d_split_configure(size_t smem);
 cudaError_t launch_assoc2d_split(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, int max_pts, cudaStream_t st,
