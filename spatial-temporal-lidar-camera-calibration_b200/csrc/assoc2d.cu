@@ -43,6 +43,8 @@ struct Smem {  // fixed part; dynamic arrays follow
     int n_surv, overflow, n_groups, n_match, next_group;
     // persistent-loop state (written by thread 0 between two barriers, read by everybody)
     int unit, u_end, new_tab, cur_f;
+    int next_ticket, have_next;  // drawn ahead by a helper thread while the current unit runs
+    int n_cells;                 // visible level-1 cells of the current unit
     unsigned covis_mask;  // bit j: covisible slot j of this keyframe is valid
     double he_val;
     int warp_cnt[16], warp_q[16];
@@ -146,6 +148,7 @@ struct Tables {
     const unsigned short *gstart, *gkp;      // [gw*gh+1], [n_kp]
     const uint32_t *has_mp;                  // [(n_kp+31)/32]
     unsigned short *groups;                  // [n_pad/128]
+    unsigned short *cells;                   // [n_pad/1024] visible level-1 cells
 };
 
 // A correspondence key: (original index << 32) | (sorted position << 12) | survivor slot.  Original indices are unique
@@ -193,7 +196,7 @@ __device__ __forceinline__ void exact_point(const DevPack &pk, const DevKf &K, c
 // ticket; consecutive units of a chunk share the keyframe when B > 1, so the table blob stays in shared memory.
 __global__ void __launch_bounds__(kThreads, 2)
 k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, const int with_terms, const int n_units, const int chunk,
-          const int max_kp, const int max_tab) {
+          const int max_kp, const int max_tab, const int max_groups) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     unsigned char *const tab = smem_raw + ((sizeof(Smem) + 15) & ~size_t(15));
@@ -202,12 +205,13 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
         unsigned char *q = tab + max_tab;
         T.best_d2 = reinterpret_cast<unsigned long long *>(q); q += 8 * (size_t)max_kp;
         T.best_key = reinterpret_cast<unsigned long long *>(q); q += 8 * (size_t)max_kp;
-        T.groups = reinterpret_cast<unsigned short *>(q);
+        T.groups = reinterpret_cast<unsigned short *>(q); q += 2 * (size_t)max_groups;
+        T.cells = reinterpret_cast<unsigned short *>(q);
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         mbar_init(&S.mbar, 1);
-        S.unit = -1; S.u_end = 0; S.cur_f = -1; S.new_tab = 0;
+        S.unit = -1; S.u_end = 0; S.cur_f = -1; S.new_tab = 0; S.have_next = 0;
     }
     uint32_t tab_phase = 0;
     for (;;) {
@@ -219,7 +223,8 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
     if (tid == 0) {
         int u = S.unit + 1;
         if (S.unit < 0 || u >= S.u_end) {
-            const long long t0 = (long long)atomicAdd(wk.k1_ticket, 1) * chunk;
+            const long long t0 = (long long)(S.have_next ? S.next_ticket : atomicAdd(wk.k1_ticket, 1)) * chunk;
+            S.have_next = 0;
             if (t0 >= n_units) {  // every CTA draws exactly one failing ticket; the last one to leave re-arms the counters
                 if (atomicAdd(wk.k1_ticket + 1, 1) == (int)gridDim.x - 1) { wk.k1_ticket[0] = 0; wk.k1_ticket[1] = 0; __threadfence(); }
                 u = -1;
@@ -286,7 +291,7 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
                 S.thr[1] = -mslab_u; S.thr[2] = -mslab_u;
                 S.thr[3] = -mslab_v; S.thr[4] = -mslab_v;
             }
-            S.n_surv = 0; S.overflow = 0; S.n_groups = 0; S.n_match = 0; S.next_group = 0; S.he_val = 0.0;
+            S.n_surv = 0; S.overflow = 0; S.n_groups = 0; S.n_match = 0; S.next_group = 0; S.he_val = 0.0; S.n_cells = 0;
             S.base_corr = 0; S.base_q = 0;
             unsigned cm = 0;
             for (int j = 0; j < pk.n_covis; ++j) cm |= (pk.covis_valid[f * pk.n_covis + j] ? 1u : 0u) << j;
@@ -315,13 +320,30 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
     const bool timing = wk.k1_clk != nullptr && tid == 0;
     if (timing) clk[0] = clock64();
 
-    // ---- phase A1: which 128-point groups can hold a visible point?  One warp per level-1 cell
-    // (1024 points): test the cell, then its 32 leaf boxes, one per lane.
+    // the ticket of the NEXT chunk is drawn now, by a thread of another warp, so that its round trip to L2 is off the
+    // critical path of the next prologue (only when this unit ends the chunk in hand; a CTA stops at its first failing ticket)
+    if (tid == 32 && unit + 1 >= S.u_end) { S.next_ticket = atomicAdd(wk.k1_ticket, 1); S.have_next = 1; }
+
+    // ---- phase A1: which 128-point groups can hold a visible point?  Level-1 cells (1024 points) one per THREAD first,
+    // then one warp per visible cell tests its 32 leaf boxes, one per lane: two dependent round trips to the boxes in all.
     {
         const float4 *nlo = pk.node_lo + K.node_off, *nhi = pk.node_hi + K.node_off;
         const int n_l1 = (K.n_pad + 1023) >> 10;
-        for (int node = warp; node < n_l1; node += kThreads / 32) {
-            if (!box_visible(S, nlo[K.n0 + node], nhi[K.n0 + node])) continue;
+        for (int n0 = 0; n0 < n_l1; n0 += kThreads) {
+            const int node = n0 + tid;
+            const bool vis = node < n_l1 && box_visible(S, nlo[K.n0 + node], nhi[K.n0 + node]);
+            const unsigned vm = __ballot_sync(0xffffffffu, vis);
+            if (vm) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&S.n_cells, __popc(vm));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (vis) T.cells[base + __popc(vm & ((1u << lane) - 1))] = (unsigned short)node;
+            }
+        }
+        __syncthreads();
+        const int nc = S.n_cells;
+        for (int ci = warp; ci < nc; ci += kThreads / 32) {
+            const int node = T.cells[ci];
             const bool lv = box_visible(S, nlo[node * 32 + lane], nhi[node * 32 + lane]);
             const unsigned lmask = __ballot_sync(0xffffffffu, lv);
             // lane g < 8 owns group g of the cell (leaves 4g .. 4g+3)
@@ -483,7 +505,8 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
     // ---- phase D: corrset in keypoint order, query list = correspondences with a map point, and the 3-D/2-D term of
     // every correspondence (iba_global.cpp:291-328).  One block scan: thread t owns the consecutive keypoints
     // [t*per, (t+1)*per); nothing here gathers from HBM (keys and map-point flags in shared memory, point
-    // coordinates from the CTA's records, covisible pixels prefetched into L2 by the prologue).
+    // coordinates from the CTA's records, covisible pixels prefetched into L2 by the prologue); the (correspondence,
+    // covisible keyframe) pairs are dealt evenly to the threads.
     const unsigned long long *best_key = T.best_key;
     const long long out_base = (long long)b * pk.n_kp_total + K.kp_off;
     double s2d = 0, v2d = 0, c2d = 0;
@@ -513,48 +536,52 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
         ncorr = tc; nq = tq;
         kept = ncorr >= pr.num_min_corr;  // iba_global.cpp:203
         const bool terms = kept && with_terms && pk.n_covis > 0;
-        const int C = pk.n_covis;
-        const unsigned cmask = S.covis_mask;
-        const double fx = K.fx, fy = K.fy, cx = K.cx, cy = K.cy, W = K.W, H = K.H;
+        // (keypoint, position, slot) of correspondence i, for the pair loop below; the per-keypoint minima are dead by now
+        unsigned long long *clist = T.best_d2;  // (last read in the tie pass, two barriers ago)
         for (int k = k_lo; k < k_hi; ++k) {
             const unsigned long long key = best_key[k];
             if (key == kNoKey) continue;
             const uint32_t low = (uint32_t)(key & 0xffffffffu), sp = low >> 12;
-            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-            float2 uv = make_float2(0.f, 0.f);
-            const float2 *uvk = pk.covis_uv + (K.kp_off + k) * C;
-            if (terms) {  // issued before the stores below: both are L2 hits
-                r = ovf ? make_float4(gx[sp], gy[sp], gz[sp], 0.f) : rec[low & 0xfffu];
-                uv = uvk[0];
-            }
             wk.corr_kp[out_base + pc] = (uint32_t)k;
             wk.corr_pt[out_base + pc] = (uint32_t)(key >> 32);
             wk.corr_sp[out_base + pc] = sp;
+            clist[pc] = ((unsigned long long)k << 32) | low;
             if ((T.has_mp[k >> 5] >> (k & 31)) & 1u) {
                 wk.q_corr[out_base + pq] = (uint32_t)pc;
                 wk.q_kpsp[out_base + pq] = make_uint2((uint32_t)k, sp);
                 ++pq;
             }
             ++pc;
-            if (!terms) continue;
-            double p0x, p0y, p0z;
-            xform(c.R, c.t, (double)r.x, (double)r.y, (double)r.z, p0x, p0y, p0z);
+        }
+        if (terms) {
+            // 3-D/2-D term over (covisible keyframe) x (correspondence), the pairs dealt evenly to the threads
+            __syncthreads();
+            const int C = pk.n_covis;
+            const unsigned cmask = S.covis_mask;
+            const double fx = K.fx, fy = K.fy, cx = K.cx, cy = K.cy, W = K.W, H = K.H;
             for (int j = 0; j < C; ++j) {
-                const float2 uvj = uv;
-                if (j + 1 < C) uv = uvk[j + 1];  // the next pixel is on its way while this pair is evaluated
                 if (!((cmask >> j) & 1u)) continue;
-                if (isnan(uvj.x)) continue;
                 const float *rp = pk.relpose + ((long long)f * C + j) * 12;
-                const double p1x = dadd(dot3e((double)rp[0], (double)rp[1], (double)rp[2], p0x, p0y, p0z), dmul((double)rp[3], c.s));
-                const double p1y = dadd(dot3e((double)rp[4], (double)rp[5], (double)rp[6], p0x, p0y, p0z), dmul((double)rp[7], c.s));
-                const double p1z = dadd(dot3e((double)rp[8], (double)rp[9], (double)rp[10], p0x, p0y, p0z), dmul((double)rp[11], c.s));
-                const double ou = dadd(ddiv(dmul(fx, p1x), p1z), cx);
-                const double ov = dadd(ddiv(dmul(fy, p1y), p1z), cy);
-                if (!(ou >= 0 && ou < W && ov >= 0 && ov < H)) continue;
-                const double du = dsub(ou, (double)uvj.x), dv = dsub(ov, (double)uvj.y);
-                const double dist = sqrt(dadd(dmul(du, du), dmul(dv, dv)));
-                if (dist < pr.thr2d) { s2d += dist; v2d += 1.0; }
-                c2d += 1.0;
+                const float2 *uvj = pk.covis_uv + K.kp_off * C + j;
+                for (int i = tid; i < ncorr; i += kThreads) {
+                    const unsigned long long e = clist[i];
+                    const uint32_t k = (uint32_t)(e >> 32), low = (uint32_t)(e & 0xffffffffu);
+                    const float2 uv = uvj[(long long)k * C];
+                    if (isnan(uv.x)) continue;
+                    const float4 r = ovf ? make_float4(gx[low >> 12], gy[low >> 12], gz[low >> 12], 0.f) : rec[low & 0xfffu];
+                    double p0x, p0y, p0z;
+                    xform(c.R, c.t, (double)r.x, (double)r.y, (double)r.z, p0x, p0y, p0z);
+                    const double p1x = dadd(dot3e((double)rp[0], (double)rp[1], (double)rp[2], p0x, p0y, p0z), dmul((double)rp[3], c.s));
+                    const double p1y = dadd(dot3e((double)rp[4], (double)rp[5], (double)rp[6], p0x, p0y, p0z), dmul((double)rp[7], c.s));
+                    const double p1z = dadd(dot3e((double)rp[8], (double)rp[9], (double)rp[10], p0x, p0y, p0z), dmul((double)rp[11], c.s));
+                    const double ou = dadd(ddiv(dmul(fx, p1x), p1z), cx);
+                    const double ov = dadd(ddiv(dmul(fy, p1y), p1z), cy);
+                    if (!(ou >= 0 && ou < W && ov >= 0 && ov < H)) continue;
+                    const double du = dsub(ou, (double)uv.x), dv = dsub(ov, (double)uv.y);
+                    const double dist = sqrt(dadd(dmul(du, du), dmul(dv, dv)));
+                    if (dist < pr.thr2d) { s2d += dist; v2d += 1.0; }
+                    c2d += 1.0;
+                }
             }
         }
     }
@@ -593,7 +620,7 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
 }  // namespace
 
 size_t assoc2d_smem_bytes(int max_kp, int max_tab_bytes, int max_groups) {
-    return ((sizeof(Smem) + 15) & ~size_t(15)) + (size_t)max_tab_bytes + (size_t)max_kp * 16 + 2 * (size_t)max_groups + 16;
+    return ((sizeof(Smem) + 15) & ~size_t(15)) + (size_t)max_tab_bytes + (size_t)max_kp * 16 + 2 * (size_t)max_groups + 2 * (size_t)(max_groups / 8 + 1) + 16;
 }
 
 // The opt-in dynamic shared-memory limit is a per-function, per-device attribute shared by every
@@ -613,7 +640,7 @@ cudaError_t assoc2d_configure(size_t smem) {
 }
 
 cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, int max_kp, int max_tab_bytes,
-                           cudaStream_t st, int with_terms) {
+                           int max_groups, cudaStream_t st, int with_terms) {
     if (B <= 0 || pk.n_kf <= 0) return cudaSuccess;
     const long long n_units = (long long)pk.n_kf * B;
     if (n_units > 0x7fffffffll || wk.k1_slots <= 0) return cudaErrorInvalidValue;
@@ -621,7 +648,7 @@ cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams
     const int chunk = B >= 64 ? 8 : (B >= 16 ? 4 : (B >= 4 ? 2 : 1));
     const long long n_chunks = (n_units + chunk - 1) / chunk;
     const unsigned grid = (unsigned)std::min<long long>(n_chunks, wk.k1_slots);
-    k_assoc2d<<<grid, kThreads, smem, st>>>(pk, wk, pr, B, with_terms, (int)n_units, chunk, max_kp, max_tab_bytes);
+    k_assoc2d<<<grid, kThreads, smem, st>>>(pk, wk, pr, B, with_terms, (int)n_units, chunk, max_kp, max_tab_bytes, max_groups);
     return cudaGetLastError();
 }
 

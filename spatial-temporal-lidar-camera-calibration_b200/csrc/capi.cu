@@ -37,7 +37,7 @@ struct stl_ctx {
     float adj_r2 = 0.f;  // squared radius of the leaf adjacency lists, rounded up (0: none)
     DevPack pk;
     std::vector<DevKf> h_kf;
-    int max_kp = 0, max_bm_words = 0, max_tab = 0, n_sm = 0;
+    int max_kp = 0, max_bm_words = 0, max_tab = 0, max_groups = 0, n_sm = 0;
     size_t k1_smem = 0, k1_split_smem = 0;
     bool k1_mono = true;   // the one-kernel K1 (assoc2d.cu); STL_K1_SPLIT=1 selects the three-kernel form (assoc2d_split.cu)
     long long n_pts_total = 0;
@@ -305,7 +305,7 @@ stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, c
         const int nb = std::min(Bc, B - c0);
         CK(cudaMemcpyAsync(ctx->wk.cand, ctx->h_cand + c0, sizeof(DevCand) * nb, cudaMemcpyHostToDevice, st));
         { StageTimer t(ctx, STL_STAGE_ASSOC2D, st);
-          if (ctx->k1_mono) CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_smem, ctx->max_kp, ctx->max_tab, st));
+          if (ctx->k1_mono) CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_smem, ctx->max_kp, ctx->max_tab, ctx->max_groups, st));
           else CK(launch_assoc2d_split(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_split_smem, 0, st)); }
         ctx->launches += ctx->k1_mono ? 0 : 2;
         { StageTimer t(ctx, STL_STAGE_KNN3D, st); CK(launch_align3d(ctx->pk, ctx->wk, ctx->dpr, nb, debug ? 1 : 0, st)); }
@@ -366,7 +366,7 @@ stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st) 
         CK(cudaEventRecord(ctx->h2d_done, st));
         // 2-D association at x0 (FindProjectCorrespondences, iba_local.cpp:191): K1 without the cost terms
         { StageTimer t(ctx, STL_STAGE_ASSOC2D, st);
-          if (ctx->k1_mono) CK(launch_assoc2d(pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, ctx->max_kp, ctx->max_tab, st, 0));
+          if (ctx->k1_mono) CK(launch_assoc2d(pk, ctx->wk, ctx->dpr, 1, ctx->k1_smem, ctx->max_kp, ctx->max_tab, ctx->max_groups, st, 0));
           else CK(launch_assoc2d_split(pk, ctx->wk, ctx->dpr, 1, ctx->k1_split_smem, 0, st, 0)); }
         ctx->launches += ctx->k1_mono ? 1 : 3;
         ctx->wk_x.assign(x0, x0 + 7);
@@ -558,7 +558,7 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
     lm_free(ctx->lm);
     ctx->h_kf.swap(hk_new);
     std::vector<DevKf> &hk2 = ctx->h_kf;
-    ctx->max_kp = max_kp; ctx->max_bm_words = max_bm; ctx->max_tab = max_tab;
+    ctx->max_kp = max_kp; ctx->max_bm_words = max_bm; ctx->max_tab = max_tab; ctx->max_groups = max_groups;
     CK(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
     ctx->k1_smem = k1_smem_new; ctx->k1_split_smem = k1_split_new;
     ctx->k1_mono = getenv("STL_K1_SPLIT") == nullptr;

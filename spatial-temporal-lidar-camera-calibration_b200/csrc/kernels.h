@@ -118,7 +118,7 @@ cudaError_t assoc2d_configure(size_t smem);
 // with_terms = 0: correspondences only (the association pass of the LM path needs neither the covisible
 // re-projection term nor the hand-eye term)
 cudaError_t launch_assoc2d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, int max_kp, int max_tab_bytes,
-                           cudaStream_t st, int with_terms = 1);
+                           int max_groups, cudaStream_t st, int with_terms = 1);
 size_t assoc2d_split_smem_bytes(int max_bm_words, int max_groups);
 cudaError_t assoc2d_split_configure(size_t smem);
 cudaError_t launch_assoc2d_split(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, size_t smem, int max_pts, cudaStream_t st,
