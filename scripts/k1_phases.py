@@ -22,8 +22,10 @@ for ln in out.splitlines():
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
         lines.append(cur)
-PH = [("prologue", 154, 237), ("cells (A1)", 238, 259), ("stream (A2)", 260, 343), ("exact-1", 344, 351), ("tie pass", 352, 366),
-      ("compaction", 367, 410), ("covisible", 411, 443), ("epilogue", 444, 480)]
+# line ranges of assoc2d.cu (update when the file moves): device helpers are attributed to the phase that inlines them
+PH = [("prologue (thread 0)", 197, 302), ("unit setup", 303, 326), ("cells (A1) + table wait", 327, 366), ("cells (A1) + table wait", 125, 140),
+      ("stream (A2)", 367, 451), ("exact-1", 452, 470), ("exact-1", 87, 100), ("exact-1", 156, 193), ("tie pass", 471, 504),
+      ("corrset", 505, 555), ("covisible pairs", 556, 588), ("reduction + epilogue", 589, 618), ("hand-eye", 104, 120)]
 def phase(l):
     if l is None: return "?"
     for n, a, b in PH:

@@ -293,9 +293,7 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
             }
             S.n_surv = 0; S.overflow = 0; S.n_groups = 0; S.n_match = 0; S.next_group = 0; S.he_val = 0.0; S.n_cells = 0;
             S.base_corr = 0; S.base_q = 0;
-            unsigned cm = 0;
-            for (int j = 0; j < pk.n_covis; ++j) cm |= (pk.covis_valid[f * pk.n_covis + j] ? 1u : 0u) << j;
-            S.covis_mask = cm;
+            S.covis_mask = K.covis_mask;
         }
     }
     for (int k = tid; k < max_kp; k += kThreads) { T.best_d2[k] = kInf64; T.best_key[k] = kNoKey; }

@@ -530,6 +530,8 @@ stl_status_t stl_upload_pack(stl_ctx_t *ctx, const stl_pack_t *p) {
             max_tab = std::max(max_tab, tl.bytes);
         }
         K.he_valid = p->he_valid[f] ? 1 : 0;
+        K.covis_mask = 0;
+        for (int j = 0; j < C; ++j) K.covis_mask |= (p->covis_valid[(size_t)f * C + j] ? 1u : 0u) << j;
         K.mp_off = mp_total;
         K.n_mp = 0;
         for (long long k = 0; k < nk; ++k) K.n_mp += !(p->kp_mappoint[(K.kp_off + k) * 3] != p->kp_mappoint[(K.kp_off + k) * 3]);

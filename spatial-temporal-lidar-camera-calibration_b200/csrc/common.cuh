@@ -41,7 +41,7 @@ struct DevKf {
     int he_valid;
     float fx, fy, cx, cy;
     float pmax;  // max |coordinate| of the scan (fast-path error bound)
-    float pad_;
+    uint32_t covis_mask;  // bit j: covisible slot j of this keyframe is valid (DevPack::covis_valid)
 };
 
 // K1 table blob of one keyframe: everything the association kernel stages in shared memory, contiguous and 16-byte
