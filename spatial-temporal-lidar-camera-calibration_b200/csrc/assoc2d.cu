@@ -34,25 +34,18 @@ constexpr unsigned long long kInf64 = 0x7ff0000000000000ull;  // +inf bits
 constexpr unsigned long long kNoKey = 0xffffffffffffffffull;
 static_assert(kSurvCap <= 4096, "a correspondence key keeps the survivor slot in 12 bits");
 
-// Everything K1 derives from (candidate, keyframe) before it touches a point.  Two of these live in shared memory: while the
-// CTA works on one unit, a helper thread prepares the next one (ticket, fast rows, error bounds, culling half-spaces).
-struct UnitPar {
-    float4 plane[5];   // conservative half-spaces of "may pass the pre-cull": a.xyz . p + a.w >= thr
-    float thr[5];
+struct Smem {  // fixed part; dynamic arrays follow
     float mu[4], mv[4], mz[4];  // fast projection rows: u*z, v*z, z
     float zmin, ub_u, ub_v, ez;
     float u_hi, v_hi;
-    int unit;          // (keyframe, candidate) unit; -1: no work left, -2: nothing prepared yet (first pass of the loop)
-    int new_tab;       // the keyframe differs from the previous unit's: its table blob must be brought in
-    int tab_bytes;     // ... from here (DevKf::tab_off / tab_bytes, so that thread 0 need not wait for the keyframe record)
-    long long tab_off;
-};
-
-struct Smem {  // fixed part; dynamic arrays follow
-    UnitPar par[2];
+    float4 plane[5];   // conservative half-spaces of "may pass the pre-cull": a.xyz . p + a.w >= thr
+    float thr[5];
     int n_surv, overflow, n_groups, n_match, next_group;
-    int u_end;         // end of the chunk of units in hand (helper thread only)
-    int n_cells;       // visible level-1 cells of the current unit
+    // persistent-loop state (written by thread 0 between two barriers, read by everybody)
+    int unit, u_end, new_tab, cur_f;
+    int next_ticket, have_next;  // drawn ahead by a helper thread while the current unit runs
+    int n_cells;                 // visible level-1 cells of the current unit
+    unsigned covis_mask;  // bit j: covisible slot j of this keyframe is valid
     double he_val;
     int warp_cnt[16], warp_q[16];
     int base_corr, base_q;
@@ -129,7 +122,7 @@ __device__ __noinline__ double hand_eye_term(const DevPack &pk, const DevCand &c
 // Can any point of the box satisfy all five half-spaces?  max over the box of a.p + w is
 // a.c + |a|.e + w (c = centre, e = half extent); float32 evaluation error is covered by a relative
 // slack of 2^-16 on the magnitude of the terms.  Empty boxes (lo > hi) are never visible.
-__device__ __forceinline__ bool box_visible(const UnitPar &S, float4 lo, float4 hi) {
+__device__ __forceinline__ bool box_visible(const Smem &S, float4 lo, float4 hi) {
     if (!(lo.x <= hi.x)) return false;
     const float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
     const float ex = 0.5f * (hi.x - lo.x), ey = 0.5f * (hi.y - lo.y), ez = 0.5f * (hi.z - lo.z);
@@ -218,43 +211,21 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         mbar_init(&S.mbar, 1);
-        S.par[0].unit = -2; S.par[1].unit = -2; S.u_end = 0;
+        S.unit = -1; S.u_end = 0; S.cur_f = -1; S.new_tab = 0; S.have_next = 0;
     }
     uint32_t tab_phase = 0;
-    int cur = 0;
     for (;;) {
     __syncthreads();  // the previous unit is finished by every thread: tables, records and S are free again
-    const UnitPar &P = S.par[cur];
-    const int unit = P.unit;
-    if (unit == -1) break;
     long long clk_top = 0;
     if (wk.k1_clk != nullptr && tid == 0) clk_top = clock64();
-    const int f = unit < 0 ? 0 : unit / B, b = unit < 0 ? 0 : unit - f * B;
-    const DevKf K = pk.kf[f];
-    const DevCand &c = wk.cand[b];
-    const bool new_tab = P.new_tab != 0;
-    // ---- prologue: thread 0 sends for the table blob (one bulk copy) and clears the counters, everybody clears the
-    // per-keypoint minima
-    if (tid == 0 && unit >= 0) {
-        if (new_tab) {
-            fence_proxy_async();
-            mbar_expect_tx(&S.mbar, (uint32_t)P.tab_bytes);
-            bulk_g2s(tab, pk.k1tab + P.tab_off, (uint32_t)P.tab_bytes, &S.mbar);
-        }
-        S.n_surv = 0; S.overflow = 0; S.n_groups = 0; S.n_match = 0; S.next_group = 0; S.he_val = 0.0; S.n_cells = 0;
-        S.base_corr = 0; S.base_q = 0;
-    }
-    for (int k = tid; k < max_kp; k += kThreads) { T.best_d2[k] = kInf64; T.best_key[k] = kNoKey; }
-    __syncthreads();
-    // ---- the NEXT unit is prepared now, by one thread of another warp, off the critical path: next unit of the chunk in
-    // hand or a new ticket (every CTA draws exactly one failing ticket; the last one to do so re-arms the counters), fast
-    // rows, float32 error bounds, culling half-spaces, and the covisible pixels of its keypoints asked into L2
-    if (tid == 32) {
-        UnitPar &N = S.par[cur ^ 1];
-        int u = unit + 1;
-        if (unit < 0 || u >= S.u_end) {
-            const long long t0 = (long long)atomicAdd(wk.k1_ticket, 1) * chunk;
-            if (t0 >= n_units) {
+    // ---- prologue, thread 0: next unit (from the chunk in hand or a new ticket), table blob on its way (one bulk copy),
+    // fast rows, error bounds, culling half-spaces.  Everybody else clears the per-keypoint minima meanwhile.
+    if (tid == 0) {
+        int u = S.unit + 1;
+        if (S.unit < 0 || u >= S.u_end) {
+            const long long t0 = (long long)(S.have_next ? S.next_ticket : atomicAdd(wk.k1_ticket, 1)) * chunk;
+            S.have_next = 0;
+            if (t0 >= n_units) {  // every CTA draws exactly one failing ticket; the last one to leave re-arms the counters
                 if (atomicAdd(wk.k1_ticket + 1, 1) == (int)gridDim.x - 1) { wk.k1_ticket[0] = 0; wk.k1_ticket[1] = 0; __threadfence(); }
                 u = -1;
             } else {
@@ -262,63 +233,77 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
                 S.u_end = (int)min(t0 + chunk, (long long)n_units);
             }
         }
-        N.unit = u;
+        S.unit = u;
         if (u >= 0) {
-            const int fn = u / B;
-            const DevKf &Kn = pk.kf[fn];
-            const DevCand &cn = wk.cand[u - fn * B];
-            N.new_tab = (unit < 0 || fn != f) ? 1 : 0;
-            N.tab_off = Kn.tab_off; N.tab_bytes = Kn.tab_bytes;
-            if (with_terms && pk.n_covis > 0 && Kn.n_kp > 0) {
-                const unsigned long long a0 = (unsigned long long)(pk.covis_uv + Kn.kp_off * pk.n_covis);
-                const unsigned long long a = a0 & ~15ull, e = (a0 + 8ull * Kn.n_kp * pk.n_covis) & ~15ull;
+            const int f = u / B;
+            const DevKf &K = pk.kf[f];
+            const DevCand &c = wk.cand[u - f * B];
+            S.new_tab = f != S.cur_f;
+            S.cur_f = f;
+            if (S.new_tab) {
+                fence_proxy_async();
+                mbar_expect_tx(&S.mbar, (uint32_t)K.tab_bytes);
+                bulk_g2s(tab, pk.k1tab + K.tab_off, (uint32_t)K.tab_bytes, &S.mbar);
+            }
+            if (with_terms && pk.n_covis > 0 && K.n_kp > 0) {  // covisible pixels of this keyframe's keypoints: wanted in L2 ~50 us from now
+                const unsigned long long a0 = (unsigned long long)(pk.covis_uv + K.kp_off * pk.n_covis);
+                const unsigned long long a = a0 & ~15ull, e = (a0 + 8ull * K.n_kp * pk.n_covis) & ~15ull;
                 if (e > a) bulk_prefetch_l2(reinterpret_cast<const void *>(a), (uint32_t)(e - a));
             }
-            const double fx = Kn.fx, cx = Kn.cx, cy = Kn.cy;
+            const double fx = K.fx, cx = K.cx, cy = K.cy;
             double ru[4], rv[4], rz[4];
             for (int j = 0; j < 3; ++j) {
-                ru[j] = fx * cn.R[j] + cx * cn.R[6 + j];
-                rv[j] = fx * cn.R[3 + j] + cy * cn.R[6 + j];
-                rz[j] = cn.R[6 + j];
+                ru[j] = fx * c.R[j] + cx * c.R[6 + j];
+                rv[j] = fx * c.R[3 + j] + cy * c.R[6 + j];
+                rz[j] = c.R[6 + j];
             }
-            ru[3] = fx * cn.t[0] + cx * cn.t[2];
-            rv[3] = fx * cn.t[1] + cy * cn.t[2];
-            rz[3] = cn.t[2];
-            for (int j = 0; j < 4; ++j) { N.mu[j] = (float)ru[j]; N.mv[j] = (float)rv[j]; N.mz[j] = (float)rz[j]; }
+            ru[3] = fx * c.t[0] + cx * c.t[2];
+            rv[3] = fx * c.t[1] + cy * c.t[2];
+            rz[3] = c.t[2];
+            for (int j = 0; j < 4; ++j) { S.mu[j] = (float)ru[j]; S.mv[j] = (float)rv[j]; S.mz[j] = (float)rz[j]; }
             // float32 error model of the fast path: 3 FMAs + rounded matrix entries
-            const double eps = 1.1920928955078125e-07, pm = Kn.pmax;
+            const double eps = 1.1920928955078125e-07, pm = K.pmax;
             const double Az = (fabs(rz[0]) + fabs(rz[1]) + fabs(rz[2])) * pm + fabs(rz[3]);
             const double Au = (fabs(ru[0]) + fabs(ru[1]) + fabs(ru[2])) * pm + fabs(ru[3]);
             const double Av = (fabs(rv[0]) + fabs(rv[1]) + fabs(rv[2])) * pm + fabs(rv[3]);
             const double ez = 4 * eps * Az, eu = 4 * eps * fmax(Au, Av);
-            const double Umax = (double)max(Kn.W, Kn.H) + 8.0;
+            const double Umax = (double)max(K.W, K.H) + 8.0;
             const double zmin = (eu + Umax * ez) / ((double)kFastErrPx - Umax * 3 * eps);
-            N.zmin = (float)(zmin * 1.0001) + 1e-30f;
-            N.ez = (float)(ez * 1.0001);
-            N.ub_u = (float)(((double)Kn.W + 2.0) * (zmin + ez) + eu);
-            N.ub_v = (float)(((double)Kn.H + 2.0) * (zmin + ez) + eu);
-            N.u_hi = (float)(kBmCell * (Kn.bm_wpr * 32 - 1));  // never index past the row
-            N.u_hi = fminf(N.u_hi, (float)(Kn.W + kBmCell));
-            N.v_hi = (float)(Kn.H + kBmCell);
+            S.zmin = (float)(zmin * 1.0001) + 1e-30f;
+            S.ez = (float)(ez * 1.0001);
+            S.ub_u = (float)(((double)K.W + 2.0) * (zmin + ez) + eu);
+            S.ub_v = (float)(((double)K.H + 2.0) * (zmin + ez) + eu);
+            S.u_hi = (float)(kBmCell * (K.bm_wpr * 32 - 1));  // never index past the row
+            S.u_hi = fminf(S.u_hi, (float)(K.W + kBmCell));
+            S.v_hi = (float)(K.H + kBmCell);
             // Half-spaces every point that can pass the pre-cull satisfies (main case g_i >= 0; points of
             // the thin slab z <= zmin only satisfy g_i >= -m, so -m is the threshold).
             {
-                const float uh = N.u_hi, vh = N.v_hi, two = (float)kBmCell;
-                const float rzx = N.mz[0], rzy = N.mz[1], rzz = N.mz[2], rzw = N.mz[3];
-                N.plane[0] = make_float4(rzx, rzy, rzz, rzw);
-                N.plane[1] = make_float4(N.mu[0] + two * rzx, N.mu[1] + two * rzy, N.mu[2] + two * rzz, N.mu[3] + two * rzw);
-                N.plane[2] = make_float4(uh * rzx - N.mu[0], uh * rzy - N.mu[1], uh * rzz - N.mu[2], uh * rzw - N.mu[3]);
-                N.plane[3] = make_float4(N.mv[0] + two * rzx, N.mv[1] + two * rzy, N.mv[2] + two * rzz, N.mv[3] + two * rzw);
-                N.plane[4] = make_float4(vh * rzx - N.mv[0], vh * rzy - N.mv[1], vh * rzz - N.mv[2], vh * rzw - N.mv[3]);
-                const float mslab_u = N.ub_u + (uh + two) * (N.ez + N.zmin), mslab_v = N.ub_v + (vh + two) * (N.ez + N.zmin);
-                N.thr[0] = -N.ez;
-                N.thr[1] = -mslab_u; N.thr[2] = -mslab_u;
-                N.thr[3] = -mslab_v; N.thr[4] = -mslab_v;
+                const float uh = S.u_hi, vh = S.v_hi, two = (float)kBmCell;
+                const float rzx = S.mz[0], rzy = S.mz[1], rzz = S.mz[2], rzw = S.mz[3];
+                S.plane[0] = make_float4(rzx, rzy, rzz, rzw);
+                S.plane[1] = make_float4(S.mu[0] + two * rzx, S.mu[1] + two * rzy, S.mu[2] + two * rzz, S.mu[3] + two * rzw);
+                S.plane[2] = make_float4(uh * rzx - S.mu[0], uh * rzy - S.mu[1], uh * rzz - S.mu[2], uh * rzw - S.mu[3]);
+                S.plane[3] = make_float4(S.mv[0] + two * rzx, S.mv[1] + two * rzy, S.mv[2] + two * rzz, S.mv[3] + two * rzw);
+                S.plane[4] = make_float4(vh * rzx - S.mv[0], vh * rzy - S.mv[1], vh * rzz - S.mv[2], vh * rzw - S.mv[3]);
+                const float mslab_u = S.ub_u + (uh + two) * (S.ez + S.zmin), mslab_v = S.ub_v + (vh + two) * (S.ez + S.zmin);
+                S.thr[0] = -S.ez;
+                S.thr[1] = -mslab_u; S.thr[2] = -mslab_u;
+                S.thr[3] = -mslab_v; S.thr[4] = -mslab_v;
             }
+            S.n_surv = 0; S.overflow = 0; S.n_groups = 0; S.n_match = 0; S.next_group = 0; S.he_val = 0.0; S.n_cells = 0;
+            S.base_corr = 0; S.base_q = 0;
+            S.covis_mask = K.covis_mask;
         }
     }
-    cur ^= 1;  // (P keeps naming this unit's block)
-    if (unit < 0) continue;  // first pass: nothing was prepared yet
+    for (int k = tid; k < max_kp; k += kThreads) { T.best_d2[k] = kInf64; T.best_key[k] = kNoKey; }
+    __syncthreads();
+    const int unit = S.unit;
+    if (unit < 0) break;
+    const int f = unit / B, b = unit - f * B;
+    const DevKf K = pk.kf[f];
+    const DevCand &c = wk.cand[b];
+    const bool new_tab = S.new_tab != 0;
     float4 *const rec = wk.k1_rec + (size_t)blockIdx.x * kSurvCap;            // this CTA's survivor records
     ulonglong2 *const matches = wk.k1_match + (size_t)blockIdx.x * kMatchCap;  // ... and match list (both stay in L2)
     {
@@ -333,6 +318,10 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
     const bool timing = wk.k1_clk != nullptr && tid == 0;
     if (timing) clk[0] = clock64();
 
+    // the ticket of the NEXT chunk is drawn now, by a thread of another warp, so that its round trip to L2 is off the
+    // critical path of the next prologue (only when this unit ends the chunk in hand; a CTA stops at its first failing ticket)
+    if (tid == 32 && unit + 1 >= S.u_end) { S.next_ticket = atomicAdd(wk.k1_ticket, 1); S.have_next = 1; }
+
     // ---- phase A1: which 128-point groups can hold a visible point?  Level-1 cells (1024 points) one per THREAD first,
     // then one warp per visible cell tests its 32 leaf boxes, one per lane: two dependent round trips to the boxes in all.
     {
@@ -340,7 +329,7 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
         const int n_l1 = (K.n_pad + 1023) >> 10;
         for (int n0 = 0; n0 < n_l1; n0 += kThreads) {
             const int node = n0 + tid;
-            const bool vis = node < n_l1 && box_visible(P, nlo[K.n0 + node], nhi[K.n0 + node]);
+            const bool vis = node < n_l1 && box_visible(S, nlo[K.n0 + node], nhi[K.n0 + node]);
             const unsigned vm = __ballot_sync(0xffffffffu, vis);
             if (vm) {
                 int base = 0;
@@ -353,7 +342,7 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
         const int nc = S.n_cells;
         for (int ci = warp; ci < nc; ci += kThreads / 32) {
             const int node = T.cells[ci];
-            const bool lv = box_visible(P, nlo[node * 32 + lane], nhi[node * 32 + lane]);
+            const bool lv = box_visible(S, nlo[node * 32 + lane], nhi[node * 32 + lane]);
             const unsigned lmask = __ballot_sync(0xffffffffu, lv);
             // lane g < 8 owns group g of the cell (leaves 4g .. 4g+3)
             const bool need = lane < 8 && ((lmask >> (4 * lane)) & 0xfu) && (node * 8 + lane) * 128 < K.n_pad;
@@ -375,10 +364,10 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
 
     // ---- phase A2: stream the visible groups (SoA float4 loads, 12 B/point), float32 pre-cull
     {
-        const float mu0 = P.mu[0], mu1 = P.mu[1], mu2 = P.mu[2], mu3 = P.mu[3];
-        const float mv0 = P.mv[0], mv1 = P.mv[1], mv2 = P.mv[2], mv3 = P.mv[3];
-        const float mz0 = P.mz[0], mz1 = P.mz[1], mz2 = P.mz[2], mz3 = P.mz[3];
-        const float zmin = P.zmin, u_hi = P.u_hi, v_hi = P.v_hi, lo = -(float)kBmCell;
+        const float mu0 = S.mu[0], mu1 = S.mu[1], mu2 = S.mu[2], mu3 = S.mu[3];
+        const float mv0 = S.mv[0], mv1 = S.mv[1], mv2 = S.mv[2], mv3 = S.mv[3];
+        const float mz0 = S.mz[0], mz1 = S.mz[1], mz2 = S.mz[2], mz3 = S.mz[3];
+        const float zmin = S.zmin, u_hi = S.u_hi, v_hi = S.v_hi, lo = -(float)kBmCell;
         const int wpr = K.bm_wpr, cu_max = K.bm_wpr * 32 - 1, cv_max = K.bm_rows - 1;
         const float4 *X = reinterpret_cast<const float4 *>(pk.px + K.pt_off);
         const float4 *Y = reinterpret_cast<const float4 *>(pk.py + K.pt_off);
@@ -423,9 +412,9 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
                         const int cv = min(max((int)floorf(vz * inv * (1.0f / kBmCell)) + 1, 0), cv_max);
                         pass = (T.bm[cv * wpr + (cu >> 5)] >> (cu & 31)) & 1u;
                     }
-                } else if (zc > -P.ez) {
+                } else if (zc > -S.ez) {
                     // thin slab in front of the camera plane where the float32 bound does not hold: exact path decides
-                    pass = fabsf(uz) <= P.ub_u && fabsf(vz) <= P.ub_v;
+                    pass = fabsf(uz) <= S.ub_u && fabsf(vz) <= S.ub_v;
                 }
                 pm |= (pass ? 1u : 0u) << e;
             }
@@ -566,7 +555,7 @@ k_assoc2d(const DevPack pk, const DevWork wk, const DevParams pr, const int B, c
             // 3-D/2-D term over (covisible keyframe) x (correspondence), the pairs dealt evenly to the threads
             __syncthreads();
             const int C = pk.n_covis;
-            const unsigned cmask = K.covis_mask;
+            const unsigned cmask = S.covis_mask;
             const double fx = K.fx, fy = K.fy, cx = K.cx, cy = K.cy, W = K.W, H = K.H;
             for (int j = 0; j < C; ++j) {
                 if (!((cmask >> j) & 1u)) continue;
