@@ -1,9 +1,10 @@
-python bench.py --config c4 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/r02l_c4.json 2> gpurun_out/r02l_c4.err; tail -3 gpurun_out/r02l_c4.err
-python bench.py --nkf 188 --steps 30 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r02l_c2_188.json 2> gpurun_out/r02l_c2_188.err
-STL_K1_SPLIT=1 python bench.py --nkf 188 --steps 30 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r02l_c2_188_split.json 2> gpurun_out/r02l_c2_188_split.err
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r02m_c2.json 2> gpurun_out/r02m_c2.err; tail -3 gpurun_out/r02m_c2.err
+python bench.py --nkf 188 --steps 30 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r02m_c2_188.json 2> gpurun_out/r02m_c2_188.err
 python - <<'PY'
 import json
-for n in ('r02l_c4','r02l_c2_188','r02l_c2_188_split'):
+for n in ('r02m_c2','r02m_c2_188'):
     d=json.load(open(f'gpurun_out/{n}.json'))
-    print(n,'value',round(d['value'],1),'ms',round(d['ms_per_step'],4),'e2e',round(d['e2e']['value'],1),d['stage_ms_per_launch'], 'k1 launches', d['roofline']['launches'], d['roofline'].get('candidates_per_launch'))
+    print(n,'value',round(d['value'],1),'ms',round(d['ms_per_step'],4),'e2e',round(d['e2e']['value'],1),d['stage_ms_per_launch'])
 PY
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/r02m_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/r02m_launches_bench.log 2>&1
