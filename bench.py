@@ -512,6 +512,7 @@ def main():
                 "note": "12 B read + 16 B written per point; dominated by the shared-memory KD refinement (bitonic networks), not by HBM",
             },
             "stage_share": share,
+            "stage_note": "device time per stage from CUDA events on the stream each stage runs on; in the step the association chain (assoc_lm, linearize) runs on a second stream beside knn3d / reduce, so the stages overlap and do not add up to ms_per_step (STL_NO_OVERLAP=1 serialises them)",
             "stage_ms_per_launch": {k: round(v[0] / v[1], 4) for k, v in stats.items() if v[1] and k not in ("build", "plane_index")},
             "knn": {"queries_per_eval": knn_q_eval, "queries_per_s_whole_step": knn_q_eval * value,
                     "k2_pairs_per_s": (q3 * B / (world if by_kf else 1) / (k2_ms / max(k2_n, 1) * 1e-3)) if k2_ms > 0 else None},

@@ -30,6 +30,10 @@ struct stl_ctx {
     cudaStream_t stream = nullptr;       // default stream of calls without an explicit one (stl_set_stream)
     cudaStream_t last_stream = nullptr;  // stream of the previous call: a change inserts an event dependency
     cudaEvent_t handoff = nullptr;
+    // stl_step_batch: BuildProblem + linearisation run on a stream of their own beside the evaluation's 3-D stage
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_k1 = nullptr, ev_k2a = nullptr, ev_k3 = nullptr, ev_aux = nullptr;
+    long long overlapped_steps = 0;
     long long launches = 0;
     std::mutex mu;
     std::string err;
@@ -74,7 +78,7 @@ struct stl_ctx {
     long long lin_cap = 0;  // doubles
     // profiling
     bool profiling = false;
-    struct Ev { cudaEvent_t a, b; int stage; };
+    struct Ev { cudaEvent_t a, b; int stage; bool count; };
     std::vector<Ev> evs;
     std::vector<cudaEvent_t> ev_pool;
     double stage_ms[STL_NSTAGES] = {0};
@@ -166,8 +170,9 @@ void set_dev_params(stl_ctx *c) {
 }
 
 struct StageTimer {
-    stl_ctx *c; int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
-    StageTimer(stl_ctx *c_, int s, cudaStream_t st_) : c(c_), stage(s), st(st_) {
+    stl_ctx *c; int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; bool count;
+    // count = false: the time is added to the stage, the launch count is not (second half of a stage split around a wait)
+    StageTimer(stl_ctx *c_, int s, cudaStream_t st_, bool count_ = true) : c(c_), stage(s), st(st_), count(count_) {
         if (!c->profiling) return;
         auto get = [&]() { cudaEvent_t e; if (c->ev_pool.empty()) cudaEventCreate(&e); else { e = c->ev_pool.back(); c->ev_pool.pop_back(); } return e; };
         a = get(); b = get();
@@ -176,7 +181,7 @@ struct StageTimer {
     ~StageTimer() {
         if (!a) return;
         cudaEventRecord(b, st);
-        c->evs.push_back({a, b, stage});
+        c->evs.push_back({a, b, stage, count});
     }
 };
 
@@ -184,7 +189,7 @@ void drain_events(stl_ctx *c) {
     for (auto &e : c->evs) {
         cudaEventSynchronize(e.b);
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { c->stage_ms[e.stage] += ms; c->stage_n[e.stage] += 1; }
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { c->stage_ms[e.stage] += ms; c->stage_n[e.stage] += e.count ? 1 : 0; }
         c->ev_pool.push_back(e.a);
         c->ev_pool.push_back(e.b);
     }
@@ -293,8 +298,9 @@ stl_status_t ensure_work(stl_ctx *ctx, int B, bool debug) {
 // Enqueues the evaluation of B candidates; d_out [B][STL_EVAL_NSUMS] device.
 // exchange: the record of this call is complete after K3 (stl_eval_batch): K3 sums it over the ranks, chunk by chunk, when
 // the peer path is up; *exchanged tells the caller whether that happened (else it runs the NCCL all-reduce)
+// marks: record ev_k1 / ev_k2a / ev_k3 behind K1 / K2a / K3 (single-chunk batches only: the overlapped step)
 stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, cudaStream_t st, bool debug, int out_stride = STL_EVAL_NSUMS,
-                          bool exchange = false, bool *exchanged = nullptr) {
+                          bool exchange = false, bool *exchanged = nullptr, bool marks = false) {
     stl_status_t s = ensure_work(ctx, B, debug);
     if (s != STL_OK) return s;
     if (!ctx->h2d_done) CK(cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming));
@@ -308,13 +314,15 @@ stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, c
           if (ctx->k1_mono) CK(launch_assoc2d(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_smem, ctx->max_kp, ctx->max_tab, ctx->max_groups, st));
           else CK(launch_assoc2d_split(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_split_smem, 0, st)); }
         ctx->launches += ctx->k1_mono ? 0 : 2;
-        { StageTimer t(ctx, STL_STAGE_KNN3D, st); CK(launch_align3d(ctx->pk, ctx->wk, ctx->dpr, nb, debug ? 1 : 0, st)); }
+        if (marks) CK(cudaEventRecord(ctx->ev_k1, st));
+        { StageTimer t(ctx, STL_STAGE_KNN3D, st); CK(launch_align3d(ctx->pk, ctx->wk, ctx->dpr, nb, debug ? 1 : 0, st, marks ? ctx->ev_k2a : nullptr)); }
         {
             StageTimer t(ctx, STL_STAGE_REDUCE, st);
             const P2pView pv = exchange ? p2p_view(ctx, nb, 0, STL_EVAL_NSUMS) : P2pView();
             if (exchanged) *exchanged = pv.n > 1;
             CK(launch_reduce(ctx->pk, ctx->wk, ctx->dpr, nb, d_out + (size_t)c0 * out_stride, st, out_stride, &pv));
         }
+        if (marks) CK(cudaEventRecord(ctx->ev_k3, st));
         ctx->launches += 4;  // K1, K2a, K2b, K3
         ctx->wk_x.assign(x + (size_t)c0 * 7, x + (size_t)(c0 + nb) * 7);
         ctx->wk_has_nn = true;  // K2a runs for every query of a kept frame and writes its nn_pos
@@ -341,7 +349,7 @@ stl_status_t allreduce_record(stl_ctx *ctx, double *d_buf, size_t count, cudaStr
 
 // Enqueues BuildProblem at x0 on `st`.  The 2-D association (FindProjectCorrespondences) is taken from the
 // workspace when the preceding evaluation left the correspondences of exactly this x0 there, else K1 runs.
-stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st) {
+stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st, cudaEvent_t hint_ready = nullptr) {
     const DevPack &pk = ctx->pk;
     int slot = -1;
     for (size_t j = 0; j * 7 + 7 <= ctx->wk_x.size(); ++j)
@@ -373,7 +381,14 @@ stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st) 
         ctx->wk_has_nn = false;
     }
     cudaError_t e;
-    { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint, getenv("STL_NO_NN_CERT") ? nullptr : nn_g2); }
+    const float *g2 = getenv("STL_NO_NN_CERT") ? nullptr : nn_g2;
+    if (hint_ready) {  // on a stream of its own: the part that needs K2a's answer waits for it, outside the stage timers
+        { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint, g2, 1); }
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, hint_ready, 0);
+        if (e == cudaSuccess) { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st, false); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint, g2, 2); }
+    } else {
+        StageTimer t(ctx, STL_STAGE_ASSOC_LM, st); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint, g2);
+    }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "associate: %s", cudaGetErrorString(e));
     ctx->launches += (ctx->dpr.plane_index && !ctx->dpr.use_gpr) ? 3 : 4;  // the association kernels (cub select kernels not counted)
     if (ctx->params.use_gpr && ctx->params.gpr_optimize) {  // GPR::fit per factor (IBACalib2.hpp:460-461), host side
@@ -467,6 +482,8 @@ void stl_destroy(stl_ctx_t *c) {
     if (c->h_lin) cudaFreeHost(c->h_lin);
     if (c->h2d_done) cudaEventDestroy(c->h2d_done);
     if (c->handoff) cudaEventDestroy(c->handoff);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    for (cudaEvent_t e : {c->ev_k1, c->ev_k2a, c->ev_k3, c->ev_aux}) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -968,12 +985,12 @@ stl_status_t stl_block_counts(stl_ctx_t *ctx, int64_t n_blocks[4]) {
 // exch_off / exch_width: the record k_lin_finish completes starts exch_off doubles from its own output row and is exch_width
 // long (0: no exchange); *exchanged as in enqueue_eval
 static stl_status_t lin_enqueue(stl_ctx *ctx, const double *x, int B, double *d_out, cudaStream_t st, int out_stride = STL_LIN_NSUMS,
-                                int exch_off = 0, int exch_width = 0, bool *exchanged = nullptr) {
+                                int exch_off = 0, int exch_width = 0, bool *exchanged = nullptr, cudaEvent_t before_finish = nullptr) {
     if (!ctx->lm.ready) return fail(ctx, STL_ERR_STATE, "stl_associate has not been called");
     cudaError_t e;
     const P2pView pv = exch_width > 0 ? p2p_view(ctx, B, exch_off, exch_width) : P2pView();
     if (exchanged) *exchanged = pv.n > 1;
-    { StageTimer t(ctx, STL_STAGE_LINEARIZE, st); e = lm_linearize(ctx->pk, ctx->dpr, ctx->lm, x, B, d_out, st, nullptr, out_stride, &pv); }
+    { StageTimer t(ctx, STL_STAGE_LINEARIZE, st); e = lm_linearize(ctx->pk, ctx->dpr, ctx->lm, x, B, d_out, st, nullptr, out_stride, &pv, before_finish); }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "linearize: %s", cudaGetErrorString(e));
     ctx->launches += 2 + (ctx->lm.use_gpr ? 1 : 0);  // k_linearize, (k_linearize_gpr,) k_lin_finish
     return STL_OK;
@@ -993,7 +1010,36 @@ static stl_status_t ensure_lin(stl_ctx *ctx, int B, int width) {
 }
 
 static stl_status_t step_enqueue(stl_ctx *ctx, const double *x, int B, int reassociate, double *d_out, cudaStream_t st) {
-    stl_status_t s = enqueue_eval(ctx, x, B, d_out, st, false, STL_STEP_NSUMS);
+    stl_status_t s = ensure_work(ctx, B, false);
+    if (s != STL_OK) return s;
+    // One LM iteration at x with the plane index: BuildProblem needs K1's correspondences and (for its map-point 1-NN) K2a's
+    // answer, the linearisation needs BuildProblem, and nothing of that needs K2b / K3 — so the association chain runs on a
+    // second stream beside K2a / K2b / K3 (plane look-ups are bound by scattered sectors, the traversal by issue slots) and
+    // the two meet again in front of the kernel that finishes the record.
+    const bool overlap = reassociate && B <= ctx->wk.Bc && ctx->dpr.plane_index && !ctx->dpr.use_gpr &&
+                         !getenv("STL_NO_ASSOC_REUSE") && !getenv("STL_NO_OVERLAP");
+    if (overlap) {
+        if (!ctx->aux_stream) {
+            CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ctx->ev_k1, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_k2a, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_k3, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
+        }
+        cudaStream_t ax = ctx->aux_stream;
+        s = enqueue_eval(ctx, x, B, d_out, st, false, STL_STEP_NSUMS, false, nullptr, true);
+        if (s != STL_OK) return s;
+        CK(cudaStreamWaitEvent(ax, ctx->ev_k1, 0));
+        s = enqueue_associate(ctx, x, ax, ctx->ev_k2a);
+        bool done = false;
+        if (s == STL_OK) s = lin_enqueue(ctx, x, B, d_out + STL_EVAL_NSUMS, ax, STL_STEP_NSUMS, -STL_EVAL_NSUMS, STL_STEP_NSUMS, &done, ctx->ev_k3);
+        // whatever happened, the caller's stream is not released before the second stream has drained
+        cudaEventRecord(ctx->ev_aux, ax);
+        cudaStreamWaitEvent(st, ctx->ev_aux, 0);
+        if (s != STL_OK) return s;
+        ctx->overlapped_steps += 1;
+        ctx->last_x.assign(x, x + (size_t)B * 7);
+        return done ? STL_OK : allreduce_record(ctx, d_out, (size_t)B * STL_STEP_NSUMS, st);
+    }
+    s = enqueue_eval(ctx, x, B, d_out, st, false, STL_STEP_NSUMS);
     if (s != STL_OK) return s;
     if (reassociate) {
         s = enqueue_associate(ctx, x, st);

@@ -242,11 +242,12 @@ cudaError_t launch_debug_trig(const double *d_x, int n, double *d_acos, double *
     return cudaGetLastError();
 }
 
-cudaError_t launch_align3d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, int debug, cudaStream_t st) {
+cudaError_t launch_align3d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, int debug, cudaStream_t st, cudaEvent_t after_traversal) {
     if (B <= 0 || pk.n_kf <= 0) return cudaSuccess;
     k_nn_knn<<<(unsigned)(pk.n_kf * B * wk.sub), kWarps * 32, 0, st>>>(pk, wk, pr, B);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (after_traversal && (e = cudaEventRecord(after_traversal, st)) != cudaSuccess) return e;
     k_plane_dist<<<(unsigned)(pk.n_kf * B * wk.sub), kPlaneThreads, 0, st>>>(pk, wk, pr, B, debug);
     return cudaGetLastError();
 }

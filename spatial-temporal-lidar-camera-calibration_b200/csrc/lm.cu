@@ -730,7 +730,7 @@ void lm_free(LmState &lm) {
 // (d_counts: plane, 3-D, point-to-point, GPR), where the linearisation kernels read them; a copy lands
 // in pinned host memory behind `counts_done` for callers that want the numbers (lm_block_counts).
 cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st, const uint32_t *nn_hint,
-                         const float *nn_g2) {
+                         const float *nn_g2, int part) {
     cudaError_t e;
 #define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
     const long long ns = pk.n_kp_total > 0 ? pk.n_kp_total : 1;
@@ -760,12 +760,16 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
         lm.n_slots = ns;
         lm.max_blocks = nm;
     }
+    if (part != 2) {
     lm.ready = false;
     lm.sub = wk.sub;
     TRY(cudaMemsetAsync(lm.flags, 0, lm.flags_bytes, st));
     if (!(pr.plane_index && !pr.use_gpr))  // with the plane index there is no neighbourhood to search at the scan point
         k_lm_knn_a<<<(unsigned)(pk.n_kf * lm.sub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
     k_lm_plane_a<<<(unsigned)(pk.n_kf * lm.sub), 128, 0, st>>>(pk, wk, pr, lm);
+    TRY(cudaGetLastError());
+    }
+    if (part == 1) return cudaSuccess;
     k_lm_knn_b<<<(unsigned)(pk.n_kf * lm.sub), kWarps * 32, 0, st>>>(pk, wk, pr, lm, nn_hint, nn_g2);
     k_lm_plane_b<<<(unsigned)(pk.n_kf * lm.sub), 128, 0, st>>>(pk, wk, pr, lm);
     TRY(cudaGetLastError());
@@ -906,7 +910,7 @@ cudaError_t lm_get_gpr_hyper(const DevParams &pr, LmState &lm, double *out, cuda
 }
 
 cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
-                         const BlockOut *blocks, int out_stride, const P2pView *p2p) {
+                         const BlockOut *blocks, int out_stride, const P2pView *p2p, cudaEvent_t before_finish) {
     cudaError_t e;
 #define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
     if (B > lm.cand_cap) {
@@ -949,6 +953,7 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
         else k_linearize_gpr<false><<<dim3(gchunks, B), 32, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, chunks, bo);
         TRY(cudaGetLastError());
     }
+    if (before_finish) TRY(cudaStreamWaitEvent(st, before_finish, 0));
     k_lin_finish<<<B, 1024, 0, st>>>(lm.partial, stride, d_out, out_stride > 0 ? out_stride : STL_LIN_NSUMS, p2p ? *p2p : P2pView());
     TRY(cudaGetLastError());
 #undef TRY

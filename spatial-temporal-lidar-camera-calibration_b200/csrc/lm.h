@@ -60,8 +60,10 @@ void lm_free(LmState &lm);
 // wk must hold the K1 result (correspondences) of the association extrinsic at candidate slot 0.
 // nn_hint / nn_g2 (optional): per map-point slot, the 1-NN position an evaluation at the SAME extrinsic found and its
 // lower bound of the squared distance to any other scan point (Sink1::g2): seeds, or settles, the 3-D search
+// part: 0 = everything; 1 = up to the plane at the associated scan point (needs K1's result only); 2 = the rest (needs nn_hint /
+// nn_g2, i.e. K2a, when given) — the overlapped step enqueues the two parts around a wait for K2a
 cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st,
-                         const uint32_t *nn_hint = nullptr, const float *nn_g2 = nullptr);
+                         const uint32_t *nn_hint = nullptr, const float *nn_g2 = nullptr, int part = 0);
 // x: HOST [B][7]; d_out: DEVICE [B][STL_LIN_NSUMS]
 // optional per-block output of a linearisation (device pointers; B must be 1)
 struct BlockOut {
@@ -73,7 +75,8 @@ struct BlockOut {
 
 // out_stride: doubles between the records of consecutive candidates in d_out (0 = STL_LIN_NSUMS)
 cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
-                         const BlockOut *blocks = nullptr, int out_stride = 0, const P2pView *p2p = nullptr);
+                         const BlockOut *blocks = nullptr, int out_stride = 0, const P2pView *p2p = nullptr, cudaEvent_t before_finish = nullptr);
+// before_finish (optional): event the finishing kernel waits for (the rest of the record it completes / exchanges)
 // waits for the last association and mirrors its block counts into lm.n2d / n3d / nG / n_blocks
 cudaError_t lm_block_counts(LmState &lm);
 // GPR::fit for every GPR block of the last association (IBA_GPRFactor's constructor, IBACalib2.hpp:441-461): the
