@@ -532,6 +532,14 @@ def test_step_batch_equals_separate_calls(pkg, small_pack, small_candidates, mon
         L0 = c.linearize(X)
         assert np.array_equal(S[:, 12:], L0)
         assert np.array_equal(S[:, 12 + 57], np.full(len(X), nb0[0])) and np.array_equal(S[:, 12 + 61], np.full(len(X), nb0[3]))
+        # the step runs BuildProblem + linearisation on a second stream beside the 3-D stage: same bits when serialised,
+        # and again on repetition (nothing races)
+        monkeypatch.setenv("STL_NO_OVERLAP", "1")
+        S_seq = c.step(X, reassociate=True)
+        monkeypatch.delenv("STL_NO_OVERLAP")
+        assert np.array_equal(S_seq, S)
+        for _ in range(3):
+            assert np.array_equal(c.step(X, reassociate=True), S)
         # frozen association, batch of candidates (the NOMAD poll shape)
         S2 = c.step(X[1:], reassociate=False)
         assert np.array_equal(S2[:, :12], e[1:]) and np.array_equal(S2[:, 12:], L0[1:])
