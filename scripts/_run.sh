@@ -1,11 +1,11 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r02n_c2.json 2> gpurun_out/r02n_c2.err; tail -3 gpurun_out/r02n_c2.err
-STL_NO_OVERLAP=1 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r02n_c2_seq.json 2> gpurun_out/r02n_c2_seq.err
-python bench.py --nkf 188 --steps 30 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r02n_c2_188.json 2> gpurun_out/r02n_c2_188.err
-STL_NO_OVERLAP=1 python bench.py --nkf 188 --steps 30 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r02n_c2_188_seq.json 2> gpurun_out/r02n_c2_188_seq.err
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r02o_c2.json 2> gpurun_out/r02o_c2.err; tail -3 gpurun_out/r02o_c2.err
+STL_NO_OVERLAP=1 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r02o_c2_seq.json 2> gpurun_out/r02o_c2_seq.err
+python bench.py --nkf 188 --steps 30 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r02o_c2_188.json 2> gpurun_out/r02o_c2_188.err
+STL_NO_OVERLAP=1 python bench.py --nkf 188 --steps 30 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r02o_c2_188_seq.json 2> gpurun_out/r02o_c2_188_seq.err
 python - <<'PY'
 import json
-for n in ('r02n_c2','r02n_c2_seq','r02n_c2_188','r02n_c2_188_seq'):
+for n in ('r02o_c2','r02o_c2_seq','r02o_c2_188','r02o_c2_188_seq'):
     d=json.load(open(f'gpurun_out/{n}.json'))
     print(n,'value',round(d['value'],1),'ms',round(d['ms_per_step'],4),'e2e',round(d['e2e']['value'],1),d['stage_ms_per_launch'])
 PY
