@@ -333,25 +333,30 @@ __device__ __forceinline__ void knn_around_point(const ScanView &S, uint32_t pos
     traverse(S, x, y, z, kn, lane, (int)(pos >> 5));
 }
 
+// Distance from a query to the box of leaf `home`, rounded up (float32): what the adjacency certificate of a 1-NN adds to the
+// nearest distance found (nn_near_leaf).
+__device__ __forceinline__ float home_box_delta(const ScanView &S, int home, double qx, double qy, double qz) {
+    const float4 lo = S.lo[home], hi = S.hi[home];
+    const float xl = __double2float_rd(qx), xh = __double2float_ru(qx), yl = __double2float_rd(qy), yh = __double2float_ru(qy);
+    const float zl = __double2float_rd(qz), zh = __double2float_ru(qz);
+    const float gx = fmaxf(fmaxf(__fsub_ru(lo.x, xl), __fsub_ru(xh, hi.x)), 0.f);
+    const float gy = fmaxf(fmaxf(__fsub_ru(lo.y, yl), __fsub_ru(yh, hi.y)), 0.f);
+    const float gz = fmaxf(fmaxf(__fsub_ru(lo.z, zl), __fsub_ru(zh, hi.z)), 0.f);
+    return __fsqrt_ru(__fadd_ru(__fadd_ru(__fmul_ru(gx, gx), __fmul_ru(gy, gy)), __fmul_ru(gz, gz)));
+}
+
 // 1-NN of an arbitrary query that is expected to lie near leaf `home` (the leaf of the scan point its
 // keypoint was associated with).  The adjacency scan is exact when nearest distance + distance from the
 // query to the home box stays inside the covered range (all bounds rounded to the safe side); otherwise
 // the descent finishes the search with the bound already found (re-visiting a leaf cannot change a
 // (d2, index) minimum).
-// `hint` (optional, 0xffffffff = none) is a scan point of leaf `home` believed to be near the query: it seeds the bound.
-__device__ __forceinline__ void nn_near_leaf(const ScanView &S, float adj_r, int home, double qx, double qy, double qz, Sink1 &nn,
-                                             int lane, uint32_t hint = 0xffffffffu) {
-    if (hint != 0xffffffffu) nn.seed(S, hint, qx, qy, qz);
+// The sink arrives seeded (or empty) and `delta` = home_box_delta of the query: both are per-query scalars that a caller
+// holding one query per lane computes for 32 queries at once (k_nn_knn) before the warp searches them one after another.
+__device__ __forceinline__ void nn_near_leaf_seeded(const ScanView &S, float adj_r, int home, double qx, double qy, double qz, Sink1 &nn,
+                                                    int lane, float delta) {
     const float cov = scan_adjacent(S, home, qx, qy, qz, nn, lane);
     if (S.stats && lane == 0) atomicAdd(S.stats + 4, 1ull);
     if (cov >= 0.f && nn.pos != 0xffffffffu) {
-        const float4 lo = S.lo[home], hi = S.hi[home];
-        const float xl = __double2float_rd(qx), xh = __double2float_ru(qx), yl = __double2float_rd(qy), yh = __double2float_ru(qy);
-        const float zl = __double2float_rd(qz), zh = __double2float_ru(qz);
-        const float gx = fmaxf(fmaxf(__fsub_ru(lo.x, xl), __fsub_ru(xh, hi.x)), 0.f);
-        const float gy = fmaxf(fmaxf(__fsub_ru(lo.y, yl), __fsub_ru(yh, hi.y)), 0.f);
-        const float gz = fmaxf(fmaxf(__fsub_ru(lo.z, zl), __fsub_ru(zh, hi.z)), 0.f);
-        const float delta = __fsqrt_ru(__fadd_ru(__fadd_ru(__fmul_ru(gx, gx), __fmul_ru(gy, gy)), __fmul_ru(gz, gz)));
         const float reach = __fadd_ru(__fsqrt_ru(nn.df), delta);
         if (cov > 3.0e38f ? reach <= adj_r : reach < __fsqrt_rd(cov)) {
             if (S.stats && lane == 0) atomicAdd(S.stats + 5, 1ull);
@@ -380,6 +385,13 @@ __device__ __forceinline__ void nn_near_leaf(const ScanView &S, float adj_r, int
     }
     if (S.stats && lane == 0) atomicAdd(S.stats + (cov >= 0.f ? 6 : 7), 1ull);
     traverse(S, qx, qy, qz, nn, lane);
+}
+
+// `hint` (optional, 0xffffffff = none) is a scan point of leaf `home` believed to be near the query: it seeds the bound.
+__device__ __forceinline__ void nn_near_leaf(const ScanView &S, float adj_r, int home, double qx, double qy, double qz, Sink1 &nn,
+                                             int lane, uint32_t hint = 0xffffffffu) {
+    if (hint != 0xffffffffu) nn.seed(S, hint, qx, qy, qz);
+    nn_near_leaf_seeded(S, adj_r, home, qx, qy, qz, nn, lane, home_box_delta(S, home, qx, qy, qz));
 }
 
 // ---- local plane around a scan point (one THREAD per neighbourhood) ---------------------

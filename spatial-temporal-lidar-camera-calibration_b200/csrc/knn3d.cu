@@ -15,6 +15,9 @@
 //   K2b k_plane_dist one THREAD per query: gates, ordered covariance, closed-form eigenvector,
 //                    regression gate, distance; fixed-order CTA reduction per (candidate, keyframe).
 // plus the stand-alone k-NN entry used by the parity tests.
+#include <algorithm>
+#include <cstdlib>
+
 #include "kernels.h"
 #include "knn.cuh"
 
@@ -44,16 +47,19 @@ __device__ __forceinline__ void map_point_lidar(const DevPack &pk, const DevKf &
     xform(c.Ri, c.ti, cxm, cym, czm, qx, qy, qz);  // Tcl.inverse() * P
 }
 
-// K2a — grid: (candidate, keyframe, sub-block), one warp per query
+// K2a — grid: (candidate, keyframe, sub-block).  A warp draws `batch` queries at a time: everything that is a function of ONE
+// query (the map point in the LiDAR frame, the seed distance at the associated scan point, the distance to the home box — 40 %
+// of the kernel's instructions when every lane repeats them for the same query) is computed one query per LANE, then the warp
+// searches the queries one after another with those scalars broadcast.
 __global__ void __launch_bounds__(kWarps * 32, STL_KNN_MINB)
-k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
+k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B, const int batch) {
     const int sub = wk.sub;
     const int j = blockIdx.x % sub;
     const int bf = blockIdx.x / sub;
     const int f = bf / B, b = bf - f * B;
     const int nq = wk.n_q[(long long)b * pk.n_kf + f];
     if (nq <= 0) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const DevKf K = pk.kf[f];
     const DevCand &c = wk.cand[b];
     ScanView S = make_view(pk, K);
@@ -64,22 +70,50 @@ k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B) {
     if (threadIdx.x == 0) ticket = 0;
     __syncthreads();
     for (;;) {
-        const int qi = next_ticket(&ticket, lane) * sub + j;
-        if (qi >= nq) break;
-        const uint2 ks = wk.q_kpsp[cbase + qi];  // (keypoint, associated scan position)
-        double qx, qy, qz;
-        map_point_lidar(pk, K, c, f, ks.x, qx, qy, qz);
-        Sink1 nn;
-        nn_near_leaf(S, pr.adj_r, (int)(ks.y >> 5), qx, qy, qz, nn, lane, ks.y);  // seeded with the associated scan point
-        if (lane == 0) { wk.nn_pos[qbase + qi] = nn.pos; wk.nn_g2[qbase + qi] = nn.g2; }
-        if (pr.use_plane && !pr.plane_index) {  // with the plane index the neighbourhood of nn is already fitted
-            SinkK kn(pr.k, pr.radius2);
-            knn_around_point(S, nn.pos, kn, lane);
-            wk.nb[(qbase + qi) * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
-            store_nb_coords(wk.nbx, wk.nbx_stride, qbase + qi, S, lane, kn.count, kn.kpos);
-            const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
-            if (lane == 0) { wk.nb_m[qbase + qi] = kn.count; wk.nb_last[qbase + qi] = last; }
+        const int t0 = next_ticket(&ticket, lane) * batch;
+        if ((long long)t0 * sub + j >= nq) break;
+        // ---- one query per lane
+        const int qi = (t0 + lane) * sub + j;
+        const bool valid = lane < batch && qi < nq;
+        double qx = 0, qy = 0, qz = 0, sd = DBL_MAX;
+        uint32_t hint = 0, soi = 0xffffffffu, spos = 0xffffffffu;
+        float delta = 0.f;
+        if (valid) {
+            const uint2 ks = wk.q_kpsp[cbase + qi];  // (keypoint, associated scan position)
+            hint = ks.y;
+            map_point_lidar(pk, K, c, f, ks.x, qx, qy, qz);
+            // Sink1::seed at the associated scan point
+            const double dd = dist3e(qx, qy, qz, (double)S.px[hint], (double)S.py[hint], (double)S.pz[hint]);
+            if (dd == dd) { sd = dd; soi = S.orig[hint]; spos = hint; }
+            delta = home_box_delta(S, (int)(hint >> 5), qx, qy, qz);
         }
+        uint32_t out_pos = 0xffffffffu;
+        float out_g2 = 0.f;
+        // ---- the warp searches them one after another
+        unsigned todo = __ballot_sync(kFull, valid);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const double x = __shfl_sync(kFull, qx, src), y = __shfl_sync(kFull, qy, src), z = __shfl_sync(kFull, qz, src);
+            const uint32_t h = __shfl_sync(kFull, hint, src);
+            Sink1 nn;
+            nn.d = __shfl_sync(kFull, sd, src);
+            nn.oi = __shfl_sync(kFull, soi, src);
+            nn.pos = __shfl_sync(kFull, spos, src);
+            if (nn.pos != 0xffffffffu) nn.df = __double2float_ru(nn.d);
+            nn_near_leaf_seeded(S, pr.adj_r, (int)(h >> 5), x, y, z, nn, lane, __shfl_sync(kFull, delta, src));
+            if (lane == src) { out_pos = nn.pos; out_g2 = nn.g2; }
+            if (pr.use_plane && !pr.plane_index) {  // with the plane index the neighbourhood of nn is already fitted
+                const long long slot = qbase + (long long)(t0 + src) * sub + j;
+                SinkK kn(pr.k, pr.radius2);
+                knn_around_point(S, nn.pos, kn, lane);
+                wk.nb[slot * kMaxK + lane] = lane < kn.count ? kn.kpos : 0xffffffffu;
+                store_nb_coords(wk.nbx, wk.nbx_stride, slot, S, lane, kn.count, kn.kpos);
+                const double last = __shfl_sync(kFull, kn.kd, kn.count > 0 ? kn.count - 1 : 0);
+                if (lane == 0) { wk.nb_m[slot] = kn.count; wk.nb_last[slot] = last; }
+            }
+        }
+        if (valid) { wk.nn_pos[qbase + qi] = out_pos; wk.nn_g2[qbase + qi] = out_g2; }
     }
 }
 
@@ -244,7 +278,11 @@ cudaError_t launch_debug_trig(const double *d_x, int n, double *d_acos, double *
 
 cudaError_t launch_align3d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, int debug, cudaStream_t st, cudaEvent_t after_traversal) {
     if (B <= 0 || pk.n_kf <= 0) return cudaSuccess;
-    k_nn_knn<<<(unsigned)(pk.n_kf * B * wk.sub), kWarps * 32, 0, st>>>(pk, wk, pr, B);
+    // queries a warp draws at a time: the per-query preamble runs one query per lane, the searches one after another — a long
+    // batch is cheap in instructions and long in latency, so small keyframe shards (one wave of CTAs) get the short one
+    int batch = (long long)pk.n_kf * B >= 600 ? 8 : 4;
+    if (const char *e = getenv("STL_K2_BATCH")) batch = std::max(1, std::min(32, atoi(e)));
+    k_nn_knn<<<(unsigned)(pk.n_kf * B * wk.sub), kWarps * 32, 0, st>>>(pk, wk, pr, B, batch);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (after_traversal && (e = cudaEventRecord(after_traversal, st)) != cudaSuccess) return e;
