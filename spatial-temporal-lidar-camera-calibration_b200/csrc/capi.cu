@@ -315,7 +315,8 @@ stl_status_t enqueue_eval(stl_ctx *ctx, const double *x, int B, double *d_out, c
           else CK(launch_assoc2d_split(ctx->pk, ctx->wk, ctx->dpr, nb, ctx->k1_split_smem, 0, st)); }
         ctx->launches += ctx->k1_mono ? 0 : 2;
         if (marks) CK(cudaEventRecord(ctx->ev_k1, st));
-        { StageTimer t(ctx, STL_STAGE_KNN3D, st); CK(launch_align3d(ctx->pk, ctx->wk, ctx->dpr, nb, debug ? 1 : 0, st, marks ? ctx->ev_k2a : nullptr)); }
+        { StageTimer t(ctx, STL_STAGE_KNN3D, st); CK(launch_align3d(ctx->pk, ctx->wk, ctx->dpr, nb, debug ? 1 : 0, st, marks ? ctx->ev_k2a : nullptr,
+                                                                            marks ? ctx->lm.nnb_pos : nullptr, marks ? ctx->lm.nbb_m : nullptr)); }
         {
             StageTimer t(ctx, STL_STAGE_REDUCE, st);
             const P2pView pv = exchange ? p2p_view(ctx, nb, 0, STL_EVAL_NSUMS) : P2pView();
@@ -349,6 +350,8 @@ stl_status_t allreduce_record(stl_ctx *ctx, double *d_buf, size_t count, cudaStr
 
 // Enqueues BuildProblem at x0 on `st`.  The 2-D association (FindProjectCorrespondences) is taken from the
 // workspace when the preceding evaluation left the correspondences of exactly this x0 there, else K1 runs.
+// hint_ready: the association runs on a stream of its own beside the evaluation that (a) answers its map-point 1-NN
+// itself (K2a with lm_pos / lm_m: k_lm_knn_b is not launched) and (b) signals hint_ready behind K2a
 stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st, cudaEvent_t hint_ready = nullptr) {
     const DevPack &pk = ctx->pk;
     int slot = -1;
@@ -385,7 +388,7 @@ stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st, 
     if (hint_ready) {  // on a stream of its own: the part that needs K2a's answer waits for it, outside the stage timers
         { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint, g2, 1); }
         if (e == cudaSuccess) e = cudaStreamWaitEvent(st, hint_ready, 0);
-        if (e == cudaSuccess) { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st, false); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint, g2, 2); }
+        if (e == cudaSuccess) { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st, false); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint, g2, 2, true); }
     } else {
         StageTimer t(ctx, STL_STAGE_ASSOC_LM, st); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint, g2);
     }
@@ -1025,6 +1028,10 @@ static stl_status_t step_enqueue(stl_ctx *ctx, const double *x, int B, int reass
             CK(cudaEventCreateWithFlags(&ctx->ev_k3, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
         }
         cudaStream_t ax = ctx->aux_stream;
+        {   // K2a fills the association's 1-NN buffers: they must exist before it is launched
+            const cudaError_t e = lm_reserve(ctx->pk, ctx->dpr, ctx->lm, st);
+            if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "association buffers: %s", cudaGetErrorString(e));
+        }
         s = enqueue_eval(ctx, x, B, d_out, st, false, STL_STEP_NSUMS, false, nullptr, true);
         if (s != STL_OK) return s;
         CK(cudaStreamWaitEvent(ax, ctx->ev_k1, 0));

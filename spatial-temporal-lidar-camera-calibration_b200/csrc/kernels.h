@@ -127,8 +127,10 @@ cudaError_t launch_assoc2d_split(const DevPack &pk, const DevWork &wk, const Dev
 // ---- K2 (knn3d.cu) ---------------------------------------------------------------
 // K2a (traversal: 1-NN + k-NN, warp per query) then K2b (plane fit + distance, thread per query)
 // after_traversal (optional): recorded between K2a and K2b (nn_pos / nn_g2 are complete behind it)
+// lm_pos / lm_m (optional, plane index only): K2a also answers BuildProblem's 1-NN of the map points of candidate 0 (LmState::nnb_pos /
+// nbb_m), so that k_lm_knn_b need not run
 cudaError_t launch_align3d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, int debug, cudaStream_t st,
-                           cudaEvent_t after_traversal = nullptr);
+                           cudaEvent_t after_traversal = nullptr, uint32_t *lm_pos = nullptr, int *lm_m = nullptr);
 cudaError_t launch_knn3d(const DevPack &pk, int kf, const double *d_q, int nq, int k, double radius2, uint32_t *d_idx, double *d_d2,
                          int *d_cnt, cudaStream_t st);
 

@@ -52,7 +52,8 @@ __device__ __forceinline__ void map_point_lidar(const DevPack &pk, const DevKf &
 // of the kernel's instructions when every lane repeats them for the same query) is computed one query per LANE, then the warp
 // searches the queries one after another with those scalars broadcast.
 __global__ void __launch_bounds__(kWarps * 32, STL_KNN_MINB)
-k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B, const int batch) {
+k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B, const int batch, uint32_t *__restrict__ lm_pos,
+         int *__restrict__ lm_m) {
     const int sub = wk.sub;
     const int j = blockIdx.x % sub;
     const int bf = blockIdx.x / sub;
@@ -114,6 +115,51 @@ k_nn_knn(const DevPack pk, const DevWork wk, const DevParams pr, const int B, co
             }
         }
         if (valid) { wk.nn_pos[qbase + qi] = out_pos; wk.nn_g2[qbase + qi] = out_g2; }
+        // ---- one LM iteration at this extrinsic (stl_step_batch): BuildProblem asks for the 1-NN of the SAME map point scaled
+        // in fp64 (q', iba_local.cpp:283), a few micrometres from q.  Everything k_lm_knn_b would gather again is in registers
+        // here, so the question is settled on the spot — by the certificate (lm.cu: sqrt(g2) - |q - q'| > |q' - h|: every other
+        // point is strictly farther from q' than h), else by an exact search seeded with h — and that kernel is not launched.
+        if (lm_pos != nullptr && b == 0) {
+            double lx = 0, ly = 0, lz = 0, nn_d = DBL_MAX;
+            uint32_t nn_p = 0xffffffffu;
+            bool need = false;
+            if (valid) {
+                const float *Tcw = pk.Tcw + (long long)f * 12;
+                const float *mp = pk.kp_mp + (K.kp_off + wk.q_kpsp[cbase + qi].x) * 3;
+                const double ma = (double)mp[0], mb = (double)mp[1], mc = (double)mp[2];
+                const double Mx = dadd(dot3e((double)Tcw[0], (double)Tcw[1], (double)Tcw[2], ma, mb, mc), (double)Tcw[3]);
+                const double My = dadd(dot3e((double)Tcw[4], (double)Tcw[5], (double)Tcw[6], ma, mb, mc), (double)Tcw[7]);
+                const double Mz = dadd(dot3e((double)Tcw[8], (double)Tcw[9], (double)Tcw[10], ma, mb, mc), (double)Tcw[11]);
+                xform(c.Ri, c.ti, dmul(Mx, c.s), dmul(My, c.s), dmul(Mz, c.s), lx, ly, lz);  // initSE3.inverse() * (MapPoint * init_scale)
+                need = true;
+                if (out_pos != 0xffffffffu) {
+                    const double move = sqrt(dist3e(qx, qy, qz, lx, ly, lz)) * (1.0 + 1e-9) + 1e-12;  // |q - q'|, rounded up
+                    const double dh = dist3e(lx, ly, lz, (double)S.px[out_pos], (double)S.py[out_pos], (double)S.pz[out_pos]);
+                    const double reach = (double)__fsqrt_rd(out_g2) - move;                          // every other point is at least this far from q'
+                    if (reach > 0.0 && reach * reach > dh * (1.0 + 1e-6) + 1e-18) { need = false; nn_p = out_pos; nn_d = dh; }
+                }
+            }
+            unsigned todo2 = __ballot_sync(kFull, need);
+            while (todo2) {
+                const int src = __ffs(todo2) - 1;
+                todo2 &= todo2 - 1;
+                const double x = __shfl_sync(kFull, lx, src), y = __shfl_sync(kFull, ly, src), z = __shfl_sync(kFull, lz, src);
+                uint32_t h = __shfl_sync(kFull, out_pos, src);
+                if (h == 0xffffffffu) h = __shfl_sync(kFull, hint, src);
+                Sink1 nn;
+                nn_near_leaf(S, pr.adj_r, (int)(h >> 5), x, y, z, nn, lane, h);
+                if (lane == src) { nn_p = nn.pos; nn_d = nn.d; }
+            }
+            if (valid) {
+                const long long slot = K.mp_off + qi;
+                if (nn_d > pr.max_3d_dist2) {  // iba_local.cpp:289
+                    lm_pos[slot] = 0xffffffffu;
+                } else {
+                    lm_pos[slot] = nn_p;
+                    lm_m[slot] = nn_p == hint ? -2 : -3;  // the associated scan point itself (its plane is known) / looked up by k_lm_plane_b
+                }
+            }
+        }
     }
 }
 
@@ -276,13 +322,14 @@ cudaError_t launch_debug_trig(const double *d_x, int n, double *d_acos, double *
     return cudaGetLastError();
 }
 
-cudaError_t launch_align3d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, int debug, cudaStream_t st, cudaEvent_t after_traversal) {
+cudaError_t launch_align3d(const DevPack &pk, const DevWork &wk, const DevParams &pr, int B, int debug, cudaStream_t st, cudaEvent_t after_traversal,
+                           uint32_t *lm_pos, int *lm_m) {
     if (B <= 0 || pk.n_kf <= 0) return cudaSuccess;
     // queries a warp draws at a time: the per-query preamble runs one query per lane, the searches one after another — a long
     // batch is cheap in instructions and long in latency, so small keyframe shards (one wave of CTAs) get the short one
     int batch = (long long)pk.n_kf * B >= 600 ? 8 : 4;
     if (const char *e = getenv("STL_K2_BATCH")) batch = std::max(1, std::min(32, atoi(e)));
-    k_nn_knn<<<(unsigned)(pk.n_kf * B * wk.sub), kWarps * 32, 0, st>>>(pk, wk, pr, B, batch);
+    k_nn_knn<<<(unsigned)(pk.n_kf * B * wk.sub), kWarps * 32, 0, st>>>(pk, wk, pr, B, batch, lm_pos, lm_m);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (after_traversal && (e = cudaEventRecord(after_traversal, st)) != cudaSuccess) return e;

@@ -729,8 +729,9 @@ void lm_free(LmState &lm) {
 // Enqueues BuildProblem on `st` and returns without waiting: the block counts stay on the device
 // (d_counts: plane, 3-D, point-to-point, GPR), where the linearisation kernels read them; a copy lands
 // in pinned host memory behind `counts_done` for callers that want the numbers (lm_block_counts).
-cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st, const uint32_t *nn_hint,
-                         const float *nn_g2, int part) {
+// The buffers of an association (sized by the pack): allocated on the first association, or ahead of it by a caller that
+// wants LmState::nnb_pos / nbb_m filled by K2a.
+cudaError_t lm_reserve(const DevPack &pk, const DevParams &pr, LmState &lm, cudaStream_t st) {
     cudaError_t e;
 #define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
     const long long ns = pk.n_kp_total > 0 ? pk.n_kp_total : 1;
@@ -760,6 +761,16 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
         lm.n_slots = ns;
         lm.max_blocks = nm;
     }
+#undef TRY
+    return cudaSuccess;
+}
+
+cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st, const uint32_t *nn_hint,
+                         const float *nn_g2, int part, bool nn_folded) {
+    cudaError_t e;
+#define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
+    const long long ns = pk.n_kp_total > 0 ? pk.n_kp_total : 1;
+    TRY(lm_reserve(pk, pr, lm, st));
     if (part != 2) {
     lm.ready = false;
     lm.sub = wk.sub;
@@ -770,7 +781,7 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
     TRY(cudaGetLastError());
     }
     if (part == 1) return cudaSuccess;
-    k_lm_knn_b<<<(unsigned)(pk.n_kf * lm.sub), kWarps * 32, 0, st>>>(pk, wk, pr, lm, nn_hint, nn_g2);
+    if (!nn_folded) k_lm_knn_b<<<(unsigned)(pk.n_kf * lm.sub), kWarps * 32, 0, st>>>(pk, wk, pr, lm, nn_hint, nn_g2);  // else K2a has filled nnb_pos / nbb_m
     k_lm_plane_b<<<(unsigned)(pk.n_kf * lm.sub), 128, 0, st>>>(pk, wk, pr, lm);
     TRY(cudaGetLastError());
     cub::CountingInputIterator<int> it(0);

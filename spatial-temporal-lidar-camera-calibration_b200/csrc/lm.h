@@ -63,7 +63,9 @@ void lm_free(LmState &lm);
 // part: 0 = everything; 1 = up to the plane at the associated scan point (needs K1's result only); 2 = the rest (needs nn_hint /
 // nn_g2, i.e. K2a, when given) — the overlapped step enqueues the two parts around a wait for K2a
 cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st,
-                         const uint32_t *nn_hint = nullptr, const float *nn_g2 = nullptr, int part = 0);
+                         const uint32_t *nn_hint = nullptr, const float *nn_g2 = nullptr, int part = 0, bool nn_folded = false);
+// nn_folded: LmState::nnb_pos / nbb_m were written by K2a (launch_align3d with lm_pos / lm_m): k_lm_knn_b is not launched
+cudaError_t lm_reserve(const DevPack &pk, const DevParams &pr, LmState &lm, cudaStream_t st);
 // x: HOST [B][7]; d_out: DEVICE [B][STL_LIN_NSUMS]
 // optional per-block output of a linearisation (device pointers; B must be 1)
 struct BlockOut {
