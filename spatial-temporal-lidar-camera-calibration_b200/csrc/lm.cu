@@ -125,7 +125,7 @@ k_lm_plane_a(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
         const PlaneOut po = from_index ? plane_lookup(pk, K, sp)
                                        : plane_fit(NbCoords{wk.nbx + slot, wk.nbx_stride}, m, wk.nb_last[slot], cx, cy, cz, pr);
         if (!po.gates_ok) continue;  // m < min_pts || d2[m-1] < min_diff^2 (pointcloud.h:754)
-        const long long cs = K.kp_off + ci;  // block slot = correspondence slot
+        const long long cs = slot;  // block slot = query slot (the only keypoints that can carry a block are those with a map point)
         lm.slot_kf[cs] = f;
         lm.slot_kp[cs] = kp;
         double *pa = lm.plane_a + slot * 4;
@@ -255,7 +255,7 @@ k_lm_plane_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
         if (np == 0xffffffffu) continue;
         const uint32_t ci = wk.q_corr[K.kp_off + qi];
         const uint32_t kp = wk.corr_kp[K.kp_off + ci];
-        const long long cs = K.kp_off + ci;
+        const long long cs = slot;
         const double nx = (double)S.px[np], ny = (double)S.py[np], nz = (double)S.pz[np];
         bool gates_ok, state;
         double n3[3];
@@ -734,7 +734,9 @@ void lm_free(LmState &lm) {
 cudaError_t lm_reserve(const DevPack &pk, const DevParams &pr, LmState &lm, cudaStream_t st) {
     cudaError_t e;
 #define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
-    const long long ns = pk.n_kp_total > 0 ? pk.n_kp_total : 1;
+    // block slots = query slots: one per map-point-carrying keypoint (a twelfth of the keypoints at the KITTI-00 shape), so the
+    // flag arrays the selects compact, and the per-block geometry, are that much smaller than one-per-keypoint arrays
+    const long long ns = pk.n_mp_total > 0 ? pk.n_mp_total : 1;
     if (lm.n_slots != ns) {
         lm_free(lm);  // n_slots stays 0 until every allocation below succeeded: a failure midway starts over next time
         TRY(cudaMalloc(&lm.slot_kf, 4 * ns)); TRY(cudaMalloc(&lm.slot_kp, 4 * ns));
@@ -769,7 +771,7 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
                          const float *nn_g2, int part, bool nn_folded) {
     cudaError_t e;
 #define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
-    const long long ns = pk.n_kp_total > 0 ? pk.n_kp_total : 1;
+    const long long ns = pk.n_mp_total > 0 ? pk.n_mp_total : 1;
     TRY(lm_reserve(pk, pr, lm, st));
     if (part != 2) {
     lm.ready = false;

@@ -5,7 +5,7 @@
 namespace stl {
 
 // Residual blocks frozen by stl_associate (BuildProblem, src/examples/iba_local.cpp:145-323).
-// One slot per 2-D correspondence of the association pass (slot = kp_off[kf] + i); dense index
+// One slot per map-point-carrying correspondence of the association pass (slot = mp_off[kf] + qi); dense index
 // lists select the slots that carry a 3-D/2-D block (IBA_PlaneFactor) and a 3-D/3-D block
 // (Point2Point_Factor / Point2Plane_Factor).
 struct LmState {
