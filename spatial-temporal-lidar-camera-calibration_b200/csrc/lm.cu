@@ -285,6 +285,30 @@ struct Acc {
     double v[kLinVals];
 };
 
+// D7 with the PARTIALS formed by fused multiply-adds (the values keep the reference's separate multiply and add, so costs
+// and the robust-kernel branch are bit-identical to the plain-D7 evaluation; a partial differs from the Jet's by one
+// rounding, 1e-16 relative, on these well-conditioned blocks).  Same layout as D7: the candidate's Sim3Exp duals are read
+// as F7.  Used by k_linearize only — the GPR blocks (cond ~1e12) stay on D7, operation for operation.
+struct F7 {
+    double a;
+    double v[7];
+};
+static_assert(sizeof(F7) == sizeof(D7), "F7 views D7 storage");
+__device__ __forceinline__ F7 f7_const(double x) { F7 r; r.a = x; for (int i = 0; i < 7; ++i) r.v[i] = 0.0; return r; }
+__device__ __forceinline__ F7 operator+(const F7 &f, const F7 &g) { F7 r; r.a = f.a + g.a; for (int i = 0; i < 7; ++i) r.v[i] = f.v[i] + g.v[i]; return r; }
+__device__ __forceinline__ F7 operator-(const F7 &f, const F7 &g) { F7 r; r.a = f.a - g.a; for (int i = 0; i < 7; ++i) r.v[i] = f.v[i] - g.v[i]; return r; }
+__device__ __forceinline__ F7 operator*(const F7 &f, const F7 &g) { F7 r; r.a = f.a * g.a; for (int i = 0; i < 7; ++i) r.v[i] = fma(f.a, g.v[i], f.v[i] * g.a); return r; }
+__device__ __forceinline__ F7 operator/(const F7 &f, const F7 &g) {
+    F7 r;
+    const double gi = 1.0 / g.a, q = f.a * gi;
+    r.a = q;
+    for (int i = 0; i < 7; ++i) r.v[i] = fma(-q, g.v[i], f.v[i]) * gi;
+    return r;
+}
+__device__ __forceinline__ F7 operator*(const F7 &f, double c) { F7 r; r.a = f.a * c; for (int i = 0; i < 7; ++i) r.v[i] = f.v[i] * c; return r; }
+__device__ __forceinline__ F7 operator+(const F7 &f, double c) { F7 r = f; r.a = f.a + c; return r; }
+__device__ __forceinline__ F7 operator-(const F7 &f, double c) { F7 r = f; r.a = f.a - c; return r; }
+
 __device__ __forceinline__ void huber(double sq, double delta, double &rho0, double &sr) {
     if (sq > delta * delta) {  // ceres::HuberLoss::Evaluate
         const double r = sqrt(sq);
@@ -314,11 +338,29 @@ __device__ __forceinline__ void mv3(const D7 *M, const D7 *p, D7 *o) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) o[i] = (M[i * 3] * p[0] + M[i * 3 + 1] * p[1]) + M[i * 3 + 2] * p[2];
 }
+__device__ __forceinline__ void mv3(const F7 *M, const F7 *p, F7 *o) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[i] = (M[i * 3] * p[0] + M[i * 3 + 1] * p[1]) + M[i * 3 + 2] * p[2];
+}
+__device__ __forceinline__ void accumulate(Acc &A, const F7 &e, double sr) {
+    const double r = sr * e.a;
+    double J[7];
+#pragma unroll
+    for (int a = 0; a < 7; ++a) J[a] = sr * e.v[a];
+    int h = 8;
+#pragma unroll
+    for (int a = 0; a < 7; ++a) {
+        A.v[1 + a] = fma(J[a], r, A.v[1 + a]);
+#pragma unroll
+        for (int b = a; b < 7; ++b) { A.v[h] = fma(J[a], J[b], A.v[h]); ++h; }
+    }
+}
 
 // Optional per-block output (stl_eval_blocks): what a Ceres CostFunction::Evaluate / a g2o edge would
 // return for each frozen residual block — raw residuals and their 7-column Jacobian rows, no robust
 // kernel (the solver applies its own loss).  Fixed stride of rmax rows per block.
-__device__ __forceinline__ void put_row(const BlockOut &o, long long blk, int r, const D7 &e) {
+template <class T7>
+__device__ __forceinline__ void put_row(const BlockOut &o, long long blk, int r, const T7 &e) {
     o.res[blk * o.rmax + r] = e.a;
     double *j = o.jac + (blk * o.rmax + r) * 7;
 #pragma unroll
@@ -340,6 +382,9 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
         for (int i = threadIdx.x; i < (int)(sizeof(LmCand) / 8); i += kLinThreads) dst[i] = src[i];
     }
     __syncthreads();
+    const F7 *cR = reinterpret_cast<const F7 *>(c.R), *ct = reinterpret_cast<const F7 *>(c.t);
+    const F7 *cRlc = reinterpret_cast<const F7 *>(c.Rlc), *ctlc = reinterpret_cast<const F7 *>(c.tlc);
+    const F7 &cs7 = *reinterpret_cast<const F7 *>(&c.s);
     Acc A;
 #pragma unroll
     for (int i = 0; i < kLinVals; ++i) A.v[i] = 0.0;
@@ -357,17 +402,17 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
         const double fx = K.fx, fy = K.fy, cx = K.cx, cy = K.cy;
         const float2 kxy = pk.kp_xy[K.kp_off + kp];
         const double *g = lm.geo2d + (long long)slot * 6;
-        const D7 p0[3] = {d7_const(g[0]), d7_const(g[1]), d7_const(g[2])}, n0[3] = {d7_const(g[3]), d7_const(g[4]), d7_const(g[5])};
-        D7 p0c[3], n0c[3];
-        mv3(c.R, p0, p0c);
+        const F7 p0[3] = {f7_const(g[0]), f7_const(g[1]), f7_const(g[2])}, n0[3] = {f7_const(g[3]), f7_const(g[4]), f7_const(g[5])};
+        F7 p0c[3], n0c[3];
+        mv3(cR, p0, p0c);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) p0c[i] = p0c[i] + c.t[i];
-        mv3(c.R, n0, n0c);
+        for (int i = 0; i < 3; ++i) p0c[i] = p0c[i] + ct[i];
+        mv3(cR, n0, n0c);
         const double Cxz = ((double)kxy.x - cx) / fx, Cyz = ((double)kxy.y - cy) / fy;
-        const D7 num = (n0c[0] * p0c[0] + n0c[1] * p0c[1]) + n0c[2] * p0c[2];
-        const D7 den = (n0c[0] * Cxz + n0c[1] * Cyz) + n0c[2];
-        const D7 Z0 = num / den;
-        const D7 P0[3] = {Z0 * Cxz, Z0 * Cyz, Z0};
+        const F7 num = (n0c[0] * p0c[0] + n0c[1] * p0c[1]) + n0c[2] * p0c[2];
+        const F7 den = (n0c[0] * Cxz + n0c[1] * Cyz) + n0c[2];
+        const F7 Z0 = num / den;
+        const F7 P0[3] = {Z0 * Cxz, Z0 * Cyz, Z0};
         // pass 1: squared norm of the block (values only) for the robust kernel
         double sq = 0.0;
         int nres = 0;
@@ -397,12 +442,12 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
             const float2 uv = pk.covis_uv[(K.kp_off + kp) * C + s];
             if (isnan(uv.x)) continue;
             const float *rp = pk.relpose + ((long long)f * C + s) * 12;
-            D7 P1[3];
+            F7 P1[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i)
-                P1[i] = ((P0[0] * (double)rp[i * 4] + P0[1] * (double)rp[i * 4 + 1]) + P0[2] * (double)rp[i * 4 + 2]) + c.s * (double)rp[i * 4 + 3];
-            const D7 eu = ((P1[0] * fx) / P1[2] + cx) - (double)uv.x;
-            const D7 ev = ((P1[1] * fy) / P1[2] + cy) - (double)uv.y;
+                P1[i] = ((P0[0] * (double)rp[i * 4] + P0[1] * (double)rp[i * 4 + 1]) + P0[2] * (double)rp[i * 4 + 2]) + cs7 * (double)rp[i * 4 + 3];
+            const F7 eu = ((P1[0] * fx) / P1[2] + cx) - (double)uv.x;
+            const F7 ev = ((P1[1] * fy) / P1[2] + cy) - (double)uv.y;
             accumulate(A, eu, sr);
             accumulate(A, ev, sr);
             if (WB) { put_row(bo, it, wrow, eu); put_row(bo, it, wrow + 1, ev); wrow += 2; }
@@ -414,12 +459,12 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
     for (int it = t0; it < n3d; it += stride) {
         const int slot = lm.idx3d[it];
         const double *g = lm.geo3d + (long long)slot * 9;
-        const D7 Ms[3] = {c.s * g[0], c.s * g[1], c.s * g[2]};  // MapPoint * s
-        D7 M[3];
-        mv3(c.Rlc, Ms, M);
+        const F7 Ms[3] = {cs7 * g[0], cs7 * g[1], cs7 * g[2]};  // MapPoint * s
+        F7 M[3];
+        mv3(cRlc, Ms, M);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) M[i] = M[i] + c.tlc[i];
-        const D7 d[3] = {M[0] - g[3], M[1] - g[4], M[2] - g[5]};
+        for (int i = 0; i < 3; ++i) M[i] = M[i] + ctlc[i];
+        const F7 d[3] = {M[0] - g[3], M[1] - g[4], M[2] - g[5]};
         double rho0, sr;
         if (lm.type3d[slot] == 1) {
             huber((d[0].a * d[0].a + d[1].a * d[1].a) + d[2].a * d[2].a, pr.delta3d, rho0, sr);
@@ -434,7 +479,7 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
                 put_head(bo, blk, 1, lm.slot_kf[slot], lm.slot_kp[slot], 3);
             }
         } else {
-            const D7 e = (d[0] * g[6] + d[1] * g[7]) + d[2] * g[8];
+            const F7 e = (d[0] * g[6] + d[1] * g[7]) + d[2] * g[8];
             huber(e.a * e.a, pr.delta3d, rho0, sr);
             accumulate(A, e, sr);
             A.v[38] += 1.0;
