@@ -991,7 +991,10 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
     // the exact counts from the device
     const long long work = lm.max_blocks;
     long long chunks_ll = (work + kLinThreads * 2 - 1) / (kLinThreads * 2);
-    int chunks = (int)(chunks_ll < 1 ? 1 : (chunks_ll > 148 * 8 ? 148 * 8 : chunks_ll));
+    // at most ONE wave of CTAs per candidate (2 CTAs of 255 registers per SM): 296 chunks measured 0.134 ms against 0.140 (592),
+    // 0.163 (444: a wave and a half) and 0.157 (1184) at the KITTI-00 shape, and the finishing kernel sums four times fewer partials
+    static const int kChunkCap = getenv("STL_LIN_CHUNKS") ? atoi(getenv("STL_LIN_CHUNKS")) : 148 * 2;
+    int chunks = (int)(chunks_ll < 1 ? 1 : (chunks_ll > kChunkCap ? kChunkCap : chunks_ll));
     const long long gwork = lm.use_gpr ? lm.max_blocks : 0;
     long long gchunks_ll = gwork > 0 ? (gwork + 3) / 4 : 0;
     int gchunks = (int)(gchunks_ll > 148 * 8 ? 148 * 8 : gchunks_ll);
