@@ -1,10 +1,1 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --config c4 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/r02x_c4.json 2> gpurun_out/r02x_c4.err; tail -3 gpurun_out/r02x_c4.err
-STL_LIN_CHUNKS=1184 python bench.py --config c4 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/r02x_c4_1184.json 2> gpurun_out/r02x_c4_1184.err
-python bench.py --nkf 188 --steps 40 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r02x_c2_188.json 2> gpurun_out/r02x_c2_188.err
-python - <<'PY'
-import json
-for n in ('r02x_c4','r02x_c4_1184','r02x_c2_188'):
-    d=json.load(open(f'gpurun_out/{n}.json'))
-    print(n,'value',round(d['value'],1),'ms',round(d['ms_per_step'],4),'e2e',round(d['e2e']['value'],1),d['stage_ms_per_launch'])
-PY
+bash scripts/ab_lib.sh scripts/ab/lib_minb8.so scripts/ab/lib_minb6.so scripts/ab/lib_minb5.so

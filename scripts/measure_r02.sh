@@ -11,10 +11,11 @@ if [ "$N" = "1" ]; then
   done
   python bench.py --impl reference --steps 5 --warmup 1 > $O/r02_bench_reference_c2.json 2> $O/r02_bench_reference_c2.err
   ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > $O/r02_launches_bench.log 2>&1
-  for spec in "k1:k_assoc2d:2" "k2:k_nn_knn:2" "lm:k_lm_knn_b:2" "lin:k_linearize:2" "k0:k_kd_refine:1" "kidx:k_index_knn:3"; do
+  for spec in "k1:k_assoc2d:2" "k2:k_nn_knn:2" "lm:k_lm_plane_b:2" "lin:k_linearize:2" "k0:k_kd_refine:1" "kidx:k_index_knn:3"; do
     IFS=: read name pat skip <<< "$spec"
     ncu --set full --clock-control none --import-source on -k regex:$pat -s $skip -c 1 -o $O/r02_${name}_full -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > $O/r02_ncu_$name.log 2>&1
   done
+  ncu -i $O/r02_k1_full.ncu-rep --page source --csv --print-source sass > $O/r02_k1_src.csv 2>/dev/null
   ncu --set full --clock-control none -k regex:k_assoc2d -s 6 -c 1 -o $O/r02_k1poll_full -f python bench.py --config c4 --steps 1 --warmup 1 --no-cpu-baseline > $O/r02_ncu_k1poll.log 2>&1
 else
   for c in c2 c4 c3; do
