@@ -297,7 +297,12 @@ stl_status_t stl_block_counts(stl_ctx_t *ctx, int64_t n_blocks[4]);
  *      (FindProjectCorrespondences at the same extrinsic, iba_global.cpp:201 == iba_local.cpp:191)
  *   3. cost, J^T r, J^T J of the frozen blocks at x[0..B)                  (as stl_linearize_batch)
  * Nothing waits on the host between the stages; with a communicator attached the [B][74] record is
- * all-reduced ONCE.  out[b] = {eval sums, linearisation} of candidate b. */
+ * all-reduced ONCE.  out[b] = {eval sums, linearisation} of candidate b.
+ * With the plane index (the default) stages 2 and 3 run on a second stream of the context beside the 3-D stage of
+ * step 1 — BuildProblem needs the 2-D association and the map-point 1-NN of step 1, not its sums — and the map-point
+ * 1-NN of BuildProblem is answered inside step 1's search kernel; both streams are joined before the call returns
+ * its stream to the caller, so the ordering a caller sees is that of ONE stream.  Same bits as the three calls made
+ * one after another. */
 stl_status_t stl_step_batch(stl_ctx_t *ctx, const double *x, int32_t B, int32_t reassociate, stl_step_sums_t *out);
 /* Same; the [B][STL_STEP_NSUMS] record stays in DEVICE memory `d_out` on `stream`, no synchronisation. */
 stl_status_t stl_step_batch_device(stl_ctx_t *ctx, const double *x, int32_t B, int32_t reassociate, double *d_out, void *stream);

@@ -369,6 +369,7 @@ stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st, 
         if (ctx->wk_has_nn) { nn_hint = ctx->wk.nn_pos + slot * pk.n_mp_total; nn_g2 = ctx->wk.nn_g2 + slot * pk.n_mp_total; }  // K2a's 1-NN of the same map points at this x
         ctx->assoc_reused += 1;
     } else {
+        if (hint_ready) return fail(ctx, STL_ERR_STATE, "overlapped step: the evaluation's correspondences are not in the workspace");
         DevCand *hc = ctx->h_cand;
         if (!ctx->h2d_done) CK(cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming));
         CK(cudaEventSynchronize(ctx->h2d_done));
