@@ -389,7 +389,7 @@ stl_status_t enqueue_associate(stl_ctx *ctx, const double *x0, cudaStream_t st, 
     if (hint_ready) {  // on a stream of its own: the part that needs K2a's answer waits for it, outside the stage timers
         { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint, g2, 1); }
         if (e == cudaSuccess) e = cudaStreamWaitEvent(st, hint_ready, 0);
-        if (e == cudaSuccess) { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st, false); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint, g2, 2, true); }
+        if (e == cudaSuccess) { StageTimer t(ctx, STL_STAGE_ASSOC_LM, st, false); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint, g2, 2, true, true); }
     } else {
         StageTimer t(ctx, STL_STAGE_ASSOC_LM, st); e = lm_associate(pk, view, ctx->dpr, ctx->lm, st, nn_hint, g2);
     }
@@ -989,12 +989,12 @@ stl_status_t stl_block_counts(stl_ctx_t *ctx, int64_t n_blocks[4]) {
 // exch_off / exch_width: the record k_lin_finish completes starts exch_off doubles from its own output row and is exch_width
 // long (0: no exchange); *exchanged as in enqueue_eval
 static stl_status_t lin_enqueue(stl_ctx *ctx, const double *x, int B, double *d_out, cudaStream_t st, int out_stride = STL_LIN_NSUMS,
-                                int exch_off = 0, int exch_width = 0, bool *exchanged = nullptr, cudaEvent_t before_finish = nullptr) {
+                                int exch_off = 0, int exch_width = 0, bool *exchanged = nullptr, cudaEvent_t before_finish = nullptr, bool cand_staged = false) {
     if (!ctx->lm.ready) return fail(ctx, STL_ERR_STATE, "stl_associate has not been called");
     cudaError_t e;
     const P2pView pv = exch_width > 0 ? p2p_view(ctx, B, exch_off, exch_width) : P2pView();
     if (exchanged) *exchanged = pv.n > 1;
-    { StageTimer t(ctx, STL_STAGE_LINEARIZE, st); e = lm_linearize(ctx->pk, ctx->dpr, ctx->lm, x, B, d_out, st, nullptr, out_stride, &pv, before_finish); }
+    { StageTimer t(ctx, STL_STAGE_LINEARIZE, st); e = lm_linearize(ctx->pk, ctx->dpr, ctx->lm, x, B, d_out, st, nullptr, out_stride, &pv, before_finish, cand_staged); }
     if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "linearize: %s", cudaGetErrorString(e));
     ctx->launches += 2 + (ctx->lm.use_gpr ? 1 : 0);  // k_linearize, (k_linearize_gpr,) k_lin_finish
     return STL_OK;
@@ -1036,9 +1036,14 @@ static stl_status_t step_enqueue(stl_ctx *ctx, const double *x, int B, int reass
         s = enqueue_eval(ctx, x, B, d_out, st, false, STL_STEP_NSUMS, false, nullptr, true);
         if (s != STL_OK) return s;
         CK(cudaStreamWaitEvent(ax, ctx->ev_k1, 0));
+        {   // the candidates' duals go to the device now, not between the association and the linearisation
+            const cudaError_t e = lm_stage_candidates(ctx->lm, x, B, ax);
+            if (e != cudaSuccess) return fail(ctx, STL_ERR_CUDA, "candidate staging: %s", cudaGetErrorString(e));
+        }
         s = enqueue_associate(ctx, x, ax, ctx->ev_k2a);
         bool done = false;
-        if (s == STL_OK) s = lin_enqueue(ctx, x, B, d_out + STL_EVAL_NSUMS, ax, STL_STEP_NSUMS, -STL_EVAL_NSUMS, STL_STEP_NSUMS, &done, ctx->ev_k3);
+        if (s == STL_OK) s = lin_enqueue(ctx, x, B, d_out + STL_EVAL_NSUMS, ax, STL_STEP_NSUMS, -STL_EVAL_NSUMS, STL_STEP_NSUMS, &done, ctx->ev_k3, true);
+        if (s == STL_OK && lm_copy_counts(ctx->lm, ax) != cudaSuccess) s = fail(ctx, STL_ERR_CUDA, "block-count read-back");  // deferred by the association
         // whatever happened, the caller's stream is not released before the second stream has drained
         cudaEventRecord(ctx->ev_aux, ax);
         cudaStreamWaitEvent(st, ctx->ev_aux, 0);

@@ -813,7 +813,7 @@ cudaError_t lm_reserve(const DevPack &pk, const DevParams &pr, LmState &lm, cuda
 }
 
 cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st, const uint32_t *nn_hint,
-                         const float *nn_g2, int part, bool nn_folded) {
+                         const float *nn_g2, int part, bool nn_folded, bool defer_counts) {
     cudaError_t e;
 #define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
     const long long ns = pk.n_mp_total > 0 ? pk.n_mp_total : 1;
@@ -841,12 +841,22 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
         TRY(cub::DeviceSelect::Flagged(lm.d_tmp, tb, it, lm.flagG, lm.idxG, lm.d_counts + 3, (int)ns, st));
     }
     TRY(cudaGetLastError());
-    TRY(cudaMemcpyAsync(lm.h_counts, lm.d_counts, 16, cudaMemcpyDeviceToHost, st));
-    TRY(cudaEventRecord(lm.counts_done, st));
+    if (!defer_counts) {
+        TRY(cudaMemcpyAsync(lm.h_counts, lm.d_counts, 16, cudaMemcpyDeviceToHost, st));
+        TRY(cudaEventRecord(lm.counts_done, st));
+    }
     lm.counts_valid = false;
     lm.use_gpr = pr.use_gpr != 0;
     lm.ready = true;
     return cudaSuccess;
+}
+
+// The read-back of the block counts, for a caller that deferred it (lm_associate with defer_counts) to get it out of the
+// way of the linearisation that follows the association on the same stream.
+cudaError_t lm_copy_counts(LmState &lm, cudaStream_t st) {
+    cudaError_t e = cudaMemcpyAsync(lm.h_counts, lm.d_counts, 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(lm.counts_done, st);
+    return e;
 }
 
 // Host copy of the block counts of the last association (waits for it to finish).
@@ -967,8 +977,9 @@ cudaError_t lm_get_gpr_hyper(const DevParams &pr, LmState &lm, double *out, cuda
     return e;
 }
 
-cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
-                         const BlockOut *blocks, int out_stride, const P2pView *p2p, cudaEvent_t before_finish) {
+// Sim3Exp / SE3Exp duals of the B parameter vectors, host -> device: the first thing lm_linearize does, or — ahead of it — a
+// caller that has other work to put on the stream in between (the overlapped step)
+cudaError_t lm_stage_candidates(LmState &lm, const double *x, int B, cudaStream_t st) {
     cudaError_t e;
 #define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
     if (B > lm.cand_cap) {
@@ -985,6 +996,15 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
     for (int b = 0; b < B; ++b) make_lm_candidate(x + (size_t)b * 7, hc + b);
     TRY(cudaMemcpyAsync(lm.d_cand, hc, sizeof(LmCand) * B, cudaMemcpyHostToDevice, st));
     TRY(cudaEventRecord(lm.h2d_done, st));
+#undef TRY
+    return cudaSuccess;
+}
+
+cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
+                         const BlockOut *blocks, int out_stride, const P2pView *p2p, cudaEvent_t before_finish, bool cand_staged) {
+    cudaError_t e;
+#define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
+    if (!cand_staged) TRY(lm_stage_candidates(lm, x, B, st));
     // grids are sized from the host-side upper bound of the block count (one block per map-point-carrying
     // keypoint at most) — never from the counts themselves, so that the chunking, and with it the order
     // of the fp64 sums, is the same whether or not the host has looked at the counts; the kernels read

@@ -63,7 +63,11 @@ void lm_free(LmState &lm);
 // part: 0 = everything; 1 = up to the plane at the associated scan point (needs K1's result only); 2 = the rest (needs nn_hint /
 // nn_g2, i.e. K2a, when given) — the overlapped step enqueues the two parts around a wait for K2a
 cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &pr, LmState &lm, cudaStream_t st,
-                         const uint32_t *nn_hint = nullptr, const float *nn_g2 = nullptr, int part = 0, bool nn_folded = false);
+                         const uint32_t *nn_hint = nullptr, const float *nn_g2 = nullptr, int part = 0, bool nn_folded = false,
+                         bool defer_counts = false);
+// defer_counts: the block-count read-back is left to lm_copy_counts (after whatever the caller enqueues next)
+cudaError_t lm_copy_counts(LmState &lm, cudaStream_t st);
+cudaError_t lm_stage_candidates(LmState &lm, const double *x, int B, cudaStream_t st);
 // nn_folded: LmState::nnb_pos / nbb_m were written by K2a (launch_align3d with lm_pos / lm_m): k_lm_knn_b is not launched
 cudaError_t lm_reserve(const DevPack &pk, const DevParams &pr, LmState &lm, cudaStream_t st);
 // x: HOST [B][7]; d_out: DEVICE [B][STL_LIN_NSUMS]
@@ -77,7 +81,9 @@ struct BlockOut {
 
 // out_stride: doubles between the records of consecutive candidates in d_out (0 = STL_LIN_NSUMS)
 cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
-                         const BlockOut *blocks = nullptr, int out_stride = 0, const P2pView *p2p = nullptr, cudaEvent_t before_finish = nullptr);
+                         const BlockOut *blocks = nullptr, int out_stride = 0, const P2pView *p2p = nullptr, cudaEvent_t before_finish = nullptr,
+                         bool cand_staged = false);
+// cand_staged: the caller has already run lm_stage_candidates(lm, x, B, st) for exactly these x on this stream
 // before_finish (optional): event the finishing kernel waits for (the rest of the record it completes / exchanges)
 // waits for the last association and mirrors its block counts into lm.n2d / n3d / nG / n_blocks
 cudaError_t lm_block_counts(LmState &lm);
