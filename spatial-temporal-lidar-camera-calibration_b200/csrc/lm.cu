@@ -240,43 +240,60 @@ k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm, c
     }
 }
 
-// L4: ComputeLocalNormalSingleThre at the map point's neighbour (pointcloud.h:699-717,651-666) -> 3-D/3-D block
+// L4: ComputeLocalNormalSingleThre at the map point's neighbour (pointcloud.h:699-717,651-666) -> 3-D/3-D block.
+// Geometry of the 3-D/3-D block of query slot `slot` (keyframe f, keypoint kp): g = map point (camera frame, unscaled), its
+// nearest scan point, the plane normal there; type 1 = Point2Point_Factor, 2 = Point2Plane_Factor (iba_local.cpp:300-309).
+// False: the slot carries no such block.  Shared by k_lm_plane_b (which freezes it) and the fused step (which linearises the
+// block on the spot, from the same numbers).
+__device__ __forceinline__ bool block3d_geometry(const DevPack &pk, const DevParams &pr, const LmState &lm, long long slot, int f, uint32_t kp,
+                                                 double g[9], int &type) {
+    if (lm.stage[slot] != 1) return false;
+    const uint32_t np = lm.nnb_pos[slot];
+    if (np == 0xffffffffu) return false;
+    const DevKf &K = pk.kf[f];
+    const float *sx = pk.px + K.pt_off, *sy = pk.py + K.pt_off, *sz = pk.pz + K.pt_off;
+    const double nx = (double)sx[np], ny = (double)sy[np], nz = (double)sz[np];
+    bool gates_ok, state;
+    double n3[3];
+    const int m = lm.nbb_m[slot];
+    if (m == -2) {
+        const double *pa = lm.plane_a + slot * 4;
+        gates_ok = true; n3[0] = pa[0]; n3[1] = pa[1]; n3[2] = pa[2];
+        state = pa[3] < pr.reg_thr;
+    } else {
+        const PlaneOut p2 = m == -3 ? plane_lookup(pk, K, np) : plane_fit(NbCoords{lm.nbbx + slot, lm.nbbx_stride}, m, lm.nbb_last[slot], nx, ny, nz, pr);
+        gates_ok = p2.gates_ok; n3[0] = p2.n.x; n3[1] = p2.n.y; n3[2] = p2.n.z;
+        state = p2.gates_ok && p2.reg < pr.reg_thr;
+    }
+    lm_map_point(pk, K, f, kp, g[0], g[1], g[2]);
+    g[3] = nx; g[4] = ny; g[5] = nz;
+    g[6] = gates_ok ? n3[0] : 0.0; g[7] = gates_ok ? n3[1] : 0.0; g[8] = gates_ok ? n3[2] : 1.0;
+    type = state ? 2 : 1;
+    return true;
+}
+
 __global__ void __launch_bounds__(128)
 k_lm_plane_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm) {
     const int j = blockIdx.x % lm.sub, f = blockIdx.x / lm.sub;
     int nq;
     if (!lm_frame_active(wk, pr, f, nq)) return;
     const DevKf K = pk.kf[f];
-    const ScanView S = make_view(pk, K);
     for (int qi = j * blockDim.x + threadIdx.x; qi < nq; qi += lm.sub * blockDim.x) {
         const long long slot = K.mp_off + qi;
         if (lm.stage[slot] != 1) continue;
-        const uint32_t np = lm.nnb_pos[slot];
-        if (np == 0xffffffffu) continue;
+        if (lm.nnb_pos[slot] == 0xffffffffu) continue;
         const uint32_t ci = wk.q_corr[K.kp_off + qi];
         const uint32_t kp = wk.corr_kp[K.kp_off + ci];
-        const long long cs = slot;
-        const double nx = (double)S.px[np], ny = (double)S.py[np], nz = (double)S.pz[np];
-        bool gates_ok, state;
-        double n3[3];
-        const int m = lm.nbb_m[slot];
-        if (m == -2) {
-            const double *pa = lm.plane_a + slot * 4;
-            gates_ok = true; n3[0] = pa[0]; n3[1] = pa[1]; n3[2] = pa[2];
-            state = pa[3] < pr.reg_thr;
-        } else {
-            const PlaneOut p2 = m == -3 ? plane_lookup(pk, K, np) : plane_fit(NbCoords{lm.nbbx + slot, lm.nbbx_stride}, m, lm.nbb_last[slot], nx, ny, nz, pr);
-            gates_ok = p2.gates_ok; n3[0] = p2.n.x; n3[1] = p2.n.y; n3[2] = p2.n.z;
-            state = p2.gates_ok && p2.reg < pr.reg_thr;
-        }
-        double Mx, My, Mz;
-        lm_map_point(pk, K, f, kp, Mx, My, Mz);
-        double *g = lm.geo3d + cs * 9;
-        g[0] = Mx; g[1] = My; g[2] = Mz; g[3] = nx; g[4] = ny; g[5] = nz;
-        g[6] = gates_ok ? n3[0] : 0.0; g[7] = gates_ok ? n3[1] : 0.0; g[8] = gates_ok ? n3[2] : 1.0;
-        lm.type3d[cs] = state ? 2 : 1;  // Point2Plane_Factor : Point2Point_Factor (iba_local.cpp:300-309)
-        lm.flag3d[cs] = 1;
-        if (!state) atomicAdd(lm.d_counts + 2, 1);  // point-to-point blocks (integer count: order does not matter)
+        double g9[9];
+        int type;
+        if (!block3d_geometry(pk, pr, lm, slot, f, kp, g9, type)) continue;
+        double *g = lm.geo3d + slot * 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) g[i] = g9[i];
+        lm.type3d[slot] = (uint8_t)type;
+        lm.flag3d[slot] = 1;
+        atomicAdd(lm.d_counts + 1, 1);                    // 3-D/3-D blocks  (integer counts: the order does not matter)
+        if (type == 1) atomicAdd(lm.d_counts + 2, 1);     // point-to-point blocks among them
     }
 }
 
@@ -370,8 +387,11 @@ __device__ __forceinline__ void put_head(const BlockOut &o, long long blk, int t
     o.type[blk] = type; o.kf[blk] = kf; o.kp[blk] = (int32_t)kp; o.nres[blk] = nres;
 }
 
-// grid (chunks, B)
-template <bool WB>
+// grid (chunks, B).  The 3-D/3-D blocks are walked over ALL query slots (no compacted list: the work per block is light, and
+// the association then has no select on the way to the linearisation); FUSED3D: their geometry is formed on the spot from the
+// association's 1-NN instead of read from the frozen arrays (the step: k_lm_plane_b runs beside this kernel, not before it).
+// WB (stl_eval_blocks) numbers the blocks and therefore walks the compacted list.
+template <bool WB, bool FUSED3D>
 __global__ void __launch_bounds__(kLinThreads)
 k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand *__restrict__ cands, double *__restrict__ partial,
             int partial_stride, const BlockOut bo) {
@@ -392,7 +412,7 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
     const int stride = gridDim.x * kLinThreads, t0 = blockIdx.x * kLinThreads + threadIdx.x;
 
     // block counts live on the device (written by the selects of the association on this stream): no host round trip
-    const int n2d = lm.d_counts[0], n3d = lm.d_counts[1];
+    const int n2d = lm.d_counts[0];
     // ---- 3-D/2-D blocks: IBA_PlaneFactor (IBACalib2.hpp:152-184)
     for (int it = t0; it < n2d; it += stride) {
         const int slot = lm.idx2d[it];
@@ -456,9 +476,26 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
     }
 
     // ---- 3-D/3-D blocks: Point2Point_Factor / Point2Plane_Factor (IBACalib2.hpp:570-584,611-625)
-    for (int it = t0; it < n3d; it += stride) {
-        const int slot = lm.idx3d[it];
-        const double *g = lm.geo3d + (long long)slot * 9;
+    const long long n3 = WB ? (long long)lm.d_counts[1] : lm.max_blocks;  // compacted list (numbered blocks) / every query slot
+    for (long long it = t0; it < n3; it += stride) {
+        long long slot = it;
+        double gl[9];
+        int type = 0;
+        if (WB) {
+            slot = lm.idx3d[it];
+        } else if (FUSED3D) {
+            if (lm.stage[slot] != 1) continue;
+            if (!block3d_geometry(pk, pr, lm, slot, lm.slot_kf[slot], lm.slot_kp[slot], gl, type)) continue;
+        } else if (!lm.flag3d[slot]) {
+            continue;
+        }
+        if (WB || !FUSED3D) {
+            const double *gg = lm.geo3d + slot * 9;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) gl[i] = gg[i];
+            type = lm.type3d[slot];
+        }
+        const double *g = gl;
         const F7 Ms[3] = {cs7 * g[0], cs7 * g[1], cs7 * g[2]};  // MapPoint * s
         F7 M[3];
         mv3(cRlc, Ms, M);
@@ -466,7 +503,7 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
         for (int i = 0; i < 3; ++i) M[i] = M[i] + ctlc[i];
         const F7 d[3] = {M[0] - g[3], M[1] - g[4], M[2] - g[5]};
         double rho0, sr;
-        if (lm.type3d[slot] == 1) {
+        if (type == 1) {
             huber((d[0].a * d[0].a + d[1].a * d[1].a) + d[2].a * d[2].a, pr.delta3d, rho0, sr);
             accumulate(A, d[0], sr);
             accumulate(A, d[1], sr);
@@ -826,18 +863,22 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
         k_lm_knn_a<<<(unsigned)(pk.n_kf * lm.sub), kWarps * 32, 0, st>>>(pk, wk, pr, lm);
     k_lm_plane_a<<<(unsigned)(pk.n_kf * lm.sub), 128, 0, st>>>(pk, wk, pr, lm);
     TRY(cudaGetLastError());
+    {   // the 3-D/2-D blocks are complete: their dense list (the linearisation walks it) needs nothing of the 3-D search
+        cub::CountingInputIterator<int> it2(0);
+        size_t tb2 = lm.tmp_bytes;
+        TRY(cub::DeviceSelect::Flagged(lm.d_tmp, tb2, it2, lm.flag2d, lm.idx2d, lm.d_counts, (int)ns, st));
+    }
     }
     if (part == 1) return cudaSuccess;
     if (!nn_folded) k_lm_knn_b<<<(unsigned)(pk.n_kf * lm.sub), kWarps * 32, 0, st>>>(pk, wk, pr, lm, nn_hint, nn_g2);  // else K2a has filled nnb_pos / nbb_m
     k_lm_plane_b<<<(unsigned)(pk.n_kf * lm.sub), 128, 0, st>>>(pk, wk, pr, lm);
     TRY(cudaGetLastError());
     cub::CountingInputIterator<int> it(0);
-    size_t tb = lm.tmp_bytes;
-    TRY(cub::DeviceSelect::Flagged(lm.d_tmp, tb, it, lm.flag2d, lm.idx2d, lm.d_counts, (int)ns, st));
-    tb = lm.tmp_bytes;
-    TRY(cub::DeviceSelect::Flagged(lm.d_tmp, tb, it, lm.flag3d, lm.idx3d, lm.d_counts + 1, (int)ns, st));
+    // the 3-D/3-D blocks are counted by k_lm_plane_b and walked slot by slot by the linearisation: their dense list is only
+    // built for stl_eval_blocks (lm_compact3d)
+    lm.idx3d_valid = false;
     if (pr.use_gpr) {
-        tb = lm.tmp_bytes;
+        size_t tb = lm.tmp_bytes;
         TRY(cub::DeviceSelect::Flagged(lm.d_tmp, tb, it, lm.flagG, lm.idxG, lm.d_counts + 3, (int)ns, st));
     }
     TRY(cudaGetLastError());
@@ -849,6 +890,17 @@ cudaError_t lm_associate(const DevPack &pk, const DevWork &wk, const DevParams &
     lm.use_gpr = pr.use_gpr != 0;
     lm.ready = true;
     return cudaSuccess;
+}
+
+// Dense list of the 3-D/3-D blocks (slot order), for the numbered walk of stl_eval_blocks.
+cudaError_t lm_compact3d(const DevPack &pk, LmState &lm, cudaStream_t st) {
+    if (lm.idx3d_valid) return cudaSuccess;
+    const long long ns = pk.n_mp_total > 0 ? pk.n_mp_total : 1;
+    cub::CountingInputIterator<int> it(0);
+    size_t tb = lm.tmp_bytes;
+    const cudaError_t e = cub::DeviceSelect::Flagged(lm.d_tmp, tb, it, lm.flag3d, lm.idx3d, lm.d_counts + 1, (int)ns, st);
+    if (e == cudaSuccess) lm.idx3d_valid = true;
+    return e;
 }
 
 // The read-back of the block counts, for a caller that deferred it (lm_associate with defer_counts) to get it out of the
@@ -1001,7 +1053,7 @@ cudaError_t lm_stage_candidates(LmState &lm, const double *x, int B, cudaStream_
 }
 
 cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
-                         const BlockOut *blocks, int out_stride, const P2pView *p2p, cudaEvent_t before_finish, bool cand_staged) {
+                         const BlockOut *blocks, int out_stride, const P2pView *p2p, cudaEvent_t before_finish, bool cand_staged, bool fused3d) {
     cudaError_t e;
 #define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
     if (!cand_staged) TRY(lm_stage_candidates(lm, x, B, st));
@@ -1026,8 +1078,14 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
         lm.partial_cap = need;
     }
     const BlockOut bo = blocks ? *blocks : BlockOut();
-    if (blocks) k_linearize<true><<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, bo);
-    else k_linearize<false><<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, bo);
+    if (blocks) {
+        TRY(lm_compact3d(pk, lm, st));
+        k_linearize<true, false><<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, bo);
+    } else if (fused3d) {
+        k_linearize<false, true><<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, bo);
+    } else {
+        k_linearize<false, false><<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, bo);
+    }
     TRY(cudaGetLastError());
     if (gchunks > 0) {
         if (blocks) k_linearize_gpr<true><<<dim3(gchunks, B), 32, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, chunks, bo);

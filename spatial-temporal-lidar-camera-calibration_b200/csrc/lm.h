@@ -31,7 +31,8 @@ struct LmState {
     long long nbbx_stride = 0;
     int *nbb_m = nullptr;         // [n_mp] (-2 = same point as the associated one)
     double *nbb_last = nullptr;
-    int *idx2d = nullptr, *idx3d = nullptr;  // [n_slots] dense slot lists
+    int *idx2d = nullptr, *idx3d = nullptr;  // [n_slots] dense slot lists (idx3d: on demand, lm_compact3d)
+    bool idx3d_valid = false;
     // IBA_GPRFactor blocks (use_gpr): flag + dense list by correspondence slot, neighbour list by map-point slot
     uint8_t *flagG = nullptr;
     int *idxG = nullptr, *slot_mp = nullptr;
@@ -82,7 +83,9 @@ struct BlockOut {
 // out_stride: doubles between the records of consecutive candidates in d_out (0 = STL_LIN_NSUMS)
 cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
                          const BlockOut *blocks = nullptr, int out_stride = 0, const P2pView *p2p = nullptr, cudaEvent_t before_finish = nullptr,
-                         bool cand_staged = false);
+                         bool cand_staged = false, bool fused3d = false);
+// fused3d: the 3-D/3-D blocks are formed from the association's 1-NN inside the kernel (k_lm_plane_b need not have run yet)
+cudaError_t lm_compact3d(const DevPack &pk, LmState &lm, cudaStream_t st);
 // cand_staged: the caller has already run lm_stage_candidates(lm, x, B, st) for exactly these x on this stream
 // before_finish (optional): event the finishing kernel waits for (the rest of the record it completes / exchanges)
 // waits for the last association and mirrors its block counts into lm.n2d / n3d / nG / n_blocks
