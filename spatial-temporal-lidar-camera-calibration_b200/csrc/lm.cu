@@ -243,8 +243,7 @@ k_lm_knn_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm, c
 // L4: ComputeLocalNormalSingleThre at the map point's neighbour (pointcloud.h:699-717,651-666) -> 3-D/3-D block.
 // Geometry of the 3-D/3-D block of query slot `slot` (keyframe f, keypoint kp): g = map point (camera frame, unscaled), its
 // nearest scan point, the plane normal there; type 1 = Point2Point_Factor, 2 = Point2Plane_Factor (iba_local.cpp:300-309).
-// False: the slot carries no such block.  Shared by k_lm_plane_b (which freezes it) and the fused step (which linearises the
-// block on the spot, from the same numbers).
+// False: the slot carries no such block.
 __device__ __forceinline__ bool block3d_geometry(const DevPack &pk, const DevParams &pr, const LmState &lm, long long slot, int f, uint32_t kp,
                                                  double g[9], int &type) {
     if (lm.stage[slot] != 1) return false;
@@ -388,10 +387,9 @@ __device__ __forceinline__ void put_head(const BlockOut &o, long long blk, int t
 }
 
 // grid (chunks, B).  The 3-D/3-D blocks are walked over ALL query slots (no compacted list: the work per block is light, and
-// the association then has no select on the way to the linearisation); FUSED3D: their geometry is formed on the spot from the
-// association's 1-NN instead of read from the frozen arrays (the step: k_lm_plane_b runs beside this kernel, not before it).
+// the association then has no select on the way to the linearisation).
 // WB (stl_eval_blocks) numbers the blocks and therefore walks the compacted list.
-template <bool WB, bool FUSED3D>
+template <bool WB>
 __global__ void __launch_bounds__(kLinThreads)
 k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand *__restrict__ cands, double *__restrict__ partial,
             int partial_stride, const BlockOut bo) {
@@ -479,23 +477,10 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
     const long long n3 = WB ? (long long)lm.d_counts[1] : lm.max_blocks;  // compacted list (numbered blocks) / every query slot
     for (long long it = t0; it < n3; it += stride) {
         long long slot = it;
-        double gl[9];
-        int type = 0;
-        if (WB) {
-            slot = lm.idx3d[it];
-        } else if (FUSED3D) {
-            if (lm.stage[slot] != 1) continue;
-            if (!block3d_geometry(pk, pr, lm, slot, lm.slot_kf[slot], lm.slot_kp[slot], gl, type)) continue;
-        } else if (!lm.flag3d[slot]) {
-            continue;
-        }
-        if (WB || !FUSED3D) {
-            const double *gg = lm.geo3d + slot * 9;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) gl[i] = gg[i];
-            type = lm.type3d[slot];
-        }
-        const double *g = gl;
+        if (WB) slot = lm.idx3d[it];
+        else if (!lm.flag3d[slot]) continue;
+        const double *g = lm.geo3d + slot * 9;
+        const int type = lm.type3d[slot];
         const F7 Ms[3] = {cs7 * g[0], cs7 * g[1], cs7 * g[2]};  // MapPoint * s
         F7 M[3];
         mv3(cRlc, Ms, M);
@@ -1053,7 +1038,7 @@ cudaError_t lm_stage_candidates(LmState &lm, const double *x, int B, cudaStream_
 }
 
 cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
-                         const BlockOut *blocks, int out_stride, const P2pView *p2p, cudaEvent_t before_finish, bool cand_staged, bool fused3d) {
+                         const BlockOut *blocks, int out_stride, const P2pView *p2p, cudaEvent_t before_finish, bool cand_staged) {
     cudaError_t e;
 #define TRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
     if (!cand_staged) TRY(lm_stage_candidates(lm, x, B, st));
@@ -1080,11 +1065,9 @@ cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, co
     const BlockOut bo = blocks ? *blocks : BlockOut();
     if (blocks) {
         TRY(lm_compact3d(pk, lm, st));
-        k_linearize<true, false><<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, bo);
-    } else if (fused3d) {
-        k_linearize<false, true><<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, bo);
+        k_linearize<true><<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, bo);
     } else {
-        k_linearize<false, false><<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, bo);
+        k_linearize<false><<<dim3(chunks, B), kLinThreads, 0, st>>>(pk, pr, lm, reinterpret_cast<const LmCand *>(lm.d_cand), lm.partial, stride, bo);
     }
     TRY(cudaGetLastError());
     if (gchunks > 0) {

@@ -83,8 +83,7 @@ struct BlockOut {
 // out_stride: doubles between the records of consecutive candidates in d_out (0 = STL_LIN_NSUMS)
 cudaError_t lm_linearize(const DevPack &pk, const DevParams &pr, LmState &lm, const double *x, int B, double *d_out, cudaStream_t st,
                          const BlockOut *blocks = nullptr, int out_stride = 0, const P2pView *p2p = nullptr, cudaEvent_t before_finish = nullptr,
-                         bool cand_staged = false, bool fused3d = false);
-// fused3d: the 3-D/3-D blocks are formed from the association's 1-NN inside the kernel (k_lm_plane_b need not have run yet)
+                         bool cand_staged = false);
 cudaError_t lm_compact3d(const DevPack &pk, LmState &lm, cudaStream_t st);
 // cand_staged: the caller has already run lm_stage_candidates(lm, x, B, st) for exactly these x on this stream
 // before_finish (optional): event the finishing kernel waits for (the rest of the record it completes / exchanges)
