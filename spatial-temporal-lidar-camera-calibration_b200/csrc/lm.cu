@@ -474,11 +474,43 @@ k_linearize(const DevPack pk, const DevParams pr, const LmState lm, const LmCand
     }
 
     // ---- 3-D/3-D blocks: Point2Point_Factor / Point2Plane_Factor (IBACalib2.hpp:570-584,611-625)
-    const long long n3 = WB ? (long long)lm.d_counts[1] : lm.max_blocks;  // compacted list (numbered blocks) / every query slot
-    for (long long it = t0; it < n3; it += stride) {
+    // WB: the compacted list (numbered blocks), one block per thread and round.  Otherwise every warp walks 32 consecutive query
+    // slots per round, queues the flagged ones in shared memory and evaluates 32 queued blocks at a time (the tail at the end): the
+    // lanes stay full although only half of the slots carry a block, and nothing outside this kernel has to compact the list.
+    // Which thread sums which block depends on the flags alone, never on the batch size.
+    const long long n3 = WB ? (long long)lm.d_counts[1] : lm.max_blocks;
+    __shared__ int q3[kLinThreads / 32][64];
+    const int lane3 = threadIdx.x & 31, warp3 = threadIdx.x >> 5;
+    int qlen = 0;                                                    // warp-uniform
+    long long base = (long long)blockIdx.x * kLinThreads + warp3 * 32;  // first slot of this warp's next round
+    for (long long it = t0;; it += stride) {
         long long slot = it;
-        if (WB) slot = lm.idx3d[it];
-        else if (!lm.flag3d[slot]) continue;
+        if (WB) {
+            if (it >= n3) break;
+            slot = lm.idx3d[it];
+        } else {
+            const bool more = base < n3;
+            if (more) {
+                const long long sl = base + lane3;
+                const bool on = sl < n3 && lm.flag3d[sl];
+                const unsigned mask = __ballot_sync(0xffffffffu, on);
+                if (on) q3[warp3][qlen + __popc(mask & ((1u << lane3) - 1))] = (int)sl;
+                qlen += __popc(mask);
+                base += stride;
+                __syncwarp();
+            }
+            if (qlen < 32 && more) continue;      // keep collecting
+            if (qlen == 0) break;                  // nothing left anywhere
+            const int take = qlen < 32 ? qlen : 32;
+            const int mine = lane3 < take ? q3[warp3][lane3] : -1;
+            const int rest = lane3 + 32 < qlen ? q3[warp3][lane3 + 32] : 0;
+            __syncwarp();
+            if (lane3 + 32 < qlen) q3[warp3][lane3] = rest;
+            qlen -= take;
+            __syncwarp();
+            if (mine < 0) continue;
+            slot = mine;
+        }
         const double *g = lm.geo3d + slot * 9;
         const int type = lm.type3d[slot];
         const F7 Ms[3] = {cs7 * g[0], cs7 * g[1], cs7 * g[2]};  // MapPoint * s
