@@ -277,6 +277,9 @@ k_lm_plane_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
     int nq;
     if (!lm_frame_active(wk, pr, f, nq)) return;
     const DevKf K = pk.kf[f];
+    __shared__ int cnt[2];  // blocks of this CTA: all, point-to-point (one pair of global atomics per CTA, not per block)
+    if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
+    __syncthreads();
     for (int qi = j * blockDim.x + threadIdx.x; qi < nq; qi += lm.sub * blockDim.x) {
         const long long slot = K.mp_off + qi;
         if (lm.stage[slot] != 1) continue;
@@ -291,9 +294,11 @@ k_lm_plane_b(const DevPack pk, const DevWork wk, const DevParams pr, LmState lm)
         for (int i = 0; i < 9; ++i) g[i] = g9[i];
         lm.type3d[slot] = (uint8_t)type;
         lm.flag3d[slot] = 1;
-        atomicAdd(lm.d_counts + 1, 1);                    // 3-D/3-D blocks  (integer counts: the order does not matter)
-        if (type == 1) atomicAdd(lm.d_counts + 2, 1);     // point-to-point blocks among them
+        atomicAdd(&cnt[0], 1);                    // 3-D/3-D blocks  (integer counts: the order does not matter)
+        if (type == 1) atomicAdd(&cnt[1], 1);     // point-to-point blocks among them
     }
+    __syncthreads();
+    if (threadIdx.x < 2 && cnt[threadIdx.x] > 0) atomicAdd(lm.d_counts + 1 + threadIdx.x, cnt[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------ K4b
