@@ -8,7 +8,8 @@
 //   hand-eye term                  src/examples/iba_global.cpp:264-276
 //   covisible re-projection term   src/examples/iba_global.cpp:291-328
 //
-// One CTA per (candidate, keyframe).  No index is ever built over the projected points (the
+// PERSISTENT: two CTAs per SM draw (keyframe, candidate) units from a global ticket; a unit is worked by one CTA from its
+// keypoint tables (ONE cp.async.bulk per keyframe, mbarrier completion) to its FrameRec.  No index is ever built over the projected points (the
 // reference rebuilds a KD-tree per candidate and keyframe): only points within max_pixel_dist
 // of a keypoint can become a correspondence, so the scan is STREAMED (SoA float4, 12 B/point)
 // through a float32 pre-cull against a shared-memory occupancy bitmap of the dilated keypoints.
@@ -16,8 +17,9 @@
 // from their bounding boxes without being loaded.  The ~2 % survivors are re-evaluated in the
 // reference's exact fp64 arithmetic against the keypoints of their 8 px grid cells (grid and
 // keypoints staged in shared memory) and min-reduced per keypoint with (distance, original
-// index) order — the KD-tree 1-NN + threshold whenever no exact distance tie exists.
-// Bound: HBM for the stream, latency for the exact part.
+// index) order — the KD-tree 1-NN + threshold whenever no exact distance tie exists.  A survivor is
+// recorded with its coordinates in an L2-resident per-CTA list, so nothing after the stream gathers
+// from the scan.  Bound: HBM for the stream, instruction latency for the survivor phases.
 #include <algorithm>
 #include <mutex>
 

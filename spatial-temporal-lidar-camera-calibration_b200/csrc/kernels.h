@@ -112,7 +112,7 @@ cudaError_t build_plane_index(const DevPack &pk, const DevKf *h_kf, int kf_begin
 constexpr int kK1SurvCap = 4096;   // survivors of the float32 pre-cull a (candidate, keyframe) unit may list
 constexpr int kK1MatchCap = 8192;  // (keypoint, point) matches a unit may record between the exact pass and the tie pass
 
-// ---- K1 (assoc2d.cu: one kernel; assoc2d_split.cu: stream / exact / correspondence kernels, the default) ----------
+// ---- K1 (assoc2d.cu: one persistent kernel, the default; assoc2d_split.cu: stream / exact / correspondence kernels, STL_K1_SPLIT=1) ----
 size_t assoc2d_smem_bytes(int max_kp, int max_tab_bytes, int max_groups);
 cudaError_t assoc2d_configure(size_t smem);
 // with_terms = 0: correspondences only (the association pass of the LM path needs neither the covisible

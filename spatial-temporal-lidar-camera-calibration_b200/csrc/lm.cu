@@ -38,7 +38,8 @@ constexpr int kLinThreads = 128;
 
 // ------------------------------------------------------------------ K4a (four small kernels)
 // All four walk the correspondences that carry a map point (the query list K1 wrote), keyframe by
-// keyframe; list slot = mp_off[f] + qi.  Traversals are warp-per-item, plane fits thread-per-item.
+// keyframe; list slot = block slot = mp_off[f] + qi.  Traversals are warp-per-item, plane fits thread-per-item.
+// With the plane index only k_lm_plane_a and k_lm_plane_b run (and inside stl_step_batch K2a answers k_lm_knn_b's question).
 
 __device__ __forceinline__ bool lm_frame_active(const DevWork &wk, const DevParams &pr, int f, int &nq) {
     nq = wk.n_q[f];
