@@ -397,6 +397,7 @@ def main():
     stats = ctx.stage_stats()
     ctx.set_profiling(False)
     wc = ctx.work_counters()
+    exch = ctx.comm_stats() if (by_kf and world > 1) else {}
     launches = int(wc["launches"] - launches0)
     rec = d_out.cpu().numpy()                  # [steps, B, W]
 
@@ -486,10 +487,12 @@ def main():
             "scaling": "strong" if (by_kf or world == 1) else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args),
             "layout": {
-                "sharding": ("keyframes sharded over the ranks + one NCCL fp64 all-reduce of the [B,%d] record per step, issued by the library" % W
+                "sharding": (("keyframes sharded over the ranks + ONE fp64 sum of the [B,%d] record per step, issued by the library: " % W) +
+                             ("inside the finishing kernel over NVLink peer memory (cudaIpc)" if exch.get("p2p") else "ncclAllReduce on the compute stream")
                              if by_kf else ("candidates (pack replicated per GPU, no collective)" if world > 1 else "single GPU")),
                 "keyframes_this_rank": int(pack.n_kf), "points_this_rank": int(n_pts), "keypoints_this_rank": int(n_kp),
                 "plane_index": bool(params.plane_index), "candidates_per_step_all_ranks": units_per_step,
+                "exchange": exch,
             },
             "setup": {"upload_s": round(t_upload, 3), "k0_index_build_device_ms": round(build_ms, 1), "plane_index_build_ms": round(pidx_ms, 1),
                       "synth_s": round(t_gen, 2), "hbm_bytes_resident": int(mem_used)},

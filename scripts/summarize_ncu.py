@@ -85,7 +85,7 @@ if d1:
     print("k1 traffic", tr)
 full("k2_full", f"{tag}_k2_knn.txt")
 full("k2b_full", f"{tag}_k2_plane.txt")
-full("lm_full", f"{tag}_lm_knn.txt")
+full("lm_full", f"{tag}_lm_plane_b.txt" if tag >= "r02" else f"{tag}_lm_knn.txt")
 full("lin_full", f"{tag}_linearize.txt")
 full("k0_full", f"{tag}_k0_kd_refine.txt")
 full("kidx_full", f"{tag}_k0_index_knn.txt")
