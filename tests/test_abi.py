@@ -88,3 +88,22 @@ def test_product_never_touches_the_oracle():
     import subprocess
     out = subprocess.run(["ldd", os.path.join(pdir, "libstlcalib.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_k1_tables_arrive_by_bulk_copy(pkg):
+    """The association kernel's per-keyframe tables are brought into shared memory by ONE cp.async.bulk with mbarrier completion
+    and its covisible pixels are asked into L2 by cp.async.bulk.prefetch.L2: the sm_100a SASS of the built library must hold the
+    bulk-copy unit's instructions (UBLKCP / UBLKPF) and the transaction-count barrier (SYNCS).  No GPU needed: cuobjdump reads
+    the embedded cubin."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    so = os.path.join(ROOT, "spatial-temporal-lidar-camera-calibration_b200", "libstlcalib.so")
+    pkg._abi.load_calib()
+    sass = subprocess.run(["cuobjdump", "-sass", "-arch", "sm_100a", so], capture_output=True, text=True).stdout
+    k1 = sass[sass.find("k_assoc2d"):]
+    k1 = k1[:k1.find("Function :", 10)] if k1.find("Function :", 10) > 0 else k1
+    assert "UBLKCP.S.G" in k1, "K1 lost its bulk copy global -> shared"
+    assert "UBLKPF.L2" in k1, "K1 lost its bulk L2 prefetch"
+    assert "SYNCS.ARRIVE.TRANS64" in k1 and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in k1, "K1 lost its mbarrier"
